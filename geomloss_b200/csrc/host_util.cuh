@@ -1,0 +1,30 @@
+// b200ot — host-side helpers shared by the translation units of libb200ot.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "b200ot.h"
+
+namespace b200ot {
+
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int64_t round_up64(int64_t a, int64_t b) { return ceil_div64(a, b) * b; }
+
+// Last CUDA error text seen by any entry point (process-wide, best effort; for diagnostics only).
+void set_last_cuda_error(cudaError_t e, const char* where);
+
+// SM count of the current device, cached per device ordinal.
+int num_sms();
+
+#define B200OT_STR2(x) #x
+#define B200OT_STR(x) B200OT_STR2(x)
+#define B200OT_CUDA_TRY(expr)                                                         \
+  do {                                                                                \
+    cudaError_t e__ = (expr);                                                         \
+    if (e__ != cudaSuccess) {                                                         \
+      ::b200ot::set_last_cuda_error(e__, __FILE__ ":" B200OT_STR(__LINE__));          \
+      return B200OT_ECUDA;                                                            \
+    }                                                                                 \
+  } while (0)
+
+}  // namespace b200ot

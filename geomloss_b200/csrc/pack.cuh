@@ -1,0 +1,49 @@
+// b200ot — column packing kernel (shared by the softmin and kernel-conv translation units).
+#pragma once
+#include "common.cuh"
+
+namespace b200ot {
+
+// -------------------------------------------------------------------------------------------------
+// pack: (M, D) columns + per-column scalars -> colpack tiles
+//   mode bit 0 (DIRECT): store -scale*(y - c) and a plain additive term
+//   otherwise          : store +scale*(y - c) and fold -|Y|^2/2 into the additive term
+//   slot D      = h_scale * (h_a + h_scale_b * h_b)  [+ fold]   (softmin)  — or the fold alone when h_a is null
+//   slot D+1    = w (kernel conv weight) when extra == 2
+// Padding columns (j >= M): coordinates 0, additive term -inf (softmin) / weight 0 (conv).
+// -------------------------------------------------------------------------------------------------
+static __global__ void pack_cols_kernel(const float* __restrict__ y, const float* __restrict__ h_a,
+                                 const float* __restrict__ h_b, float h_scale_b, float h_scale,
+                                 const float* __restrict__ w, const float* __restrict__ center, float scale,
+                                 int direct, int D, int extra, int nf2, int64_t M, int64_t Mpad,
+                                 float* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= Mpad) return;
+  float* pk = out + (j >> 1) * (int64_t)(nf2 * 2) + (j & 1);
+  if (j >= M) {
+    for (int k = 0; k < nf2; ++k) pk[2 * k] = 0.f;
+    if (h_a != nullptr) pk[2 * D] = -INFINITY;
+    return;
+  }
+  float sq = 0.f;
+  for (int k = 0; k < D; ++k) {
+    const float c = center ? center[k] : 0.f;
+    const float v = scale * (y[j * D + k] - c);
+    sq = fmaf(v, v, sq);
+    pk[2 * k] = direct ? -v : v;
+  }
+  float add = direct ? 0.f : -0.5f * sq;
+  int slot = D;
+  if (h_a != nullptr) {
+    float h = h_a[j];
+    if (h_b != nullptr) h = fmaf(h_scale_b, h_b[j], h);
+    add = fmaf(h_scale, h, add);
+    pk[2 * slot++] = add;
+  } else if (!direct) {
+    pk[2 * slot++] = add;
+  }
+  if (w != nullptr) pk[2 * slot++] = w[j];
+  for (; slot < nf2; ++slot) pk[2 * slot] = 0.f;
+}
+
+}  // namespace b200ot

@@ -1,0 +1,303 @@
+"""CPU oracle for the Sinkhorn / kernel-MMD hot path of jeanfeydy/geomloss @ 00e493f (v0.3.1).
+
+TEST INFRASTRUCTURE ONLY.  This file is a from-scratch restatement, in plain torch on the CPU, of the
+algorithm the reference's ``backend="tensorized"`` path runs.  It exists so that the CUDA engine in
+``geomloss_b200`` can be checked on the GPU box, where ``/root/reference`` does not exist.  Only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference`` legs may
+import it; the product package never does (``tests/test_no_oracle_in_product.py`` enforces this).
+
+Parity status: PINNED.  ``tests/golden/make_golden.py`` imports the real reference from
+``/root/reference/src`` in the build container, runs it on seeded inputs and stores its outputs in
+``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks every function below against those
+fixtures (the reference itself ships no test for this path — SURVEY.md section 4).
+
+Reference map (all paths under ``src/geomloss/_legacy/``):
+    sqdist / dist            utils.py:26-61          (|x|^2 - 2 x.y + |y|^2 ; sqrt(clamp_min(., 1e-8)))
+    cost_matrix              sinkhorn_samples.py:26-29   (p=1: dist, p=2: sqdist / 2)
+    softmin_dense            sinkhorn_samples.py:32-71
+    log_weights              sinkhorn_divergence.py:61-65
+    damping                  sinkhorn_divergence.py:56-58
+    max_diameter             sinkhorn_divergence.py:96-112
+    epsilon_schedule         sinkhorn_divergence.py:115-151
+    scaling_parameters       sinkhorn_divergence.py:154-163
+    sinkhorn_loop            sinkhorn_divergence.py:258-628  (single scale: jumps == [])
+    sinkhorn_value           sinkhorn_divergence.py:171-250
+    sinkhorn_dense           sinkhorn_samples.py:74-221
+    kernel_matrix / mmd_dense  kernel_samples.py:43-146
+    samples_loss             samples_loss.py:211-335  (argument handling + output shapes)
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+# ------------------------------------------------------------------------------------------------
+# costs                                                                        utils.py:26-61
+# ------------------------------------------------------------------------------------------------
+
+
+def sqdist(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """|x_i - y_j|^2 through the norm expansion, for (N,D),(M,D) or batched (B,N,D),(B,M,D)."""
+    xx = (x * x).sum(-1).unsqueeze(-1)
+    yy = (y * y).sum(-1).unsqueeze(-2)
+    return xx - 2.0 * torch.matmul(x, y.transpose(-1, -2)) + yy
+
+
+def dist(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    return sqdist(x, y).clamp_min(1e-8).sqrt()
+
+
+def cost_matrix(x, y, p: int):
+    """C(x_i, y_j) = |x_i - y_j|^p / p                                   sinkhorn_samples.py:26-29"""
+    if p == 2:
+        return sqdist(x, y) / 2
+    if p == 1:
+        return dist(x, y)
+    raise KeyError(p)
+
+
+# ------------------------------------------------------------------------------------------------
+# softmin                                                              sinkhorn_samples.py:32-71
+# ------------------------------------------------------------------------------------------------
+
+
+def softmin_dense(eps: float, C: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
+    """-eps * logsumexp_j(h_j - C_ij / eps) for C:(B,N,M), h:(B,M) -> (B,N)."""
+    nb = C.shape[0]
+    return (-eps * torch.logsumexp(h.reshape(nb, 1, -1) - C / eps, dim=2)).reshape(nb, -1)
+
+
+def softmin_points(eps: float, x: torch.Tensor, y: torch.Tensor, h: torch.Tensor, p: int = 2,
+                   row_block: int = 2048) -> torch.Tensor:
+    """Same operator on point clouds x:(N,D), y:(M,D), h:(M,) -> (N,), evaluated in row blocks so that
+    it reaches N ~ 1e5 on a CPU (semantics of softmin_online, sinkhorn_samples.py:337-346)."""
+    out = torch.empty(x.shape[0], dtype=x.dtype)
+    for s in range(0, x.shape[0], row_block):
+        C = cost_matrix(x[s:s + row_block], y, p)
+        out[s:s + row_block] = -eps * torch.logsumexp(h.reshape(1, -1) - C / eps, dim=1)
+    return out
+
+
+def softmin_grad_rows(eps: float, x, y, h, grad_out, p: int = 2):
+    """d/dx of <grad_out, softmin_points(eps, x, y, h)> with y and h held constant — the only gradient
+    the reference's autograd contract carries (sinkhorn_samples.py:179-185, sinkhorn_divergence.py:612-623)."""
+    xr = x.detach().clone().requires_grad_(True)
+    C = cost_matrix(xr, y.detach(), p)
+    f = -eps * torch.logsumexp(h.detach().reshape(1, -1) - C / eps, dim=1)
+    (g,) = torch.autograd.grad((f * grad_out).sum(), xr)
+    return g
+
+
+# ------------------------------------------------------------------------------------------------
+# schedule and scalars                                          sinkhorn_divergence.py:56-163
+# ------------------------------------------------------------------------------------------------
+
+
+def damping(eps: float, rho):
+    return 1 if rho is None else 1 / (1 + eps / rho)
+
+
+def log_weights(a: torch.Tensor) -> torch.Tensor:
+    out = a.log()
+    out[a <= 0] = -100000
+    return out
+
+
+def max_diameter(x: torch.Tensor, y: torch.Tensor) -> float:
+    lo = torch.minimum(x.min(0).values, y.min(0).values)
+    hi = torch.maximum(x.max(0).values, y.max(0).values)
+    return (hi - lo).norm().item()
+
+
+def epsilon_schedule(p, diameter, blur, scaling):
+    """[diam^p] + exp(arange(p log diam, p log blur, p log scaling)) + [blur^p]; the head is duplicated
+    on purpose (the arange starts at p log diam)."""
+    ladder = np.arange(p * np.log(diameter), p * np.log(blur), p * np.log(scaling))
+    return [diameter**p] + [np.exp(e) for e in ladder] + [blur**p]
+
+
+def scaling_parameters(x, y, p, blur, reach, diameter, scaling):
+    if diameter is None:
+        d = x.shape[-1]
+        diameter = max_diameter(x.reshape(-1, d), y.reshape(-1, d))
+    rho = None if reach is None else reach**p
+    return diameter, blur**p, epsilon_schedule(p, diameter, blur, scaling), rho
+
+
+# ------------------------------------------------------------------------------------------------
+# the loop                                                      sinkhorn_divergence.py:258-628
+# ------------------------------------------------------------------------------------------------
+
+
+def sinkhorn_loop(softmin, a_log, b_log, C_xx, C_yy, C_xy, C_yx, eps_list, rho, debias=True):
+    """Single-scale symmetric Sinkhorn with eps-scaling.
+
+    All iterations run without autograd; one last, non-averaged update with grad enabled and detached
+    right-hand sides carries the gradient (envelope theorem).  Returns (f_aa, g_bb, g_ab, f_ba).
+    """
+    with torch.no_grad():
+        eps = eps_list[0]
+        lam = damping(eps, rho)
+        g_ab = lam * softmin(eps, C_yx, a_log)
+        f_ba = lam * softmin(eps, C_xy, b_log)
+        if debias:
+            f_aa = lam * softmin(eps, C_xx, a_log)
+            g_bb = lam * softmin(eps, C_yy, b_log)
+        for eps in eps_list:
+            lam = damping(eps, rho)
+            ft_ba = lam * softmin(eps, C_xy, b_log + g_ab / eps)
+            gt_ab = lam * softmin(eps, C_yx, a_log + f_ba / eps)
+            if debias:
+                ft_aa = lam * softmin(eps, C_xx, a_log + f_aa / eps)
+                gt_bb = lam * softmin(eps, C_yy, b_log + g_bb / eps)
+            f_ba, g_ab = 0.5 * (f_ba + ft_ba), 0.5 * (g_ab + gt_ab)
+            if debias:
+                f_aa, g_bb = 0.5 * (f_aa + ft_aa), 0.5 * (g_bb + gt_bb)
+    with torch.enable_grad():
+        new_f_ba = lam * softmin(eps, C_xy, (b_log + g_ab / eps).detach())
+        new_g_ab = lam * softmin(eps, C_yx, (a_log + f_ba / eps).detach())
+        f_ba, g_ab = new_f_ba, new_g_ab
+        if debias:
+            f_aa = lam * softmin(eps, C_xx, (a_log + f_aa / eps).detach())
+            g_bb = lam * softmin(eps, C_yy, (b_log + g_bb / eps).detach())
+    if debias:
+        return f_aa, g_bb, g_ab, f_ba
+    return None, None, g_ab, f_ba
+
+
+def _dot(a, f):
+    nb = a.shape[0]
+    return (a.reshape(nb, -1) * f.reshape(nb, -1)).sum(1)
+
+
+def sinkhorn_value(eps, rho, a, b, f_aa, g_bb, g_ab, f_ba, debias=True, potentials=False):
+    """Loss value (or dual potentials) from the four potentials.   sinkhorn_divergence.py:171-250
+
+    NB the unbalanced weight is (rho + eps/2) in forward AND backward: the reference's
+    UnbalancedWeight.backward is never invoked by autograd."""
+    if potentials:
+        return (f_ba - f_aa, g_ab - g_bb) if debias else (f_ba, g_ab)
+    if rho is None:
+        if debias:
+            return _dot(a, f_ba - f_aa) + _dot(b, g_ab - g_bb)
+        return _dot(a, f_ba) + _dot(b, g_ab)
+    w = rho + eps / 2
+    if debias:
+        return _dot(a, w * ((-f_aa / rho).exp() - (-f_ba / rho).exp())) + _dot(
+            b, w * ((-g_bb / rho).exp() - (-g_ab / rho).exp()))
+    return _dot(a, w * (1 - (-f_ba / rho).exp())) + _dot(b, w * (1 - (-g_ab / rho).exp()))
+
+
+def sinkhorn_dense(a, x, b, y, p=2, blur=0.05, reach=None, diameter=None, scaling=0.5, debias=True,
+                   potentials=False):
+    """Batched dense Sinkhorn divergence: a:(B,N) x:(B,N,D) b:(B,M) y:(B,M,D).  sinkhorn_samples.py:74-221"""
+    C_xy = cost_matrix(x, y.detach(), p)
+    C_yx = cost_matrix(y, x.detach(), p)
+    C_xx = cost_matrix(x, x.detach(), p) if debias else None
+    C_yy = cost_matrix(y, y.detach(), p) if debias else None
+    diameter, eps, eps_list, rho = scaling_parameters(x, y, p, blur, reach, diameter, scaling)
+    f_aa, g_bb, g_ab, f_ba = sinkhorn_loop(softmin_dense, log_weights(a), log_weights(b), C_xx, C_yy, C_xy, C_yx,
+                                           eps_list, rho, debias=debias)
+    return sinkhorn_value(eps, rho, a, b, f_aa, g_bb, g_ab, f_ba, debias=debias, potentials=potentials)
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel MMD                                                          kernel_samples.py:43-146
+# ------------------------------------------------------------------------------------------------
+
+
+class _TwiceGrad(torch.autograd.Function):
+    """Identity whose backward doubles the gradient (compensates the detached right-hand side of the
+    symmetric terms).                                                      kernel_samples.py:43-54"""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t
+
+    @staticmethod
+    def backward(ctx, g):
+        return 2 * g
+
+
+def kernel_matrix(name: str, x, y, blur):
+    if name == "gaussian":
+        return (-sqdist(x / blur, y / blur) / 2).exp()
+    if name == "laplacian":
+        return (-dist(x / blur, y / blur)).exp()
+    if name == "energy":
+        return -dist(x, y)
+    raise KeyError(name)
+
+
+def mmd_dense(a, x, b, y, name, blur=0.05, potentials=False):
+    """Kernel norm 1/2 |a - b|_k^2 on batched inputs.                    kernel_samples.py:92-146"""
+    dg = _TwiceGrad.apply
+    K_xx = kernel_matrix(name, dg(x), x.detach(), blur)
+    K_yy = kernel_matrix(name, dg(y), y.detach(), blur)
+    K_xy = kernel_matrix(name, x, y, blur)
+    a_x = (K_xx @ a.detach().unsqueeze(-1)).squeeze(-1)
+    b_y = (K_yy @ b.detach().unsqueeze(-1)).squeeze(-1)
+    b_x = (K_xy @ b.unsqueeze(-1)).squeeze(-1)
+    if potentials:
+        a_y = (K_xy.transpose(1, 2) @ a.unsqueeze(-1)).squeeze(-1)
+        return a_x - b_x, b_y - a_y
+    return 0.5 * _dot(dg(a), a_x) + 0.5 * _dot(dg(b), b_y) - _dot(a, b_x)
+
+
+def kernel_conv_points(name: str, x, y, w, blur, row_block: int = 2048):
+    """out_i = sum_j k(x_i, y_j) w_j on unbatched clouds, in row blocks."""
+    out = torch.empty(x.shape[0], dtype=x.dtype)
+    for s in range(0, x.shape[0], row_block):
+        out[s:s + row_block] = kernel_matrix(name, x[s:s + row_block], y, blur) @ w
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# front end                                                           samples_loss.py:211-335
+# ------------------------------------------------------------------------------------------------
+
+
+def samples_loss(*args, loss="sinkhorn", p=2, blur=0.05, reach=None, diameter=None, scaling=0.5, debias=True,
+                 potentials=False):
+    """The reference's SamplesLoss(..., backend="tensorized")(*args) for 2 or 4 positional tensors."""
+    if len(args) == 2:
+        x, y = args
+
+        def uniform(t):
+            n = t.shape[-2]
+            return torch.ones(t.shape[:-1]).type_as(t) / n
+
+        a, b = uniform(x), uniform(y)
+    elif len(args) == 4:
+        a, x, b, y = args
+    else:
+        raise ValueError("expected (x, y) or (a, x, b, y)")
+    unbatched = x.dim() == 2
+    if unbatched:
+        a, x, b, y = a.reshape(1, -1), x.unsqueeze(0), b.reshape(1, -1), y.unsqueeze(0)
+    elif a.dim() == 3:
+        a, b = a.squeeze(-1), b.squeeze(-1)
+    if loss == "sinkhorn":
+        out = sinkhorn_dense(a, x, b, y, p=p, blur=blur, reach=reach, diameter=diameter, scaling=scaling,
+                             debias=debias, potentials=potentials)
+    elif loss in ("gaussian", "laplacian", "energy"):
+        out = mmd_dense(a, x, b, y, loss, blur=blur, potentials=potentials)
+    else:
+        raise KeyError(loss)
+    if potentials:
+        F, G = out
+        return F.reshape(a.shape), G.reshape(b.shape)  # (1,N) for unbatched input, like the reference
+    return out[0] if unbatched else out
+
+
+def n_softmins(n_eps: int, debias: bool = True) -> int:
+    """Softmin evaluations per loss call: init + one per eps + the final extrapolation."""
+    return (4 if debias else 2) * (n_eps + 2)
+
+
+def pair_interactions(n_eps: int, N: int, M: int, debias: bool = True) -> float:
+    """pair-interactions evaluated by one loss call."""
+    per_iter = 2.0 * N * M + (float(N) * N + float(M) * M if debias else 0.0)
+    return (n_eps + 2) * per_iter
