@@ -86,9 +86,9 @@ using namespace b200ot;
 
 extern "C" {
 
-int b200ot_version(void) { return B200OT_VERSION; }
+B200OT_API int b200ot_version(void) { return B200OT_VERSION; }
 
-const char* b200ot_strerror(int code) {
+B200OT_API const char* b200ot_strerror(int code) {
   switch (code) {
     case B200OT_OK: return "ok";
     case B200OT_EINVAL: return "invalid argument";
@@ -99,9 +99,9 @@ const char* b200ot_strerror(int code) {
   }
 }
 
-const char* b200ot_last_cuda_error(void) { return g_last_cuda_error; }
+B200OT_API const char* b200ot_last_cuda_error(void) { return g_last_cuda_error; }
 
-int b200ot_ubench(int32_t which, int32_t iters, int32_t blocks, float* sink, int32_t* ops_per_thread_iter,
+B200OT_API int b200ot_ubench(int32_t which, int32_t iters, int32_t blocks, float* sink, int32_t* ops_per_thread_iter,
                   void* stream) {
   if (!sink || iters <= 0 || blocks <= 0) return B200OT_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;

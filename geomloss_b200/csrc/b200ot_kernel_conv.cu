@@ -1,0 +1,197 @@
+// b200ot — kernel convolutions  out_i = sum_j k(x_i, y_j) w_j  and their row gradients.
+// Reference semantics: the matvecs of kernel_loss (src/geomloss/_legacy/kernel_samples.py:116-137) with
+//   gaussian  k = exp(-|x/s - y/s|^2 / 2)                    (kernel_samples.py:62-68)
+//   laplacian k = exp(-sqrt(max(|x/s - y/s|^2, 1e-8)))       (kernel_samples.py:71-77, utils.py:56-61)
+//   energy    k = -sqrt(max(|x - y|^2, 1e-8))                (kernel_samples.py:80-82)
+// evaluated on the fly (never as an N x M matrix) by rowsum_partial_kernel.
+#include "b200ot.h"
+#include "host_util.cuh"
+#include "pack.cuh"
+#include "plan.cuh"
+#include "rowsum.cuh"
+
+namespace b200ot {
+
+struct ConvScales {
+  float scale;   // coordinate scale
+  float clampq;  // clamp on the scaled squared distance
+  int direct;
+  int extra;
+};
+
+static ConvScales conv_scales(int kind, float blur) {
+  ConvScales c;
+  if (kind == B200OT_KERNEL_GAUSSIAN) {
+    c.scale = sqrtf(kLog2e) / blur;  // 2^(-|X-Y|^2/2) = exp(-|x-y|^2 / (2 blur^2))
+    c.clampq = 0.f;
+    c.direct = 0;
+    c.extra = 2;
+  } else if (kind == B200OT_KERNEL_LAPLACIAN) {
+    c.scale = kLog2e / blur;  // 2^(-|X-Y|) = exp(-|x-y| / blur)
+    c.clampq = kLog2e * kLog2e * 1e-8f;
+    c.direct = 1;
+    c.extra = 1;
+  } else {
+    c.scale = 1.f;
+    c.clampq = 1e-8f;
+    c.direct = 1;
+    c.extra = 1;
+  }
+  return c;
+}
+
+__global__ void conv_fwd_finalize_kernel(const float* __restrict__ part, int n_split, float sign,
+                                         float* __restrict__ out, int64_t N) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float a = 0.f;
+  for (int s = 0; s < n_split; ++s) a += part[(int64_t)s * N + i];
+  out[i] = sign * a;
+}
+
+// gaussian: part (n_split, N, D+1): [0] = sum W e, [1+k] = sum W e Y_k   -> go (accY - X acc0) / (scale blur^2)
+// laplacian / energy: part (n_split, N, D): sum W e u_k                    -> -go acc / blur   (energy: -go acc)
+__global__ void conv_bwd_finalize_kernel(const float* __restrict__ part, int n_split, const float* __restrict__ x,
+                                         const float* __restrict__ center, const float* __restrict__ grad_out,
+                                         float* __restrict__ grad_x, int64_t N, int D, int kind, float scale,
+                                         float coef) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float go = grad_out[i];
+  if (kind == B200OT_KERNEL_GAUSSIAN) {
+    const int na = D + 1;
+    float a0 = 0.f;
+    for (int s = 0; s < n_split; ++s) a0 += part[((int64_t)s * N + i) * na];
+    for (int k = 0; k < D; ++k) {
+      float a = 0.f;
+      for (int s = 0; s < n_split; ++s) a += part[((int64_t)s * N + i) * na + 1 + k];
+      const float c = center ? center[k] : 0.f;
+      const float X = scale * (x[i * D + k] - c);
+      grad_x[i * D + k] = go * coef * (a - X * a0);
+    }
+  } else {
+    for (int k = 0; k < D; ++k) {
+      float a = 0.f;
+      for (int s = 0; s < n_split; ++s) a += part[((int64_t)s * N + i) * D + k];
+      grad_x[i * D + k] = go * coef * a;
+    }
+  }
+}
+
+template <int MODE, int D>
+static int launch_rowsum(const ReducePlan& pl, cudaStream_t st, const float* x, const float* center, float scale,
+                         float clampq, const float* cols, float* part, int64_t N) {
+  if (pl.small) {
+    using C = RowSumCfg<MODE, D, kSmallR, kSmallNT, kSmallTJ, 3, 4>;
+    return launch_reduce<C>(rowsum_partial_kernel<C>, pl, st, x, center, scale, clampq, cols,
+                            (const float*)nullptr, part, N, pl.ntiles, pl.tiles_per_split);
+  }
+  using C = RowSumCfg<MODE, D, kBigR, kBigNT, kBigTJ, 3, 2>;
+  return launch_reduce<C>(rowsum_partial_kernel<C>, pl, st, x, center, scale, clampq, cols, (const float*)nullptr,
+                          part, N, pl.ntiles, pl.tiles_per_split);
+}
+
+template <int MODE>
+static int launch_rowsum_d(int D, const ReducePlan& pl, cudaStream_t st, const float* x, const float* center,
+                           float scale, float clampq, const float* cols, float* part, int64_t N) {
+  switch (D) {
+    case 1: return launch_rowsum<MODE, 1>(pl, st, x, center, scale, clampq, cols, part, N);
+    case 2: return launch_rowsum<MODE, 2>(pl, st, x, center, scale, clampq, cols, part, N);
+    case 3: return launch_rowsum<MODE, 3>(pl, st, x, center, scale, clampq, cols, part, N);
+    default: return B200OT_EINVAL;
+  }
+}
+
+static int conv_pack(const float* y, const float* w, const float* center, int64_t M, int D, const ConvScales& cs,
+                     float* cols, cudaStream_t st) {
+  const int nf2 = colfmt_nf2(D, cs.extra);
+  const int64_t mpad = round_up64(M, kPackPad);
+  const int threads = 256;
+  pack_cols_kernel<<<(unsigned)ceil_div64(mpad, threads), threads, 0, st>>>(
+      y, nullptr, nullptr, 0.f, 0.f, w, center, cs.scale, cs.direct, D, nf2, M, mpad, cols);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  return B200OT_OK;
+}
+
+}  // namespace b200ot
+
+using namespace b200ot;
+
+extern "C" {
+
+B200OT_API int64_t b200ot_kernel_conv_scratch_bytes(int64_t N, int64_t M, int32_t D) {
+  if (N <= 0 || M <= 0 || D <= 0) return 0;
+  const ReducePlan pl = make_plan(N, M);
+  const int64_t cols = b200ot_packed_cols_floats(M, D, 2) * 4;
+  const int64_t part = (int64_t)pl.n_split * N * 4 * (D + 1);
+  return round_up64(cols, 256) + round_up64(part, 256);
+}
+
+B200OT_API int b200ot_kernel_conv_fwd(const float* x, const float* y, const float* w, const float* center,
+                                      float* out, int64_t N, int64_t M, int32_t D, int32_t kind, float blur,
+                                      void* scratch, int64_t scratch_bytes, void* stream) {
+  if (!x || !y || !w || !out || !scratch || N <= 0 || M <= 0 || !supported_simt_dim(D) || kind < 0 || kind > 2)
+    return B200OT_EINVAL;
+  if (kind != B200OT_KERNEL_ENERGY && !(blur > 0.f)) return B200OT_EINVAL;
+  if (((uintptr_t)scratch) & 15) return B200OT_EALIGN;
+  if (scratch_bytes < b200ot_kernel_conv_scratch_bytes(N, M, D)) return B200OT_ESCRATCH;
+  const ReducePlan pl = make_plan(N, M);
+  const ConvScales cs = conv_scales(kind, blur);
+  float* cols = reinterpret_cast<float*>(scratch);
+  float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) +
+                                         round_up64(b200ot_packed_cols_floats(M, D, 2) * 4, 256));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = conv_pack(y, w, center, M, D, cs, cols, st);
+  if (rc) return rc;
+  if (kind == B200OT_KERNEL_GAUSSIAN)
+    rc = launch_rowsum_d<kGaussFwd>(D, pl, st, x, center, cs.scale, cs.clampq, cols, part, N);
+  else if (kind == B200OT_KERNEL_LAPLACIAN)
+    rc = launch_rowsum_d<kLaplaceFwd>(D, pl, st, x, center, cs.scale, cs.clampq, cols, part, N);
+  else
+    rc = launch_rowsum_d<kEnergyFwd>(D, pl, st, x, center, cs.scale, cs.clampq, cols, part, N);
+  if (rc) return rc;
+  const int threads = 256;
+  conv_fwd_finalize_kernel<<<(unsigned)ceil_div64(N, threads), threads, 0, st>>>(
+      part, pl.n_split, kind == B200OT_KERNEL_ENERGY ? -1.f : 1.f, out, N);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  return B200OT_OK;
+}
+
+B200OT_API int b200ot_kernel_conv_bwd_x(const float* x, const float* y, const float* w, const float* center,
+                                        const float* grad_out, float* grad_x, int64_t N, int64_t M, int32_t D,
+                                        int32_t kind, float blur, void* scratch, int64_t scratch_bytes,
+                                        void* stream) {
+  if (!x || !y || !w || !grad_out || !grad_x || !scratch || N <= 0 || M <= 0 || !supported_simt_dim(D) ||
+      kind < 0 || kind > 2)
+    return B200OT_EINVAL;
+  if (kind != B200OT_KERNEL_ENERGY && !(blur > 0.f)) return B200OT_EINVAL;
+  if (((uintptr_t)scratch) & 15) return B200OT_EALIGN;
+  if (scratch_bytes < b200ot_kernel_conv_scratch_bytes(N, M, D)) return B200OT_ESCRATCH;
+  const ReducePlan pl = make_plan(N, M);
+  const ConvScales cs = conv_scales(kind, blur);
+  float* cols = reinterpret_cast<float*>(scratch);
+  float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) +
+                                         round_up64(b200ot_packed_cols_floats(M, D, 2) * 4, 256));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = conv_pack(y, w, center, M, D, cs, cols, st);
+  if (rc) return rc;
+  float coef;
+  if (kind == B200OT_KERNEL_GAUSSIAN) {
+    rc = launch_rowsum_d<kGaussBwd>(D, pl, st, x, center, cs.scale, cs.clampq, cols, part, N);
+    coef = 1.0f / (cs.scale * blur * blur);
+  } else if (kind == B200OT_KERNEL_LAPLACIAN) {
+    rc = launch_rowsum_d<kLaplaceBwd>(D, pl, st, x, center, cs.scale, cs.clampq, cols, part, N);
+    coef = -1.0f / blur;
+  } else {
+    rc = launch_rowsum_d<kEnergyBwd>(D, pl, st, x, center, cs.scale, cs.clampq, cols, part, N);
+    coef = -1.0f;
+  }
+  if (rc) return rc;
+  const int threads = 256;
+  conv_bwd_finalize_kernel<<<(unsigned)ceil_div64(N, threads), threads, 0, st>>>(
+      part, pl.n_split, x, center, grad_out, grad_x, N, D, kind, cs.scale, coef);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  return B200OT_OK;
+}
+
+}  // extern "C"

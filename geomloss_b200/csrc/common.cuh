@@ -24,15 +24,8 @@ constexpr float kNegBig = -1.0e30f;
 //   additive term H, remaining slots zero padding so that a packet is a multiple of 16 bytes.
 // A tile of TJ columns is therefore one contiguous run of TJ/2 packets: a single 1-D bulk TMA copy.
 // ---------------------------------------------------------------------------------------------
-template <int D>
-struct ColFmt {
-  static constexpr int kNF2 = ((D + 1 + 1) / 2) * 2;  // float2 slots per column pair (even)
-  static constexpr int kPacketFloats = kNF2 * 2;
-  static constexpr int kPacketBytes = kPacketFloats * 4;
-  static constexpr int kLds128 = kNF2 / 2;  // LDS.128 per packet
-};
-
-__host__ __device__ inline int colfmt_nf2(int D) { return ((D + 2) / 2) * 2; }
+// float2 slots per column-pair packet for D coordinates + `extra` per-column scalars (rounded to 16 B)
+__host__ __device__ inline int colfmt_nf2(int D, int extra) { return ((D + extra + 1) / 2) * 2; }
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier + 1-D bulk TMA (cp.async.bulk -> SASS UBLKCP)

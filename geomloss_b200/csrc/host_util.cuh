@@ -1,6 +1,7 @@
 // b200ot — host-side helpers shared by the translation units of libb200ot.so.
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 #include "b200ot.h"
@@ -15,6 +16,19 @@ void set_last_cuda_error(cudaError_t e, const char* where);
 
 // SM count of the current device, cached per device ordinal.
 int num_sms();
+
+// Dimensions served by the CUDA-core (register tile) kernels that are instantiated in this build.
+inline bool supported_simt_dim(int D) { return D >= 1 && D <= 3; }
+
+// Coordinate scale of the softmin kernels: the log2-domain exponent is H - |X-Y|^2/2 (p = 2) or
+// H - |X-Y| (p = 1) with X = scale * (x - c).
+inline float softmin_coord_scale(int p, float eps) {
+  return p == 2 ? sqrtf(1.4426950408889634f / eps) : 1.4426950408889634f / eps;
+}
+
+// Shared between translation units (defined in b200ot_softmin.cu).
+int softmin_pack_impl(const float* y, const float* h_a, const float* h_b, float h_scale_b, const float* center,
+                      int64_t M, int D, int p, float eps, float* cols_out, cudaStream_t st);
 
 #define B200OT_STR2(x) #x
 #define B200OT_STR(x) B200OT_STR2(x)

@@ -5,18 +5,19 @@
 namespace b200ot {
 
 // -------------------------------------------------------------------------------------------------
-// pack: (M, D) columns + per-column scalars -> colpack tiles
-//   mode bit 0 (DIRECT): store -scale*(y - c) and a plain additive term
-//   otherwise          : store +scale*(y - c) and fold -|Y|^2/2 into the additive term
-//   slot D      = h_scale * (h_a + h_scale_b * h_b)  [+ fold]   (softmin)  — or the fold alone when h_a is null
-//   slot D+1    = w (kernel conv weight) when extra == 2
-// Padding columns (j >= M): coordinates 0, additive term -inf (softmin) / weight 0 (conv).
+// pack: (M, D) columns + per-column scalars -> colpack tiles (layout: common.cuh / ColFmt)
+//   coordinates  direct ? -scale*(y - c) : +scale*(y - c)
+//   slot D       additive exponent term:  h_scale*(h_a + h_scale_b*h_b)  (softmin, h_a != null)
+//                plus, for the expansion form (direct == 0), the fold  -|Y|^2/2;
+//                with h_a == null the slot holds the fold alone (gaussian conv) or is skipped (direct conv)
+//   next slot    w_j (kernel-conv weight) when w != null
+// Padding columns (j >= M) are neutral: coordinates 0, additive term -inf (softmin) / weight 0 (conv).
 // -------------------------------------------------------------------------------------------------
 static __global__ void pack_cols_kernel(const float* __restrict__ y, const float* __restrict__ h_a,
-                                 const float* __restrict__ h_b, float h_scale_b, float h_scale,
-                                 const float* __restrict__ w, const float* __restrict__ center, float scale,
-                                 int direct, int D, int extra, int nf2, int64_t M, int64_t Mpad,
-                                 float* __restrict__ out) {
+                                        const float* __restrict__ h_b, float h_scale_b, float h_scale,
+                                        const float* __restrict__ w, const float* __restrict__ center, float scale,
+                                        int direct, int D, int nf2, int64_t M, int64_t Mpad,
+                                        float* __restrict__ out) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= Mpad) return;
   float* pk = out + (j >> 1) * (int64_t)(nf2 * 2) + (j & 1);
@@ -37,8 +38,7 @@ static __global__ void pack_cols_kernel(const float* __restrict__ y, const float
   if (h_a != nullptr) {
     float h = h_a[j];
     if (h_b != nullptr) h = fmaf(h_scale_b, h_b[j], h);
-    add = fmaf(h_scale, h, add);
-    pk[2 * slot++] = add;
+    pk[2 * slot++] = fmaf(h_scale, h, add);
   } else if (!direct) {
     pk[2 * slot++] = add;
   }

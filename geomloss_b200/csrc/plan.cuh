@@ -1,0 +1,58 @@
+// b200ot — work decomposition shared by every N x M reduction kernel (softmin, its backward,
+// kernel convolutions): which tile shape, how many column splits.
+#pragma once
+#include "host_util.cuh"
+
+namespace b200ot {
+
+// Tile shapes (must match the Cfg instantiations in the .cu files):
+//   big   : 256 consumer threads x 2 rows, 1024-column tiles, 2 CTAs / SM
+//   small : 128 consumer threads x 1 row,   256-column tiles  — a few thousand points still spread
+//           over the 148 SMs
+constexpr int kBigNT = 256, kBigR = 2, kBigTJ = 1024;
+constexpr int kSmallNT = 128, kSmallR = 1, kSmallTJ = 256;
+constexpr int kPackPad = 1024;  // packed column buffers are padded to this many columns
+
+struct ReducePlan {
+  int tj;        // columns per tile
+  int rows_cta;  // rows per CTA
+  int ntiles;
+  int tiles_per_split;
+  int n_split;
+  int64_t row_tiles;
+  bool small;
+};
+
+// Pure function of (N, M) and the SM count, so that the scratch-size query, the pack stage and the
+// reduction stage of the C ABI always agree.
+inline ReducePlan make_plan(int64_t N, int64_t M) {
+  ReducePlan p;
+  const int big_rows = kBigNT * kBigR;
+  p.small = (N < 8 * (int64_t)big_rows) || (M < 4 * kBigTJ);
+  p.tj = p.small ? kSmallTJ : kBigTJ;
+  p.rows_cta = p.small ? kSmallNT * kSmallR : big_rows;
+  p.ntiles = (int)(round_up64(M, p.tj) / p.tj);
+  p.row_tiles = ceil_div64(N, p.rows_cta);
+  // aim for ~16 waves of resident CTAs when the problem is large enough; never split below one tile
+  const int64_t target_ctas = (int64_t)num_sms() * 2 * 16;
+  int64_t want = ceil_div64(target_ctas, p.row_tiles);
+  if (want < 1) want = 1;
+  if (want > 64) want = 64;
+  if (want > p.ntiles) want = p.ntiles;
+  p.tiles_per_split = (int)ceil_div64(p.ntiles, want);
+  p.n_split = (int)ceil_div64(p.ntiles, p.tiles_per_split);
+  return p;
+}
+
+// Launch one instantiation of a partial-reduction kernel with its dynamic shared memory opt-in.
+template <class C, class Kern, class... Args>
+inline int launch_reduce(Kern kern, const ReducePlan& pl, cudaStream_t st, Args... args) {
+  // per call, not cached: the attribute is per device and a process may drive several
+  B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  dim3 grid((unsigned)pl.row_tiles, (unsigned)pl.n_split);
+  kern<<<grid, C::NT + 32, C::SMEM_BYTES, st>>>(args...);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  return B200OT_OK;
+}
+
+}  // namespace b200ot

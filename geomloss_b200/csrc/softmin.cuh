@@ -14,8 +14,11 @@
 //   consumer thread = R rows; for each column pair it reads the packet with broadcast LDS.128 and
 //           evaluates two columns at once with packed f32x2 FMAs (FFMA2): at D=3 / p=2 a pair costs
 //           3 FFMA2 + 1 FADD2 + 1/2 FMNMX3 + 1 MUFU.EX2 + 1/2 FADD2 per row, i.e. the loop is bound
-//           by the 16-lane/SM MUFU unit, not by FP32 issue.  POLY > 0 moves a fraction of the
+//           by the 16-lane/SM MUFU unit, not by FP32 issue.  PMASK moves a fraction of the
 //           exponentials to a polynomial on the FMA pipe (ex2_poly2) to balance the two units.
+//   max     the running max is LAZY: exponentials of a chunk are taken against the max known before
+//           the chunk (so MUFU and FMA work interleave freely inside a warp) and the max is only
+//           raised — with the chunk recomputed — when a chunk exceeds it by more than kLazy.
 //   p = 2 uses the expansion  -|X-Y|^2/2 = X.Y - |Y|^2/2 - |X|^2/2  on centred, pre-scaled
 //           coordinates (the -|Y|^2/2 term lives in the packed per-column slot, -|X|^2/2 is a row
 //           constant added to m at the end); DIRECT evaluates differences explicitly
@@ -45,19 +48,18 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   return r;
 }
 
-template <int D_, int R_, int P_, bool DIRECT_, int POLY_, int NT_ = 256, int TJ_ = 1024, int STAGES_ = 3,
-          int CH_ = 4, int MINB_ = 2>
+template <int D_, int R_, int P_, bool DIRECT_, unsigned PMASK_ = 0u, int NT_ = 256, int TJ_ = 1024,
+          int STAGES_ = 3, int CH_ = 4, int MINB_ = 2>
 struct SoftminCfg {
   static constexpr int D = D_;            // ambient dimension
   static constexpr int R = R_;            // rows per consumer thread
   static constexpr int P = P_;            // cost exponent (1 or 2)
   static constexpr bool DIRECT = DIRECT_; // explicit differences instead of the dot-product expansion
-  static constexpr int POLY = POLY_;      // 0: all exp2 on MUFU; 1: one column pair per chunk on the FMA pipe;
-                                          // 2: one pair every other chunk
+  static constexpr unsigned PMASK = PMASK_; // bit c set: column pair c of every chunk takes the FMA-pipe exp2
   static constexpr int NT = NT_;          // consumer threads
   static constexpr int TJ = TJ_;          // columns per tile
   static constexpr int STAGES = STAGES_;
-  static constexpr int CH = CH_;          // column pairs per chunk (max is refreshed once per chunk)
+  static constexpr int CH = CH_;          // column pairs per chunk (running max refreshed once per chunk)
   static constexpr int MINB = MINB_;      // CTAs per SM the register budget is planned for
   static constexpr int NEXTRA = 1;
   static constexpr int NF2 = ((D + NEXTRA + 1) / 2) * 2;
@@ -68,6 +70,50 @@ struct SoftminCfg {
   static_assert(P == 2 || DIRECT, "p = 1 needs explicit differences");
   static_assert((TJ / 2) % CH == 0, "tile must hold a whole number of chunks");
 };
+
+// Lazy-max slack (log2 units): the running max m is only raised when a chunk exceeds it by more than
+// this, so exp2 arguments stay <= kLazy and row sums stay far below FLT_MAX (M * 2^64 ~ 1e25 for M = 1e6).
+constexpr float kLazy = 64.0f;
+
+// log2-domain exponent of one column pair against one row
+template <class C>
+__device__ __forceinline__ float2 pair_exponent(const float2 (&X)[C::D], const float2 (&S)[C::NF2], float clampq) {
+  constexpr int D = C::D;
+  float2 t;
+  if constexpr (!C::DIRECT) {
+    t = S[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) t = __ffma2_rn(X[d], S[d], t);
+  } else {
+    float2 qq;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const float2 df = __fadd2_rn(X[d], S[d]);  // packed columns hold -Y
+      qq = (d == 0) ? __fmul2_rn(df, df) : __ffma2_rn(df, df, qq);
+    }
+    if constexpr (C::P == 2) {
+      t = __ffma2_rn(qq, dup2(-0.5f), S[D]);
+    } else {
+      qq.x = fmaxf(qq.x, clampq);
+      qq.y = fmaxf(qq.y, clampq);
+      float2 dist;
+      dist.x = sqrt_approx(qq.x);
+      dist.y = sqrt_approx(qq.y);
+      t = __ffma2_rn(dist, dup2(-1.0f), S[D]);
+    }
+  }
+  return t;
+}
+
+template <int NF2>
+__device__ __forceinline__ void load_packet(const float4* __restrict__ tp, int pair, float2 (&S)[NF2]) {
+#pragma unroll
+  for (int q = 0; q < NF2 / 2; ++q) {
+    const float4 v = tp[pair * (NF2 / 2) + q];
+    S[2 * q] = make_float2(v.x, v.y);
+    S[2 * q + 1] = make_float2(v.z, v.w);
+  }
+}
 
 template <class C>
 __global__ void __launch_bounds__(C::NT + 32, C::MINB)
@@ -131,6 +177,7 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
     rowc[r] = C::DIRECT ? 0.f : -0.5f * acc;
   }
 
+  // running (m, s): s = sum_j 2^(t_j - m); m trails the true running max by at most kLazy
   float m[R];
   float2 nm2[R], s2[R];
 #pragma unroll
@@ -145,74 +192,66 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
     mbar_wait(&full[st], (k / STAGES) & 1);
     const float4* tp = reinterpret_cast<const float4*>(tiles + st * C::TILE_FLOATS);
 
+    // two-level accumulation: chunk sums -> tile sum ts2 -> running sum s2 (keeps the fp32 summation
+    // error at ~sqrt(chunks per tile) + sqrt(tiles) ulps instead of sqrt(M) ulps)
+    float2 ts2[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) ts2[r] = dup2(0.f);
+
 #pragma unroll 1
     for (int jp = 0; jp < C::TJ / 2; jp += CH) {
-      float2 T[R][CH];
+      // speculative pass: exponentials against the (possibly stale) max, chunk max on the side
+      float2 cs[R];
+      float cm[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        cs[r] = dup2(0.f);
+        cm[r] = kNegBig;
+      }
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
         float2 S[NF2];
-#pragma unroll
-        for (int q = 0; q < NF2 / 2; ++q) {
-          const float4 v = tp[(jp + c) * (NF2 / 2) + q];
-          S[2 * q] = make_float2(v.x, v.y);
-          S[2 * q + 1] = make_float2(v.z, v.w);
-        }
+        load_packet<NF2>(tp, jp + c, S);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          float2 t;
-          if constexpr (!C::DIRECT) {
-            t = S[D];
-#pragma unroll
-            for (int d = 0; d < D; ++d) t = __ffma2_rn(X[r][d], S[d], t);
-          } else {
-            float2 qq;
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-              const float2 df = __fadd2_rn(X[r][d], S[d]);  // packed columns hold -Y
-              qq = (d == 0) ? __fmul2_rn(df, df) : __ffma2_rn(df, df, qq);
-            }
-            if constexpr (C::P == 2) {
-              t = __ffma2_rn(qq, dup2(-0.5f), S[D]);
-            } else {
-              qq.x = fmaxf(qq.x, clampq);
-              qq.y = fmaxf(qq.y, clampq);
-              float2 dist;
-              dist.x = sqrt_approx(qq.x);
-              dist.y = sqrt_approx(qq.y);
-              t = __ffma2_rn(dist, dup2(-1.0f), S[D]);
-            }
-          }
-          T[r][c] = t;
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        float cm = fmaxf(T[r][0].x, T[r][0].y);
-#pragma unroll
-        for (int c = 1; c < CH; ++c) cm = fmax3(cm, T[r][c].x, T[r][c].y);
-        if (cm > m[r]) {
-          const float sc = ex2_approx(m[r] - cm);
-          s2[r] = __fmul2_rn(s2[r], dup2(sc));
-          m[r] = cm;
-          nm2[r] = dup2(-cm);
-        }
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          const float2 a = __fadd2_rn(T[r][c], nm2[r]);
+          const float2 t = pair_exponent<C>(X[r], S, clampq);
+          cm[r] = fmax3(cm[r], t.x, t.y);
+          const float2 a = __fadd2_rn(t, nm2[r]);
           float2 e;
-          bool poly = false;
-          if constexpr (C::POLY == 1) poly = (c == 0);
-          if constexpr (C::POLY == 2) poly = (c == 0) && ((jp / CH) & 1);
-          if (poly) {
+          if ((C::PMASK >> c) & 1u) {
             e = ex2_poly2(a);
           } else {
             e.x = ex2_approx(a.x);
             e.y = ex2_approx(a.y);
           }
-          s2[r] = __fadd2_rn(s2[r], e);
+          cs[r] = __fadd2_rn(cs[r], e);
         }
       }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (cm[r] > m[r] + kLazy) {
+          // rare: the chunk overshoots the stale max — rebase the row on the chunk max and redo the chunk
+          const float sc = ex2_approx(m[r] - cm[r]);
+          s2[r] = __fmul2_rn(s2[r], dup2(sc));
+          ts2[r] = __fmul2_rn(ts2[r], dup2(sc));
+          m[r] = cm[r];
+          nm2[r] = dup2(-cm[r]);
+          float2 acc = dup2(0.f);
+#pragma unroll 1
+          for (int c = 0; c < CH; ++c) {
+            float2 S[NF2];
+            load_packet<NF2>(tp, jp + c, S);
+            const float2 a = __fadd2_rn(pair_exponent<C>(X[r], S, clampq), nm2[r]);
+            acc.x += ex2_approx(a.x);
+            acc.y += ex2_approx(a.y);
+          }
+          cs[r] = acc;
+        }
+        ts2[r] = __fadd2_rn(ts2[r], cs[r]);
+      }
     }
+#pragma unroll
+    for (int r = 0; r < R; ++r) s2[r] = __fadd2_rn(s2[r], ts2[r]);
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);
   }

@@ -1,0 +1,244 @@
+"""Torch-facing wrappers of the C-ABI kernels: device buffers in, device buffers out, autograd wired.
+
+Mirrors the reference's operator seam — ``softmin(eps, C_xy, h_y) -> f_x`` with ``C_xy = (x, y)``
+(src/geomloss/_legacy/sinkhorn_samples.py:337-346, sinkhorn_divergence.py:291-303) and the kernel
+matvecs of ``kernel_loss`` (kernel_samples.py:128-137) — but every call lands in libb200ot.so.
+PyTorch is used for memory, streams and autograd bookkeeping only.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+KERNEL_KINDS = {"gaussian": 0, "laplacian": 1, "energy": 2}
+MAX_D = 3  # dimensions instantiated in this build of libb200ot.so (supported_simt_dim in csrc/host_util.cuh)
+
+# Number of kernels of libb200ot.so enqueued so far by this process (bench.py reports the delta over its
+# timed region as `gpu_launches`).  Every one-call entry point is pack + partial reduction + finalize.
+_launches = 0
+
+
+def count_launches(n: int):
+    global _launches
+    _launches += n
+
+
+def launches() -> int:
+    return _launches
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _f32c(t, name):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.B200OTError(f"{name} must live on a CUDA device (geomloss_b200 has no CPU path), got {t.device}")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32 (the engine computes in fp32), got {t.dtype}")
+    return t.contiguous()
+
+
+def _check_clouds(x, y):
+    if x.dim() != 2 or y.dim() != 2 or x.shape[1] != y.shape[1]:
+        raise ValueError(f"expected x:(N,D), y:(M,D); got {tuple(x.shape)}, {tuple(y.shape)}")
+    if x.shape[0] == 0 or y.shape[0] == 0:
+        raise ValueError("empty point cloud")
+    if x.shape[1] > MAX_D:
+        raise NotImplementedError(f"D = {x.shape[1]} > {MAX_D}: only D <= {MAX_D} kernels are instantiated in this "
+                                  "build (the large-D tensor-core path is not built yet)")
+    if x.device != y.device:
+        raise ValueError("x and y must be on the same device")
+
+
+_scratch_cache: dict = {}
+
+
+def _scratch(nbytes: int, dev, tag: str):
+    """Per-(device, stream, tag) scratch buffer, grown geometrically; stream-ordered reuse is safe because
+    every kernel that touches it is enqueued on that same stream."""
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream, tag)
+    buf = _scratch_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+        _scratch_cache[key] = buf
+    return buf
+
+
+def default_center(x, y):
+    """Mid-point of the joint bounding box: the origin of the |x|^2 - 2x.y + |y|^2 expansion."""
+    lo = torch.minimum(x.min(0).values, y.min(0).values)
+    hi = torch.maximum(x.max(0).values, y.max(0).values)
+    return (0.5 * (lo + hi)).float().contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# softmin
+# ------------------------------------------------------------------------------------------------
+
+
+def softmin_raw(eps, x, y, h_a, h_b=None, h_scale_b=0.0, *, p=2, center=None, out_old=None, alpha_old=0.0,
+                beta=1.0, out=None, want_lse2=False):
+    """One fused launch group: ``out <- alpha_old*out_old + beta*softmin(eps, (x, y), h_a + h_scale_b*h_b)``.
+
+    No autograd.  Returns ``(out, lse2 | None)``.
+    """
+    x, y, h_a, h_b = _f32c(x, "x"), _f32c(y, "y"), _f32c(h_a, "h_a"), _f32c(h_b, "h_b")
+    center, out_old = _f32c(center, "center"), _f32c(out_old, "out_old")
+    _check_clouds(x, y)
+    N, D = x.shape
+    M = y.shape[0]
+    if h_a.numel() != M or (h_b is not None and h_b.numel() != M):
+        raise ValueError("h must have one entry per column")
+    dev = x.device
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty(N, dtype=torch.float32, device=dev)
+        lse2 = torch.empty(N, dtype=torch.float32, device=dev) if want_lse2 else None
+        nbytes = L.b200ot_softmin_scratch_bytes(N, M, D)
+        scratch = _scratch(nbytes, dev, "softmin")
+        rc = L.b200ot_softmin_fwd(_ptr(x), _ptr(y), _ptr(h_a), _ptr(h_b), float(h_scale_b), _ptr(center),
+                                  _ptr(out_old), float(alpha_old), float(beta), _ptr(out), _ptr(lse2), N, M, D,
+                                  int(p), float(eps), _ptr(scratch), scratch.numel(), _stream(dev))
+    _lib.check(rc, "b200ot_softmin_fwd")
+    count_launches(3)
+    return out, lse2
+
+
+def softmin_grad_rows(eps, x, y, h_a, h_b, h_scale_b, lse2, grad_out, *, p=2, center=None):
+    """grad_x of <grad_out, softmin(eps, (x, y), h)> with y, h constant (b200ot_softmin_bwd_x)."""
+    x, y, h_a, h_b = _f32c(x, "x"), _f32c(y, "y"), _f32c(h_a, "h_a"), _f32c(h_b, "h_b")
+    center, lse2, grad_out = _f32c(center, "center"), _f32c(lse2, "lse2"), _f32c(grad_out, "grad_out")
+    N, D = x.shape
+    M = y.shape[0]
+    dev = x.device
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        gx = torch.empty_like(x)
+        nbytes = L.b200ot_softmin_scratch_bytes(N, M, D)
+        scratch = _scratch(nbytes, dev, "softmin")
+        rc = L.b200ot_softmin_bwd_x(_ptr(x), _ptr(y), _ptr(h_a), _ptr(h_b), float(h_scale_b), _ptr(center),
+                                    _ptr(lse2), _ptr(grad_out), _ptr(gx), N, M, D, int(p), float(eps),
+                                    _ptr(scratch), scratch.numel(), _stream(dev))
+    _lib.check(rc, "b200ot_softmin_bwd_x")
+    count_launches(3)
+    return gx
+
+
+class _Softmin(torch.autograd.Function):
+    """softmin(eps, (x, y), h) with the reference's autograd contract: the gradient flows to the row
+    cloud x only; y and h are treated as constants (they are ``.detach()``-ed at every call site of the
+    reference: sinkhorn_samples.py:392-393, sinkhorn_divergence.py:616-623)."""
+
+    @staticmethod
+    def forward(ctx, x, y, h_a, h_b, h_scale_b, eps, p, center, scale_out):
+        need_grad = ctx.needs_input_grad[0]
+        out, lse2 = softmin_raw(eps, x, y, h_a, h_b, h_scale_b, p=p, center=center, beta=scale_out,
+                                want_lse2=need_grad)
+        if need_grad:
+            ctx.save_for_backward(x, y, h_a, h_b if h_b is not None else h_a, center if center is not None else h_a,
+                                  lse2)
+            ctx.meta = (float(h_scale_b), float(eps), int(p), float(scale_out), h_b is not None, center is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, y, h_a, h_b, center, lse2 = ctx.saved_tensors
+        h_scale_b, eps, p, scale_out, has_hb, has_center = ctx.meta
+        go = (grad_out * scale_out).contiguous()
+        gx = softmin_grad_rows(eps, x, y, h_a, h_b if has_hb else None, h_scale_b, lse2, go, p=p,
+                               center=center if has_center else None)
+        return gx, None, None, None, None, None, None, None, None
+
+
+def softmin(eps, x, y, h_a, h_b=None, h_scale_b=0.0, *, p=2, center=None, scale_out=1.0):
+    """Differentiable (w.r.t. x) ``scale_out * softmin(eps, (x, y.detach()), (h_a + h_scale_b*h_b).detach())``."""
+    return _Softmin.apply(x, y.detach(), h_a.detach(), None if h_b is None else h_b.detach(), h_scale_b, eps, p,
+                          center, scale_out)
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel convolutions
+# ------------------------------------------------------------------------------------------------
+
+
+def kernel_conv_raw(kind, x, y, w, blur, *, center=None):
+    """out_i = sum_j k(x_i, y_j) w_j, no autograd."""
+    x, y, w, center = _f32c(x, "x"), _f32c(y, "y"), _f32c(w, "w"), _f32c(center, "center")
+    _check_clouds(x, y)
+    N, D = x.shape
+    M = y.shape[0]
+    if w.numel() != M:
+        raise ValueError("w must have one entry per column")
+    dev = x.device
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        out = torch.empty(N, dtype=torch.float32, device=dev)
+        nbytes = L.b200ot_kernel_conv_scratch_bytes(N, M, D)
+        scratch = _scratch(nbytes, dev, "conv")
+        rc = L.b200ot_kernel_conv_fwd(_ptr(x), _ptr(y), _ptr(w), _ptr(center), _ptr(out), N, M, D,
+                                      KERNEL_KINDS[kind], float(blur), _ptr(scratch), scratch.numel(), _stream(dev))
+    _lib.check(rc, "b200ot_kernel_conv_fwd")
+    count_launches(3)
+    return out
+
+
+def kernel_conv_grad_rows(kind, x, y, w, blur, grad_out, *, center=None):
+    x, y, w, center = _f32c(x, "x"), _f32c(y, "y"), _f32c(w, "w"), _f32c(center, "center")
+    grad_out = _f32c(grad_out, "grad_out")
+    N, D = x.shape
+    M = y.shape[0]
+    dev = x.device
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        gx = torch.empty_like(x)
+        nbytes = L.b200ot_kernel_conv_scratch_bytes(N, M, D)
+        scratch = _scratch(nbytes, dev, "conv")
+        rc = L.b200ot_kernel_conv_bwd_x(_ptr(x), _ptr(y), _ptr(w), _ptr(center), _ptr(grad_out), _ptr(gx), N, M, D,
+                                        KERNEL_KINDS[kind], float(blur), _ptr(scratch), scratch.numel(),
+                                        _stream(dev))
+    _lib.check(rc, "b200ot_kernel_conv_bwd_x")
+    count_launches(3)
+    return gx
+
+
+class _KernelConv(torch.autograd.Function):
+    """out = K(x, y) @ w, differentiable w.r.t. x, y and w (kernels are symmetric, so the y- and
+    w-gradients are the same reduction with the roles of the clouds swapped)."""
+
+    @staticmethod
+    def forward(ctx, x, y, w, kind, blur, center):
+        out = kernel_conv_raw(kind, x, y, w, blur, center=center)
+        ctx.save_for_backward(x, y, w, center if center is not None else w)
+        ctx.meta = (kind, float(blur), center is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        x, y, w, center = ctx.saved_tensors
+        kind, blur, has_center = ctx.meta
+        center = center if has_center else None
+        go = go.contiguous()
+        gx = gy = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = kernel_conv_grad_rows(kind, x, y, w, blur, go, center=center)
+        if ctx.needs_input_grad[1]:
+            # d/dy_j sum_i go_i k(x_i, y_j) w_j = w_j * sum_i go_i dk(y_j, x_i)/dy_j
+            gy = kernel_conv_grad_rows(kind, y, x, go, blur, w, center=center)
+        if ctx.needs_input_grad[2]:
+            gw = kernel_conv_raw(kind, y, x, go, blur, center=center)
+        return gx, gy, gw, None, None, None
+
+
+def kernel_conv(kind, x, y, w, blur, *, center=None):
+    return _KernelConv.apply(x, y, w, kind, blur, center)

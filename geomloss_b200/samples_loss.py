@@ -1,0 +1,194 @@
+"""``SamplesLoss`` — drop-in for ``geomloss.SamplesLoss`` on CUDA point clouds.
+
+Same constructor keywords, same 2 / 4 / 6 positional-tensor call forms, same shape rules, error types
+and output shapes as the reference module (src/geomloss/_legacy/samples_loss.py:45-474), including
+its quirks that user code may rely on:
+  * ``potentials=True`` on unbatched input returns ``(1, N)`` / ``(1, M)`` tensors;
+  * ``loss="hausdorff"`` is accepted by the constructor and fails with ``KeyError(None)`` at call
+    time, exactly like the reference at this commit;
+  * unknown ``p`` raises ``KeyError`` (the reference's cost table only has p = 1, 2).
+
+What differs by design: there is ONE engine.  ``backend`` is still validated and still drives the
+reference's routing rules (labels need "auto"/"multiscale", batches are looped over), but
+"tensorized", "online", "multiscale" and "auto" all run the same never-materialised sm_100a kernels,
+evaluated exactly (the multiscale truncation of the reference is an approximation of this exact
+computation; ``truncate`` / ``cluster_scale`` / labels are accepted and currently unused).
+Inputs must be float32 CUDA tensors: there is no CPU path.
+"""
+from __future__ import annotations
+
+import torch
+from torch.nn import Module
+
+from .kernel_loss import kernel_points
+from .sinkhorn import sinkhorn_points
+
+_LOSSES = ("sinkhorn", "hausdorff", "energy", "gaussian", "laplacian")
+_BACKENDS = ("auto", "tensorized", "online", "multiscale")
+
+
+def _route(loss):
+    """Per-loss routine taking one unbatched problem (reference: the ``routines`` table, samples_loss.py:16-42)."""
+    if loss == "sinkhorn":
+        return sinkhorn_points
+    if loss == "hausdorff":
+        return lambda *args, **kw: kernel_points(*args, name=None, **kw)
+    if loss in ("energy", "gaussian", "laplacian"):
+        return lambda *args, **kw: kernel_points(*args, name=loss, **kw)
+    raise KeyError(loss)
+
+
+class SamplesLoss(Module):
+    """Geometric loss between two weighted point clouds (see the module docstring).
+
+    Args mirror ``geomloss.SamplesLoss`` (samples_loss.py:178-194): loss, p, blur, reach, diameter,
+    scaling, truncate, cost, kernel, cluster_scale, debias, potentials, verbose, backend.
+    """
+
+    def __init__(self, loss="sinkhorn", p=2, blur=0.05, reach=None, diameter=None, scaling=0.5, truncate=5,
+                 cost=None, kernel=None, cluster_scale=None, debias=True, potentials=False, verbose=False,
+                 backend="auto"):
+        super().__init__()
+        self.loss = loss
+        self.backend = backend
+        self.p = p
+        self.blur = blur
+        self.reach = reach
+        self.truncate = truncate
+        self.diameter = diameter
+        self.scaling = scaling
+        self.cost = cost
+        self.kernel = kernel
+        self.cluster_scale = cluster_scale
+        self.debias = debias
+        self.potentials = potentials
+        self.verbose = verbose
+        # injected by geomloss_b200.distributed.shard_columns(): column-sharded reduction operators
+        self._engine = {}
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, *args):
+        l_x, a, x, l_y, b, y = self.process_args(*args)
+        B, N, M, D, l_x, a, l_y, b = self.check_shapes(l_x, a, x, l_y, b, y)
+
+        backend = self.backend
+        if backend not in _BACKENDS:
+            raise KeyError(backend)
+        if l_x is not None or l_y is not None:
+            if backend not in ("auto", "multiscale"):
+                raise ValueError(
+                    'Explicit cluster labels are only supported with the "auto" and "multiscale" backends.')
+        if self.cost is not None:
+            raise NotImplementedError(
+                "custom cost functions need a dense (B,N,M) cost matrix or a KeOps formula; the CUDA engine "
+                "only evaluates |x-y|^p/p, p in {1,2}, on the fly")
+        routine = _route(self.loss)
+        kw = dict(p=self.p, blur=self.blur, reach=self.reach, diameter=self.diameter, scaling=self.scaling,
+                  debias=self.debias, potentials=self.potentials, kernel=self.kernel, **self._engine)
+
+        if B == 0:
+            values = routine(a, x, b, y, **kw)
+            if self.potentials:
+                F, G = values
+                return F.view(1, -1), G.view(1, -1)  # the reference's (1,N) shape for unbatched input
+            return values
+        per_batch = [routine(a[k], x[k], b[k], y[k], **kw) for k in range(B)]
+        if self.potentials:
+            F = torch.stack([f for f, _ in per_batch])
+            G = torch.stack([g for _, g in per_batch])
+            return F.view_as(a), G.view_as(b)
+        return torch.stack(per_batch)
+
+    # ------------------------------------------------------------------------------------------
+    def process_args(self, *args):
+        """2 tensors: (x, y) with uniform weights; 4: (a, x, b, y); 6: (l_x, a, x, l_y, b, y)."""
+        if len(args) == 6:
+            return args
+        if len(args) == 4:
+            a, x, b, y = args
+            return None, a, x, None, b, y
+        if len(args) == 2:
+            x, y = args
+            return None, self.generate_weights(x), x, None, self.generate_weights(y), y
+        raise ValueError(
+            "A SamplesLoss accepts two (x, y), four (α, x, β, y) or six (l_x, α, x, l_y, β, y)  arguments.")
+
+    def generate_weights(self, x):
+        if x.dim() == 2:
+            return torch.ones(x.shape[0]).type_as(x) / x.shape[0]
+        if x.dim() == 3:
+            return torch.ones(x.shape[0], x.shape[1]).type_as(x) / x.shape[1]
+        raise ValueError("Input samples 'x' and 'y' should be encoded as (N,D) or (B,N,D) (batch) tensors.")
+
+    @staticmethod
+    def _check_labels(l, n, which):
+        if l is None:
+            return None
+        if l.dim() not in (1, 2) or (l.dim() == 2 and l.shape[1] > 1):
+            raise ValueError(f"Without batches, the vector of labels '{which}' should be encoded as an "
+                             f"({'N' if which == 'l_x' else 'M'},) or ({'N' if which == 'l_x' else 'M'},1) tensor.")
+        l = l.view(-1)
+        if len(l) != n:
+            raise ValueError(f"The vector of labels '{which}' should have the same length as the point cloud "
+                             f"'{'x' if which == 'l_x' else 'y'}'.")
+        return l
+
+    def check_shapes(self, l_x, a, x, l_y, b, y):
+        """Validation rules of samples_loss.py:337-474; returns (B, N, M, D, l_x, a, l_y, b), B = 0 unbatched."""
+        if a.dim() != b.dim():
+            raise ValueError("Input weights 'α' and 'β' should have the same number of dimensions.")
+        if x.dim() != y.dim():
+            raise ValueError("Input samples 'x' and 'y' should have the same number of dimensions.")
+        if x.shape[-1] != y.shape[-1]:
+            raise ValueError("Input samples 'x' and 'y' should have the same last dimension.")
+
+        if x.dim() == 2:
+            B = 0
+            N, D = x.shape
+            M = y.shape[0]
+            if a.dim() not in (1, 2):
+                raise ValueError(
+                    "Without batches, input weights 'α' and 'β' should be encoded as (N,) or (N,1) tensors.")
+            if a.dim() == 2:
+                if a.shape[1] > 1:
+                    raise ValueError(
+                        "Without batches, input weights 'α' should be encoded as (N,) or (N,1) tensors.")
+                if b.shape[1] > 1:
+                    raise ValueError(
+                        "Without batches, input weights 'β' should be encoded as (M,) or (M,1) tensors.")
+                a, b = a.view(-1), b.view(-1)
+            l_x = self._check_labels(l_x, N, "l_x")
+            l_y = self._check_labels(l_y, M, "l_y")
+            N2, M2 = a.shape[0], b.shape[0]
+        elif x.dim() == 3:
+            B, N, D = x.shape
+            B2, M, _ = y.shape
+            if B != B2:
+                raise ValueError("Samples 'x' and 'y' should have the same batchsize.")
+            if a.dim() not in (2, 3):
+                raise ValueError(
+                    "With batches, input weights 'α' and 'β' should be encoded as (B,N) or (B,N,1) tensors.")
+            if a.dim() == 3:
+                if a.shape[2] > 1:
+                    raise ValueError(
+                        "With batches, input weights 'α' should be encoded as (B,N) or (B,N,1) tensors.")
+                if b.shape[2] > 1:
+                    raise ValueError(
+                        "With batches, input weights 'β' should be encoded as (B,M) or (B,M,1) tensors.")
+                a, b = a.squeeze(-1), b.squeeze(-1)
+            if l_x is not None or l_y is not None:
+                raise NotImplementedError('The "multiscale" backend has not been implemented with batches.')
+            B2, N2 = a.shape
+            B3, M2 = b.shape
+            if B != B2:
+                raise ValueError("Samples 'x' and weights 'α' should have the same batchsize.")
+            if B != B3:
+                raise ValueError("Samples 'y' and weights 'β' should have the same batchsize.")
+        else:
+            raise ValueError("Input samples 'x' and 'y' should be encoded as (N,D) or (B,N,D) (batch) tensors.")
+
+        if N != N2:
+            raise ValueError("Weights 'α' and samples 'x' should have compatible shapes.")
+        if M != M2:
+            raise ValueError("Weights 'β' and samples 'y' should have compatible shapes.")
+        return B, N, M, D, l_x, a, l_y, b

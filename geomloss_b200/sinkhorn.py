@@ -1,0 +1,129 @@
+"""Host side of the Sinkhorn divergence on point clouds: epsilon-scaling schedule, the symmetric
+Sinkhorn loop and the dual-to-value formulas.  Every softmin lands in libb200ot.so (see ops.py).
+
+This follows the control flow of the reference because the control flow *is* the specification
+(src/geomloss/_legacy/sinkhorn_divergence.py:56-163 schedule/scalars, :171-250 value, :258-628 loop;
+driver src/geomloss/_legacy/sinkhorn_samples.py:349-424), with three B200-side changes:
+  * the "cost matrix" is the pair of point clouds — nothing of size N x M is ever stored;
+  * ``h = log_w + pot/eps``, the damping factor and the ``1/2 (f + f~)`` averaging are fused into the
+    softmin launch (prologue / epilogue) instead of separate elementwise kernels;
+  * the autograd switch is a context manager, not the reference's global ``set_grad_enabled`` toggle.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def damping(eps, rho):
+    """1 for balanced OT, 1/(1+eps/rho) with a KL marginal penalty.          sinkhorn_divergence.py:56-58"""
+    return 1.0 if rho is None else 1.0 / (1.0 + eps / rho)
+
+
+def log_weights(a):
+    """log(a) with the log of non-positive weights pinned to -1e5.           sinkhorn_divergence.py:61-65"""
+    return torch.where(a > 0, a.clamp_min(1e-45).log(), torch.full_like(a, -100000.0))
+
+
+def max_diameter(x, y):
+    """Length of the diagonal of the joint bounding box (one host sync).     sinkhorn_divergence.py:96-112"""
+    lo = torch.minimum(x.min(0).values, y.min(0).values)
+    hi = torch.maximum(x.max(0).values, y.max(0).values)
+    return (hi - lo).norm().item()
+
+
+def epsilon_schedule(p, diameter, blur, scaling):
+    """Temperatures diam^p -> blur^p, geometric with ratio scaling^p; the first value appears twice
+    (the arange starts at p log diam) exactly as in the reference.          sinkhorn_divergence.py:115-151"""
+    steps = np.arange(p * np.log(diameter), p * np.log(blur), p * np.log(scaling))
+    return [diameter**p] + [float(np.exp(e)) for e in steps] + [blur**p]
+
+
+def scaling_parameters(x, y, p, blur, reach, diameter, scaling):
+    """(diameter, eps, eps_list, rho).                                      sinkhorn_divergence.py:154-163"""
+    if diameter is None:
+        d = x.shape[-1]
+        diameter = max_diameter(x.reshape(-1, d), y.reshape(-1, d))
+    rho = None if reach is None else reach**p
+    return diameter, blur**p, epsilon_schedule(p, diameter, blur, scaling), rho
+
+
+def sinkhorn_loop_points(a_log, b_log, x, y, eps_list, rho, *, p=2, debias=True, center=None, softmin_raw=None,
+                         softmin_grad=None):
+    """Symmetric Sinkhorn iterations with eps-scaling on one pair of clouds.   sinkhorn_divergence.py:258-628
+
+    The iterations run without autograd on detached clouds.  All four updates of an iteration read the
+    OLD potentials (Jacobi), then  f <- 1/2 f + 1/2 lam softmin(...)  — one fused launch each.
+    The last update is not averaged, takes ``x`` / ``y`` with autograd and detached right-hand sides,
+    and therefore carries the whole gradient (envelope theorem).  Returns (f_aa, g_bb, g_ab, f_ba).
+
+    ``softmin_raw`` / ``softmin_grad`` default to the single-GPU kernels; the column-sharded
+    multi-GPU engine (distributed.py) injects its own pair with the same signatures.
+    """
+    sm = softmin_raw or ops.softmin_raw
+    smg = softmin_grad or ops.softmin
+    xd, yd = x.detach(), y.detach()
+    with torch.no_grad():
+        eps = eps_list[0]
+        lam = damping(eps, rho)
+        g_ab = sm(eps, yd, xd, a_log, p=p, center=center, beta=lam)[0]
+        f_ba = sm(eps, xd, yd, b_log, p=p, center=center, beta=lam)[0]
+        if debias:
+            f_aa = sm(eps, xd, xd, a_log, p=p, center=center, beta=lam)[0]
+            g_bb = sm(eps, yd, yd, b_log, p=p, center=center, beta=lam)[0]
+        for eps in eps_list:
+            lam = damping(eps, rho)
+            inv = 1.0 / eps
+            ft_ba = sm(eps, xd, yd, b_log, g_ab, inv, p=p, center=center, out_old=f_ba, alpha_old=0.5,
+                       beta=0.5 * lam)[0]
+            gt_ab = sm(eps, yd, xd, a_log, f_ba, inv, p=p, center=center, out_old=g_ab, alpha_old=0.5,
+                       beta=0.5 * lam)[0]
+            if debias:
+                ft_aa = sm(eps, xd, xd, a_log, f_aa, inv, p=p, center=center, out_old=f_aa, alpha_old=0.5,
+                           beta=0.5 * lam)[0]
+                gt_bb = sm(eps, yd, yd, b_log, g_bb, inv, p=p, center=center, out_old=g_bb, alpha_old=0.5,
+                           beta=0.5 * lam)[0]
+                f_aa, g_bb = ft_aa, gt_bb
+            f_ba, g_ab = ft_ba, gt_ab
+    # final extrapolation: eps / lam are the last values of the schedule (reference: leaked loop variables)
+    inv = 1.0 / eps
+    new_f_ba = smg(eps, x, yd, b_log, g_ab, inv, p=p, center=center, scale_out=lam)
+    new_g_ab = smg(eps, y, xd, a_log, f_ba, inv, p=p, center=center, scale_out=lam)
+    if debias:
+        new_f_aa = smg(eps, x, xd, a_log, f_aa, inv, p=p, center=center, scale_out=lam)
+        new_g_bb = smg(eps, y, yd, b_log, g_bb, inv, p=p, center=center, scale_out=lam)
+        return new_f_aa, new_g_bb, new_g_ab, new_f_ba
+    return None, None, new_g_ab, new_f_ba
+
+
+def sinkhorn_cost(eps, rho, a, b, f_aa, g_bb, g_ab, f_ba, debias=True, potentials=False):
+    """Value of the divergence (or the dual potentials) from the four potentials, unbatched vectors.
+    sinkhorn_divergence.py:171-250.  The unbalanced weight is (rho + eps/2) in both passes — the
+    reference's UnbalancedWeight.backward is dead code."""
+    if potentials:
+        return (f_ba - f_aa, g_ab - g_bb) if debias else (f_ba, g_ab)
+    if rho is None:
+        if debias:
+            return torch.dot(a, f_ba - f_aa) + torch.dot(b, g_ab - g_bb)
+        return torch.dot(a, f_ba) + torch.dot(b, g_ab)
+    w = rho + eps / 2
+    if debias:
+        return torch.dot(a, w * ((-f_aa / rho).exp() - (-f_ba / rho).exp())) + torch.dot(
+            b, w * ((-g_bb / rho).exp() - (-g_ab / rho).exp()))
+    return torch.dot(a, w * (1 - (-f_ba / rho).exp())) + torch.dot(b, w * (1 - (-g_ab / rho).exp()))
+
+
+def sinkhorn_points(a, x, b, y, p=2, blur=0.05, reach=None, diameter=None, scaling=0.5, debias=True,
+                    potentials=False, softmin_raw=None, softmin_grad=None, **_ignored):
+    """Sinkhorn divergence between two weighted clouds a:(N,) x:(N,D) b:(M,) y:(M,D) on one CUDA device.
+    Counterpart of sinkhorn_online (sinkhorn_samples.py:349-424) for a single batch element."""
+    if p not in (1, 2):
+        raise KeyError(p)  # the reference's cost table only knows p = 1, 2 (sinkhorn_samples.py:26-29)
+    diameter, eps, eps_list, rho = scaling_parameters(x, y, p, blur, reach, diameter, scaling)
+    center = ops.default_center(x.detach(), y.detach())
+    f_aa, g_bb, g_ab, f_ba = sinkhorn_loop_points(log_weights(a.detach()), log_weights(b.detach()), x, y, eps_list,
+                                                  rho, p=p, debias=debias, center=center, softmin_raw=softmin_raw,
+                                                  softmin_grad=softmin_grad)
+    return sinkhorn_cost(eps, rho, a, b, f_aa, g_bb, g_ab, f_ba, debias=debias, potentials=potentials)

@@ -30,6 +30,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define B200OT_API __attribute__((visibility("default")))
+#else
+#define B200OT_API
+#endif
+
 #define B200OT_VERSION 100 /* 0.1.0 */
 #define B200OT_MAX_D 16    /* CUDA-core (register-tile) kernels; larger D is routed to the tensor-core path */
 
@@ -45,9 +51,9 @@ extern "C" {
 #define B200OT_KERNEL_LAPLACIAN 1 /* exp(-sqrt(max(|x-y|^2/blur^2, 1e-8))) */
 #define B200OT_KERNEL_ENERGY 2    /* -sqrt(max(|x-y|^2, 1e-8)) */
 
-const char* b200ot_strerror(int code);
-const char* b200ot_last_cuda_error(void);
-int b200ot_version(void);
+B200OT_API const char* b200ot_strerror(int code);
+B200OT_API const char* b200ot_last_cuda_error(void);
+B200OT_API int b200ot_version(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Softmin  —  out_i = -eps * log sum_j exp( h_j - |x_i - y_j|^p / (p * eps) ),   p in {1, 2}
@@ -56,7 +62,7 @@ int b200ot_version(void);
  * ------------------------------------------------------------------------------------------- */
 
 /* Bytes of scratch needed by b200ot_softmin_fwd / _bwd_x for (N rows, M cols, D). */
-int64_t b200ot_softmin_scratch_bytes(int64_t N, int64_t M, int32_t D);
+B200OT_API int64_t b200ot_softmin_scratch_bytes(int64_t N, int64_t M, int32_t D);
 
 /* One-call softmin:  out (N) <- alpha_old * out_old + beta * softmin(eps, (x, y), h)
  *   h_a (M), h_b (M, nullable):  h_j = h_a[j] + h_scale_b * h_b[j]
@@ -69,7 +75,7 @@ int64_t b200ot_softmin_scratch_bytes(int64_t N, int64_t M, int32_t D);
  *       expansion (improves fp32 conditioning; any point near the data works, zeros if null);
  *   scratch: >= b200ot_softmin_scratch_bytes(N, M, D) bytes, 16-byte aligned.
  */
-int b200ot_softmin_fwd(const float* x, const float* y, const float* h_a, const float* h_b, float h_scale_b,
+B200OT_API int b200ot_softmin_fwd(const float* x, const float* y, const float* h_a, const float* h_b, float h_scale_b,
                        const float* center, const float* out_old, float alpha_old, float beta, float* out,
                        float* lse2_out, int64_t N, int64_t M, int32_t D, int32_t p, float eps, void* scratch,
                        int64_t scratch_bytes, void* stream);
@@ -78,7 +84,7 @@ int b200ot_softmin_fwd(const float* x, const float* y, const float* h_a, const f
  * contract carries: columns and h are detached, sinkhorn_samples.py:179-185, sinkhorn_divergence.py:616-623):
  *   grad_x[i,:] = grad_out[i] * sum_j softmax_j(h_j - C_ij/eps) * dC(x_i, y_j)/dx_i
  * lse2 is the lse2_out of the matching forward call.  grad_x (N,D) is overwritten. */
-int b200ot_softmin_bwd_x(const float* x, const float* y, const float* h_a, const float* h_b, float h_scale_b,
+B200OT_API int b200ot_softmin_bwd_x(const float* x, const float* y, const float* h_a, const float* h_b, float h_scale_b,
                          const float* center, const float* lse2, const float* grad_out, float* grad_x, int64_t N,
                          int64_t M, int32_t D, int32_t p, float eps, void* scratch, int64_t scratch_bytes,
                          void* stream);
@@ -87,37 +93,54 @@ int b200ot_softmin_bwd_x(const float* x, const float* y, const float* h_a, const
 
 /* Number of floats of a packed column buffer for M columns of dimension D with `extra` per-column
  * scalars (softmin: 1 = h; gaussian conv: 2 = -|y|^2/2 and weight; laplacian / energy conv: 1 = weight). */
-int64_t b200ot_packed_cols_floats(int64_t M, int32_t D, int32_t extra);
+B200OT_API int64_t b200ot_packed_cols_floats(int64_t M, int32_t D, int32_t extra);
 
 /* Pack the column cloud for a softmin at temperature eps (coordinates pre-scaled, h folded into the
  * per-column term, padding columns neutral).  cols_out: b200ot_packed_cols_floats(M, D, 1) floats. */
-int b200ot_softmin_pack(const float* y, const float* h_a, const float* h_b, float h_scale_b, const float* center,
+B200OT_API int b200ot_softmin_pack(const float* y, const float* h_a, const float* h_b, float h_scale_b, const float* center,
                         int64_t M, int32_t D, int32_t p, float eps, float* cols_out, void* stream);
 
 /* Number of column splits the partial reduction will use for (N, M, D): partials hold n_split * N pairs. */
-int32_t b200ot_softmin_num_splits(int64_t N, int64_t M, int32_t D);
+B200OT_API int32_t b200ot_softmin_num_splits(int64_t N, int64_t M, int32_t D);
 
 /* Partial reduction over the packed columns: part[(s*N + i)*2 + {0,1}] = (running max m, sum of
  * exp2(t - m)) in the log2 domain, for s < n_split.  This is the kernel that does the N x M work. */
-int b200ot_softmin_partial(const float* x, const float* center, const float* cols, float* part, int32_t n_split,
+B200OT_API int b200ot_softmin_partial(const float* x, const float* center, const float* cols, float* part, int32_t n_split,
                            int64_t N, int64_t M, int32_t D, int32_t p, float eps, void* stream);
+
+/* Collapse n_part partial (m, s) sets into one per row: merged[i*2 + {0,1}].  A rank calls this on its own
+ * splits before exchanging partials with the other column shards (N*8 bytes per rank). */
+B200OT_API int b200ot_softmin_merge(const float* part, int32_t n_part, float* merged, int64_t N, void* stream);
 
 /* Merge n_part partial (m, s) sets (own splits and/or other ranks' shards, concatenated along the
  * leading axis) and apply the epilogue of b200ot_softmin_fwd. */
-int b200ot_softmin_finalize(const float* part, int32_t n_part, const float* out_old, float alpha_old, float beta,
+B200OT_API int b200ot_softmin_finalize(const float* part, int32_t n_part, const float* out_old, float alpha_old, float beta,
                             float* out, float* lse2_out, int64_t N, float eps, void* stream);
+
+/* --- stages of b200ot_softmin_bwd_x, for column-sharded use: per-shard partial sums
+ *     part[(s*N + i)*(D+1) + {0: sum_j w_ij, 1+k: sum_j w_ij * (coordinate or unit-vector term)}],
+ *     which add across shards (all-reduce SUM) before the finalize --- */
+B200OT_API int b200ot_softmin_bwd_partial(const float* x, const float* center, const float* cols, const float* lse2,
+                                          float* part, int32_t n_split, int64_t N, int64_t M, int32_t D, int32_t p,
+                                          float eps, void* stream);
+/* merged[i*width + a] = sum_s part[(s*N + i)*width + a] */
+B200OT_API int b200ot_rowsum_merge(const float* part, int32_t n_part, int32_t width, float* merged, int64_t N,
+                                   void* stream);
+B200OT_API int b200ot_softmin_bwd_finalize(const float* part, int32_t n_part, const float* x, const float* center,
+                                           const float* grad_out, float* grad_x, int64_t N, int32_t D, int32_t p,
+                                           float eps, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Kernel convolution  —  out_i = sum_j k(x_i, y_j) * w_j      (kernel_samples.py:128-137)
  * ------------------------------------------------------------------------------------------- */
-int64_t b200ot_kernel_conv_scratch_bytes(int64_t N, int64_t M, int32_t D);
+B200OT_API int64_t b200ot_kernel_conv_scratch_bytes(int64_t N, int64_t M, int32_t D);
 
-int b200ot_kernel_conv_fwd(const float* x, const float* y, const float* w, const float* center, float* out,
+B200OT_API int b200ot_kernel_conv_fwd(const float* x, const float* y, const float* w, const float* center, float* out,
                            int64_t N, int64_t M, int32_t D, int32_t kind, float blur, void* scratch,
                            int64_t scratch_bytes, void* stream);
 
 /* grad_x[i,:] = grad_out[i] * sum_j w_j * d k(x_i, y_j) / d x_i   (rows only; columns via a swapped call) */
-int b200ot_kernel_conv_bwd_x(const float* x, const float* y, const float* w, const float* center,
+B200OT_API int b200ot_kernel_conv_bwd_x(const float* x, const float* y, const float* w, const float* center,
                              const float* grad_out, float* grad_x, int64_t N, int64_t M, int32_t D, int32_t kind,
                              float blur, void* scratch, int64_t scratch_bytes, void* stream);
 
@@ -129,7 +152,7 @@ int b200ot_kernel_conv_bwd_x(const float* x, const float* y, const float* w, con
 #define B200OT_UBENCH_MUFU_EX2 0
 #define B200OT_UBENCH_FFMA 1
 #define B200OT_UBENCH_FFMA2 2
-int b200ot_ubench(int32_t which, int32_t iters, int32_t blocks, float* sink, int32_t* ops_per_thread_iter,
+B200OT_API int b200ot_ubench(int32_t which, int32_t iters, int32_t blocks, float* sink, int32_t* ops_per_thread_iter,
                   void* stream);
 
 #ifdef __cplusplus

@@ -1,0 +1,88 @@
+"""CPU-only checks of the C-ABI library: it loads, exports every symbol include/b200ot.h declares, and its
+argument validation (which runs before any CUDA call) returns the documented error codes."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from geomloss_b200 import _build, _lib
+
+
+@pytest.fixture(scope="module")
+def L():
+    _build.build()
+    return _lib.lib()
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "b200ot.h")).read()
+    return sorted(set(re.findall(r"B200OT_API\s+[\w\s\*]+?\b(b200ot_\w+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert _declared() == _lib.exported_symbols()
+
+
+def test_every_declared_symbol_is_exported(L):
+    for name in _declared():
+        assert hasattr(L, name), name
+
+
+def test_version_and_strerror(L):
+    assert L.b200ot_version() == 100
+    assert L.b200ot_strerror(0) == b"ok"
+    assert b"invalid" in L.b200ot_strerror(-1)
+    assert b"scratch" in L.b200ot_strerror(-2)
+    assert b"unknown" in L.b200ot_strerror(-99)
+
+
+def test_size_queries_are_pure(L):
+    # pack padding: 1024 columns; D=3 softmin packets are 8 floats per column pair
+    assert L.b200ot_packed_cols_floats(1000, 3, 1) == 1024 // 2 * 8
+    assert L.b200ot_packed_cols_floats(1025, 3, 1) == 2048 // 2 * 8
+    assert L.b200ot_packed_cols_floats(1000, 3, 2) == 1024 // 2 * 12
+    assert L.b200ot_packed_cols_floats(1000, 1, 1) == 1024 // 2 * 4
+    assert L.b200ot_packed_cols_floats(0, 3, 1) == 0
+    n = L.b200ot_softmin_num_splits(10**6, 10**6, 3)
+    assert 1 <= n <= 64
+    assert L.b200ot_softmin_scratch_bytes(10**6, 10**6, 3) >= L.b200ot_packed_cols_floats(10**6, 3, 1) * 4
+    assert L.b200ot_softmin_scratch_bytes(0, 5, 3) == 0
+
+
+def test_argument_validation_needs_no_gpu(L):
+    null = ctypes.c_void_p(None)
+    fake = ctypes.c_void_p(0x1000)
+    # null pointers / bad sizes / bad p / bad eps -> EINVAL, before any CUDA call
+    assert L.b200ot_softmin_fwd(null, fake, fake, null, 0.0, null, null, 0.0, 1.0, fake, null, 10, 10, 3, 2, 0.1,
+                                fake, 1 << 30, null) == -1
+    assert L.b200ot_softmin_fwd(fake, fake, fake, null, 0.0, null, null, 0.0, 1.0, fake, null, 10, 10, 3, 3, 0.1,
+                                fake, 1 << 30, null) == -1
+    assert L.b200ot_softmin_fwd(fake, fake, fake, null, 0.0, null, null, 0.0, 1.0, fake, null, 10, 10, 3, 2, -1.0,
+                                fake, 1 << 30, null) == -1
+    assert L.b200ot_softmin_fwd(fake, fake, fake, null, 0.0, null, null, 0.0, 1.0, fake, null, 10, 10, 99, 2, 0.1,
+                                fake, 1 << 30, null) == -1
+    # scratch too small -> ESCRATCH; misaligned scratch -> EALIGN
+    assert L.b200ot_softmin_fwd(fake, fake, fake, null, 0.0, null, null, 0.0, 1.0, fake, null, 10, 10, 3, 2, 0.1,
+                                fake, 16, null) == -2
+    assert L.b200ot_softmin_fwd(fake, fake, fake, null, 0.0, null, null, 0.0, 1.0, fake, null, 10, 10, 3, 2, 0.1,
+                                ctypes.c_void_p(0x1004), 1 << 30, null) == -4
+    assert L.b200ot_kernel_conv_fwd(fake, fake, fake, null, fake, 10, 10, 3, 7, 0.1, fake, 1 << 30, null) == -1
+    assert L.b200ot_kernel_conv_fwd(fake, fake, fake, null, fake, 10, 10, 3, 0, 0.0, fake, 1 << 30, null) == -1
+    assert L.b200ot_softmin_finalize(null, 1, null, 0.0, 1.0, fake, null, 10, 0.1, null) == -1
+    assert L.b200ot_softmin_merge(fake, 0, fake, 10, null) == -1
+
+
+def test_product_requires_cuda_tensors():
+    """The host wrappers refuse CPU tensors instead of falling back to a CPU implementation."""
+    import torch
+
+    from geomloss_b200 import SamplesLoss
+
+    x = torch.rand(10, 3)
+    y = torch.rand(12, 3)
+    with pytest.raises(_lib.B200OTError):
+        SamplesLoss("sinkhorn")(x, y)
+    with pytest.raises(_lib.B200OTError):
+        SamplesLoss("gaussian")(x, y)

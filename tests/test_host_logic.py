@@ -1,0 +1,117 @@
+"""CPU tests of the host-side mirror of the reference interface (no kernel runs here):
+schedule, scalar helpers, dual-to-value formulas, SamplesLoss argument handling and error behaviour."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from geomloss_b200 import SamplesLoss
+from geomloss_b200 import sinkhorn as S
+from oracle import geomloss_oracle as O
+
+
+def test_epsilon_schedule_matches_reference_goldens():
+    g = load_golden("epsilon_schedule")
+    for i in range(4):
+        p, diam, blur, scaling = g[f"args{i}"]
+        got = np.array(S.epsilon_schedule(int(p), diam, blur, scaling))
+        np.testing.assert_allclose(got, g[f"eps{i}"], rtol=1e-15)
+    assert len(S.epsilon_schedule(2, 3**0.5, 0.01, 0.9)) == 51  # "~50 iters" of BASELINE cfg 2
+
+
+def test_scalar_helpers_match_oracle():
+    a = torch.tensor([0.0, 0.25, 0.75, -1.0])
+    np.testing.assert_array_equal(S.log_weights(a).numpy(), O.log_weights(a.clone()).numpy())
+    assert S.damping(0.3, None) == 1.0 and abs(S.damping(0.3, 0.2) - 1 / (1 + 0.3 / 0.2)) < 1e-15
+    x, y = torch.rand(50, 3), torch.rand(40, 3) + 0.5
+    assert abs(S.max_diameter(x, y) - O.max_diameter(x, y)) < 1e-7
+    d, eps, lst, rho = S.scaling_parameters(x, y, 2, 0.05, 0.3, None, 0.5)
+    d2, eps2, lst2, rho2 = O.scaling_parameters(x, y, 2, 0.05, 0.3, None, 0.5)
+    assert (d, eps, rho) == (d2, eps2, rho2) and np.allclose(lst, lst2, rtol=1e-15)
+
+
+@pytest.mark.parametrize("rho", [None, 0.09])
+@pytest.mark.parametrize("debias", [True, False])
+def test_sinkhorn_cost_matches_oracle(rho, debias):
+    g = torch.Generator().manual_seed(3)
+    n, m = 17, 23
+    a, b = torch.rand(n, generator=g), torch.rand(m, generator=g)
+    f_aa, f_ba = torch.rand(n, generator=g), torch.rand(n, generator=g)
+    g_bb, g_ab = torch.rand(m, generator=g), torch.rand(m, generator=g)
+    got = S.sinkhorn_cost(0.01, rho, a, b, f_aa, g_bb, g_ab, f_ba, debias=debias)
+    ref = O.sinkhorn_value(0.01, rho, a[None], b[None], f_aa[None], g_bb[None], g_ab[None], f_ba[None],
+                           debias=debias)[0]
+    assert abs(got.item() - ref.item()) < 1e-6
+    F, G = S.sinkhorn_cost(0.01, rho, a, b, f_aa, g_bb, g_ab, f_ba, debias=debias, potentials=True)
+    Fr, Gr = O.sinkhorn_value(0.01, rho, a, b, f_aa, g_bb, g_ab, f_ba, debias=debias, potentials=True)
+    assert torch.equal(F, Fr) and torch.equal(G, Gr)
+
+
+def test_constructor_keeps_reference_signature():
+    L = SamplesLoss()
+    assert (L.loss, L.p, L.blur, L.reach, L.diameter, L.scaling, L.truncate, L.cost, L.kernel, L.cluster_scale,
+            L.debias, L.potentials, L.verbose, L.backend) == ("sinkhorn", 2, 0.05, None, None, 0.5, 5, None, None,
+                                                              None, True, False, False, "auto")
+    L = SamplesLoss("gaussian", blur=0.3, backend="online", potentials=True)
+    assert L.loss == "gaussian" and L.blur == 0.3 and L.backend == "online" and L.potentials
+
+
+def test_argument_forms_and_shape_errors():
+    L = SamplesLoss()
+    x, y = torch.rand(5, 3), torch.rand(7, 3)
+    with pytest.raises(ValueError, match="two .* four .* or six"):
+        L.process_args(x, y, x)
+    l_x, a, xx, l_y, b, yy = L.process_args(x, y)
+    assert l_x is None and l_y is None and torch.allclose(a, torch.full((5,), 0.2)) and b.shape == (7,)
+    assert L.generate_weights(torch.rand(2, 4, 3)).shape == (2, 4)
+    with pytest.raises(ValueError):
+        L.generate_weights(torch.rand(4))
+    # shape rules (samples_loss.py:337-474)
+    with pytest.raises(ValueError, match="same last dimension"):
+        L.check_shapes(None, a, x, None, b, torch.rand(7, 2))
+    with pytest.raises(ValueError, match="same number of dimensions"):
+        L.check_shapes(None, a, x, None, b, torch.rand(1, 7, 3))
+    with pytest.raises(ValueError, match="compatible shapes"):
+        L.check_shapes(None, torch.rand(4), x, None, b, y)
+    with pytest.raises(ValueError, match=r"\(N,\) or \(N,1\)"):
+        L.check_shapes(None, torch.rand(5, 2), x, None, torch.rand(7, 2), y)
+    B, N, M, D, _, a2, _, b2 = L.check_shapes(None, a.view(-1, 1), x, None, b.view(-1, 1), y)
+    assert (B, N, M, D) == (0, 5, 7, 3) and a2.shape == (5,) and b2.shape == (7,)
+    xb, yb = torch.rand(2, 5, 3), torch.rand(2, 7, 3)
+    B, N, M, D, _, a3, _, b3 = L.check_shapes(None, torch.rand(2, 5, 1), xb, None, torch.rand(2, 7, 1), yb)
+    assert (B, N, M, D) == (2, 5, 7, 3) and a3.shape == (2, 5)
+    with pytest.raises(ValueError, match="same batchsize"):
+        L.check_shapes(None, torch.rand(2, 5), xb, None, torch.rand(2, 7), torch.rand(3, 7, 3))
+    with pytest.raises(NotImplementedError):
+        L.check_shapes(torch.zeros(2, 5), torch.rand(2, 5), xb, None, torch.rand(2, 7), yb)
+    with pytest.raises(ValueError, match="labels 'l_x'"):
+        L.check_shapes(torch.zeros(4), a, x, None, b, y)
+
+
+def test_routing_errors_match_reference():
+    x, y = torch.rand(5, 3), torch.rand(7, 3)
+    a, b = torch.full((5,), 0.2), torch.full((7,), 1 / 7)
+    with pytest.raises(ValueError, match="Explicit cluster labels"):
+        SamplesLoss(backend="online")(torch.zeros(5), a, x, torch.zeros(7), b, y)
+    with pytest.raises(KeyError):  # the reference dies with KeyError(None) for hausdorff (SURVEY A-13)
+        SamplesLoss("hausdorff")(x, y)
+    with pytest.raises(KeyError):
+        SamplesLoss("nonsense")(x, y)
+    with pytest.raises(KeyError):
+        SamplesLoss("sinkhorn", p=3)(x, y)
+    with pytest.raises(NotImplementedError):
+        SamplesLoss("sinkhorn", cost=lambda u, v: u)(x, y)
+
+
+def test_product_never_touches_the_oracle_or_a_cpu_fallback():
+    """Only tests/, __graft_entry__.smoke() and bench.py's baseline legs may use oracle/."""
+    pkg = os.path.join(ROOT, "geomloss_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), f
+                assert "geomloss_oracle" not in text, f

@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -90,6 +91,62 @@ __global__ void __launch_bounds__(256) ub_mufu_ffma(int iters, float* sink) {
   for (int u = 0; u < U; ++u) s += v[u] + w[u];
   if (s == 123.456f) sink[0] = s;
 }
+// K integer adds (alu pipe) per FFMA2: does a packed FMA take one issue slot or two?
+template <int K>
+__global__ void __launch_bounds__(256) ub_ffma2_iadd(int iters, float* sink) {
+  float2 w[U];
+  int q[U];
+  const float2 a = make_float2(0.999f, 0.998f), b = make_float2(1e-3f, 2e-3f);
+  for (int u = 0; u < U; ++u) w[u] = make_float2(0.001f * (threadIdx.x + u), 0.5f), q[u] = threadIdx.x + u;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      w[u] = __ffma2_rn(w[u], a, b);
+#pragma unroll
+      for (int k = 0; k < K; ++k) q[u] = (q[u] ^ (it + k)) + 0x9e3779b9;
+    }
+  }
+  float s = 0;
+  for (int u = 0; u < U; ++u) s += w[u].x + w[u].y + (float)q[u];
+  if (s == 123.456f) sink[0] = s;
+}
+template <int K>
+__global__ void __launch_bounds__(256) ub_ffma_iadd(int iters, float* sink) {
+  float w[U];
+  int q[U];
+  const float a = 0.999f + 1e-6f * threadIdx.x, b = 1e-3f * threadIdx.x;
+  for (int u = 0; u < U; ++u) w[u] = 0.001f * (threadIdx.x + u), q[u] = threadIdx.x + u;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      w[u] = fmaf(w[u], a, b);
+#pragma unroll
+      for (int k = 0; k < K; ++k) q[u] = (q[u] ^ (it + k)) + 0x9e3779b9;
+    }
+  }
+  float s = 0;
+  for (int u = 0; u < U; ++u) s += w[u] + (float)q[u];
+  if (s == 123.456f) sink[0] = s;
+}
+// MUFU + K register-operand scalar FFMA
+template <int K>
+__global__ void __launch_bounds__(256) ub_mufu_ffma_reg(int iters, float* sink) {
+  float v[U];
+  float w[U];
+  const float a = 0.999f + 1e-6f * threadIdx.x, b = 1e-3f * threadIdx.x;
+  for (int u = 0; u < U; ++u) v[u] = -0.001f * (threadIdx.x + u), w[u] = v[u];
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      v[u] = ex2_approx(v[u]) - 1.0f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) w[u] = fmaf(w[u], a, b);
+    }
+  }
+  float s = 0;
+  for (int u = 0; u < U; ++u) s += v[u] + w[u];
+  if (s == 123.456f) sink[0] = s;
+}
 __global__ void __launch_bounds__(256) ub_expoly(int iters, float* sink) {
   float2 v[U];
   for (int u = 0; u < U; ++u) v[u] = make_float2(-0.001f * (threadIdx.x + u), -0.002f * (threadIdx.x + u));
@@ -157,8 +214,11 @@ struct Problem {
   std::vector<float> hx, hy, hh;
 };
 
+static const char* g_filter = nullptr;
+
 template <class C>
 static void run_variant(const char* name, Problem& P, int reps) {
+  if (g_filter && !strstr(name, g_filter)) return;
   const int D = C::D;
   const int p = C::P;
   const int64_t mpad = round_up64(P.M, 1024);
@@ -174,7 +234,7 @@ static void run_variant(const char* name, Problem& P, int reps) {
   const float clampq = scale * scale * 1e-8f;
 
   pack_cols_kernel<<<(unsigned)ceil_div64(mpad, 256), 256>>>(P.y, P.h, nullptr, 0.f, kLog2e, nullptr, P.center,
-                                                              scale, C::DIRECT ? 1 : 0, D, 1, C::NF2, P.M, mpad,
+                                                              scale, C::DIRECT ? 1 : 0, D, C::NF2, P.M, mpad,
                                                               P.cols);
   CK(cudaGetLastError());
   auto kern = softmin_partial_kernel<C>;
@@ -235,6 +295,7 @@ int main(int argc, char** argv) {
   const int64_t M = argc > 2 ? atoll(argv[2]) : 200000;
   const float eps = argc > 3 ? (float)atof(argv[3]) : 1e-4f;
   const int reps = argc > 4 ? atoi(argv[4]) : 3;
+  g_filter = argc > 5 ? argv[5] : nullptr;
 
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
@@ -247,7 +308,7 @@ int main(int argc, char** argv) {
 
   float* sink;
   CK(cudaMalloc(&sink, 1024));
-  {
+  if (!g_filter) {
     const int iters = 4096, blocks = sms * 8;
     int ops = 0;
     double ms;
@@ -273,6 +334,18 @@ int main(int argc, char** argv) {
     report_ub("mufu+3ffma2 (exps)", ms, U, iters, blocks, sms, clk_mhz);
     ms = time_kernel([&]() { ub_mufu_ffma2<4><<<blocks, 256>>>(iters, sink); });
     report_ub("mufu+4ffma2 (exps)", ms, U, iters, blocks, sms, clk_mhz);
+    ms = time_kernel([&]() { ub_ffma2_iadd<1><<<blocks, 256>>>(iters, sink); });
+    report_ub("ffma2+1x(xor,add) (ffma2 instrs)", ms, U, iters, blocks, sms, clk_mhz);
+    ms = time_kernel([&]() { ub_ffma2_iadd<2><<<blocks, 256>>>(iters, sink); });
+    report_ub("ffma2+2x(xor,add) (ffma2 instrs)", ms, U, iters, blocks, sms, clk_mhz);
+    ms = time_kernel([&]() { ub_ffma_iadd<1><<<blocks, 256>>>(iters, sink); });
+    report_ub("ffma+1x(xor,add) (ffma instrs)", ms, U, iters, blocks, sms, clk_mhz);
+    ms = time_kernel([&]() { ub_mufu_ffma_reg<2><<<blocks, 256>>>(iters, sink); });
+    report_ub("mufu+2ffma(reg) (exps)", ms, U, iters, blocks, sms, clk_mhz);
+    ms = time_kernel([&]() { ub_mufu_ffma_reg<4><<<blocks, 256>>>(iters, sink); });
+    report_ub("mufu+4ffma(reg) (exps)", ms, U, iters, blocks, sms, clk_mhz);
+    ms = time_kernel([&]() { ub_mufu_ffma_reg<6><<<blocks, 256>>>(iters, sink); });
+    report_ub("mufu+6ffma(reg) (exps)", ms, U, iters, blocks, sms, clk_mhz);
     ms = time_kernel([&]() { ub_mufu_ffma<4><<<blocks, 256>>>(iters, sink); });
     report_ub("mufu+4ffma (exps)", ms, U, iters, blocks, sms, clk_mhz);
     ms = time_kernel([&]() { ub_mufu_ffma<6><<<blocks, 256>>>(iters, sink); });
@@ -308,18 +381,27 @@ int main(int argc, char** argv) {
   const float ctr[16] = {0.5f, 0.5f, 0.5f};
   CK(cudaMemcpy(P.center, ctr, 64, cudaMemcpyHostToDevice));
 
-  run_variant<SoftminCfg<3, 4, 2, false, 0, 256, 1024, 3, 4, 2>>("expand R4 CH4", P, reps);
-  run_variant<SoftminCfg<3, 2, 2, false, 0, 256, 1024, 3, 4, 2>>("expand R2 CH4", P, reps);
-  run_variant<SoftminCfg<3, 2, 2, false, 0, 256, 1024, 3, 8, 2>>("expand R2 CH8", P, reps);
-  run_variant<SoftminCfg<3, 4, 2, false, 0, 256, 1024, 3, 2, 2>>("expand R4 CH2", P, reps);
-  run_variant<SoftminCfg<3, 4, 2, false, 1, 256, 1024, 3, 4, 2>>("expand R4 CH4 poly25", P, reps);
-  run_variant<SoftminCfg<3, 4, 2, false, 2, 256, 1024, 3, 4, 2>>("expand R4 CH4 poly12", P, reps);
-  run_variant<SoftminCfg<3, 2, 2, false, 1, 256, 1024, 3, 8, 2>>("expand R2 CH8 poly12", P, reps);
-  run_variant<SoftminCfg<3, 4, 2, false, 0, 512, 1024, 3, 4, 1>>("expand R4 NT512 occ1", P, reps);
-  run_variant<SoftminCfg<3, 8, 2, false, 0, 128, 1024, 3, 2, 2>>("expand R8 NT128 CH2", P, reps);
-  run_variant<SoftminCfg<3, 4, 2, true, 0, 256, 1024, 3, 4, 2>>("direct R4 CH4", P, reps);
-  run_variant<SoftminCfg<3, 2, 2, true, 0, 256, 1024, 3, 4, 2>>("direct R2 CH4", P, reps);
-  run_variant<SoftminCfg<3, 2, 1, true, 0, 256, 1024, 3, 4, 2>>("p1 direct R2 CH4", P, reps);
-  run_variant<SoftminCfg<3, 1, 2, false, 0, 128, 256, 3, 4, 4>>("expand small R1", P, reps);
+  run_variant<SoftminCfg<3, 4, 2, false, 0u, 256, 1024, 3, 4, 2>>("expand R4 CH4", P, reps);
+  run_variant<SoftminCfg<3, 4, 2, false, 0u, 256, 1024, 3, 8, 2>>("expand R4 CH8", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0u, 256, 1024, 3, 8, 2>>("expand R2 CH8", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0u, 256, 1024, 3, 4, 3>>("expand R2 CH4 occ3", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0u, 128, 1024, 3, 8, 4>>("expand R2 NT128 CH8 occ4", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0u, 128, 1024, 3, 4, 6>>("expand R2 NT128 CH4 occ6", P, reps);
+  run_variant<SoftminCfg<3, 1, 2, false, 0u, 256, 1024, 3, 8, 4>>("expand R1 NT256 CH8 occ4", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0u, 512, 1024, 3, 8, 1>>("expand R2 NT512 CH8 occ1", P, reps);
+  run_variant<SoftminCfg<3, 3, 2, false, 0u, 256, 1024, 3, 8, 2>>("expand R3 CH8", P, reps);
+  run_variant<SoftminCfg<3, 8, 2, false, 0u, 256, 1024, 3, 4, 1>>("expand R8 CH4 occ1", P, reps);
+  run_variant<SoftminCfg<3, 8, 2, false, 0u, 128, 1024, 3, 4, 2>>("expand R8 NT128 CH4", P, reps);
+  run_variant<SoftminCfg<3, 4, 2, false, 0u, 512, 1024, 3, 8, 1>>("expand R4 NT512 CH8 occ1", P, reps);
+  run_variant<SoftminCfg<3, 4, 2, false, 0x01u, 256, 1024, 3, 8, 2>>("expand R4 CH8 poly1/8", P, reps);
+  run_variant<SoftminCfg<3, 4, 2, false, 0x11u, 256, 1024, 3, 8, 2>>("expand R4 CH8 poly2/8", P, reps);
+  run_variant<SoftminCfg<3, 4, 2, false, 0x0421u, 256, 1024, 3, 16, 2>>("expand R4 CH16 poly3/16", P, reps);
+  run_variant<SoftminCfg<3, 8, 2, false, 0x0421u, 128, 1024, 3, 16, 2>>("expand R8 NT128 CH16 poly3/16", P, reps);
+  run_variant<SoftminCfg<3, 4, 2, false, 0x1111u, 256, 1024, 3, 16, 2>>("expand R4 CH16 poly4/16", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x0421u, 256, 1024, 3, 16, 3>>("expand R2 CH16 poly3/16 occ3", P, reps);
+  run_variant<SoftminCfg<3, 4, 2, true, 0u, 256, 1024, 3, 4, 2>>("direct R4 CH4", P, reps);
+  run_variant<SoftminCfg<3, 2, 1, true, 0u, 256, 1024, 3, 4, 2>>("p1 direct R2 CH4", P, reps);
+  run_variant<SoftminCfg<3, 4, 1, true, 0u, 256, 1024, 3, 4, 2>>("p1 direct R4 CH4", P, reps);
+  run_variant<SoftminCfg<3, 1, 2, false, 0u, 128, 256, 3, 4, 4>>("expand small R1", P, reps);
   return 0;
 }
