@@ -1,0 +1,457 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native Sinkhorn engine (contract: see DESIGN.md section 6).
+
+Metric (BASELINE.json): Sinkhorn N x M pair-interactions / second, N = M = 1e6, D = 3, p = 2, blur = .01
+(configs[1]).  One pair-interaction = one evaluation of exp(h_j - C(x_i, y_j)/eps) accumulated into row i.
+
+A "step" is ONE symmetric Sinkhorn iteration at the final temperature eps = blur^2 on the full clouds:
+the four softmins  xy, yx, xx, yy  with the fused  h = log_w + pot/eps  prologue and  1/2 (f + f~)
+epilogue (src/geomloss/_legacy/sinkhorn_divergence.py:468-493 of the reference) = 2NM + N^2 + M^2 pairs.
+A full loss of configs[1] is 53 such iteration-equivalents (212 softmins); the instruction stream does
+not depend on eps, so the step rate is the loss rate.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, libb200ot.so)
+    python bench.py --impl reference [--steps K] [--warmup W]      the reference's dense CPU algorithm
+                                                                   (oracle port) on the host cores
+
+Multi-GPU: one process per GPU (torchrun); the column cloud of every softmin is sharded over the ranks,
+one all_gather of (N, 2) partials per softmin (geomloss_b200/distributed.py).  Total work is fixed:
+strong scaling.  Timing: CUDA events on the compute stream around every step, L2 flushed between
+steps, barrier + synchronize on both sides of the timed region, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sinkhorn_pair_interactions_per_second"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000, help="points per cloud (N = M)")
+    ap.add_argument("--blur", type=float, default=0.01)
+    ap.add_argument("--e2e-steps", type=int, default=2, help="full SamplesLoss calls timed end to end")
+    ap.add_argument("--e2e-scaling", type=float, default=0.5)
+    ap.add_argument("--cpu-n", type=int, default=16000, help="cloud size of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks: sample SM clock / throttle reasons DURING the timed region (NVML, 100 ms period)
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.power = [], set(), []
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as exc:  # pragma: no cover
+            self.nv = None
+            self.err = repr(exc)
+
+    _NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+              0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+              0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self._NAMES.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "no NVML samples"}
+        return {"sm_mhz": statistics.median(self.samples), "sm_min_mhz": min(self.samples),
+                "sm_max_mhz": self.max_mhz, "power_w_max": round(max(self.power), 1),
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# the reference arm: the reference's dense CPU algorithm (oracle port) on the host cores
+# ----------------------------------------------------------------------------------------------------
+def dense_iteration_state(n, blur, seed=0):
+    import torch
+
+    from oracle import geomloss_oracle as O
+
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(n, 3, generator=g)
+    y = torch.rand(n, 3, generator=g)
+    a_log = torch.full((1, n), -float(torch.log(torch.tensor(float(n)))))
+    eps = blur**2
+    xb, yb = x[None], y[None]
+    C = dict(xy=O.cost_matrix(xb, yb, 2), yx=O.cost_matrix(yb, xb, 2), xx=O.cost_matrix(xb, xb, 2),
+             yy=O.cost_matrix(yb, yb, 2))
+    pots = {k: O.softmin_dense(eps, C[c], a_log) for k, c in (("f_ba", "xy"), ("g_ab", "yx"), ("f_aa", "xx"),
+                                                               ("g_bb", "yy"))}
+    return O, eps, a_log, C, pots
+
+
+def dense_iteration(O, eps, a_log, C, p):
+    """One symmetric Sinkhorn iteration of the reference on stored cost matrices (4 dense softmins)."""
+    ft_ba = O.softmin_dense(eps, C["xy"], a_log + p["g_ab"] / eps)
+    gt_ab = O.softmin_dense(eps, C["yx"], a_log + p["f_ba"] / eps)
+    ft_aa = O.softmin_dense(eps, C["xx"], a_log + p["f_aa"] / eps)
+    gt_bb = O.softmin_dense(eps, C["yy"], a_log + p["g_bb"] / eps)
+    return dict(f_ba=0.5 * (p["f_ba"] + ft_ba), g_ab=0.5 * (p["g_ab"] + gt_ab), f_aa=0.5 * (p["f_aa"] + ft_aa),
+                g_bb=0.5 * (p["g_bb"] + gt_bb))
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs and prints the reference line
+    n = args.cpu_n
+    O, eps, a_log, C, pots = dense_iteration_state(n, args.blur)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            pots = dense_iteration(O, eps, a_log, C, pots)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pots = dense_iteration(O, eps, a_log, C, pots)
+        dt = time.perf_counter() - t0
+    pairs = 4.0 * n * n
+    value = pairs * args.steps / dt
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1] single-scale Sinkhorn, D=3 p=2 blur=%g; step = one symmetric Sinkhorn "
+                               "iteration (4 dense softmins on stored N x N cost matrices), bounded sample "
+                               "N=M=%d of the N=M=1e6 problem (4 TB per cost matrix at full size)" % (args.blur, n),
+                   "N": n, "M": n, "D": 3, "pairs_per_step": pairs},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"N=M={n}, {args.steps} dense Sinkhorn iterations, torch CPU {cores} threads, "
+                                   f"{cpu_model()}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from geomloss_b200 import SamplesLoss, _lib, ops
+    from geomloss_b200.sinkhorn import epsilon_schedule
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torchrun (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    L = _lib.lib()  # fails loudly if libb200ot.so is missing
+    engine = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        from geomloss_b200.distributed import ColumnShardedEngine
+
+        engine = ColumnShardedEngine()
+    sm = engine.softmin_raw if engine else ops.softmin_raw
+
+    N = M = args.n
+    D, p = 3, 2
+    eps = args.blur**2
+    g = torch.Generator().manual_seed(0)
+    x_h = torch.rand(N, D, generator=g).pin_memory()
+    y_h = torch.rand(M, D, generator=g).pin_memory()
+    x, y = x_h.to(dev), y_h.to(dev)
+    a_log = torch.full((N,), -float(torch.log(torch.tensor(float(N)))), device=dev)
+    b_log = torch.full((M,), -float(torch.log(torch.tensor(float(M)))), device=dev)
+    center = ops.default_center(x, y)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    # potentials: the reference's initialisation at this temperature (sinkhorn_divergence.py:461-465)
+    pots = {"f_ba": sm(eps, x, y, b_log, p=p, center=center)[0], "g_ab": sm(eps, y, x, a_log, p=p, center=center)[0],
+            "f_aa": sm(eps, x, x, a_log, p=p, center=center)[0], "g_bb": sm(eps, y, y, b_log, p=p, center=center)[0]}
+    inv = 1.0 / eps
+
+    def step(pt):
+        new = {
+            "f_ba": sm(eps, x, y, b_log, pt["g_ab"], inv, p=p, center=center, out_old=pt["f_ba"], alpha_old=0.5,
+                       beta=0.5)[0],
+            "g_ab": sm(eps, y, x, a_log, pt["f_ba"], inv, p=p, center=center, out_old=pt["g_ab"], alpha_old=0.5,
+                       beta=0.5)[0],
+            "f_aa": sm(eps, x, x, a_log, pt["f_aa"], inv, p=p, center=center, out_old=pt["f_aa"], alpha_old=0.5,
+                       beta=0.5)[0],
+            "g_bb": sm(eps, y, y, b_log, pt["g_bb"], inv, p=p, center=center, out_old=pt["g_bb"], alpha_old=0.5,
+                       beta=0.5)[0],
+        }
+        return new
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    pairs_per_step = 2.0 * N * M + float(N) * N + float(M) * M
+    for _ in range(max(args.warmup, 3)):
+        pots = step(pots)
+    sync_all()
+
+    # ---- timed region: K steps, per-step CUDA events, L2 flushed between steps ----
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = ops.launches()
+    sampler = ClockSampler(local_rank)
+    with sampler:
+        sync_all()
+        for k in range(args.steps):
+            flush.zero_()
+            ev[k][0].record()
+            pots = step(pots)
+            ev[k][1].record()
+        sync_all()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = total_ms.item()
+    gpu_launches = ops.launches() - launches0
+    value = pairs_per_step * args.steps / (total_ms * 1e-3)
+    finite = bool(torch.isfinite(pots["f_ba"]).all().item())
+
+    # ---- dominant kernel alone: staged calls, CUDA events around the partial-reduction launch ----
+    kern = kernel_pass(L, ops, torch, dev, x, y, b_log, pots["g_ab"], inv, center, eps, p, flush, reps=max(3, args.steps // 2),
+                       world=world, rank=rank)
+    # ---- MUFU / FP32 ceilings of this device, measured now ----
+    ceil = pipe_ceilings(L, ops, torch, dev)
+
+    # ---- end to end through the public API with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        loss = SamplesLoss("sinkhorn", p=2, blur=args.blur, scaling=args.e2e_scaling, diameter=3**0.5)
+        if engine:
+            engine.attach(loss)
+        n_eps = len(epsilon_schedule(2, 3**0.5, args.blur, args.e2e_scaling))
+        pairs_loss = (n_eps + 2) * pairs_per_step
+
+        def e2e_call():
+            xd = x_h.to(dev, non_blocking=True)
+            yd = y_h.to(dev, non_blocking=True)
+            return loss(xd, yd).item()  # .item(): device -> host read of the result
+
+        e2e_call()  # warm-up
+        sync_all()
+        t0 = time.perf_counter()
+        vals = [e2e_call() for _ in range(args.e2e_steps)]
+        sync_all()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": pairs_loss * args.e2e_steps / dt.item(), "unit": UNIT,
+               "h2d_bytes_per_step": int(x_h.numel() * 4 + y_h.numel() * 4), "d2h_bytes_per_step": 4,
+               "call": f"SamplesLoss('sinkhorn', p=2, blur={args.blur}, scaling={args.e2e_scaling}, diameter=sqrt(3))"
+                       f"(x_host->cuda, y_host->cuda).item(): {n_eps} eps values, {4 * (n_eps + 2)} softmins",
+               "s_per_call": dt.item() / args.e2e_steps, "loss_value": vals[-1]}
+
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args)
+
+    if rank == 0:
+        clocks = sampler.summary()
+        mufu_peak = ceil["mufu_ex2_per_s"]
+        k_rate = kern["pairs_per_s"]
+        traffic = None
+        tfile = os.path.join(ROOT, "profiles", "softmin_partial_ncu_summary.json")
+        if os.path.exists(tfile):
+            try:
+                traffic = json.load(open(tfile)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        alg_bytes = 4.0 * ((N + M / world) * (D + 1))  # compulsory HBM bytes per softmin launch
+        peaks = {}
+        pfile = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pfile):
+            peaks = json.load(open(pfile))
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": "configs[1]: single-scale Sinkhorn N=M=%d D=3 p=2 blur=%g on uniform-in-cube clouds; "
+                            "step = one symmetric Sinkhorn iteration = 4 softmins (xy, yx, xx, yy) with fused "
+                            "prologue/epilogue" % (N, args.blur),
+                "N": N, "M": M, "D": D, "p": p, "blur": args.blur, "pairs_per_step": pairs_per_step,
+                "l2": "flushed between timed steps (256 MiB write); inputs (40 MB) are smaller than L2 by nature",
+                "parallelism": "single GPU" if world == 1 else f"columns of every softmin sharded x{world}, "
+                                                                "1 all_gather of (N,2) fp32 per softmin",
+                "finite": finite,
+            },
+            "e2e": e2e,
+            "gpu_launches": gpu_launches,
+            "clocks": clocks,
+            "roofline": {
+                "bound": "sfu",
+                "kernel": "softmin_partial_kernel (1 MUFU.EX2 per pair; SURVEY.md 8(d): the path is exp-bound, "
+                          "not HBM-bound)",
+                "achieved": k_rate / 1e9, "peak": mufu_peak / 1e9, "unit": "Gexp/s", "frac": k_rate / mufu_peak,
+                "peak_source": "MUFU.EX2 micro-benchmark (b200ot_ubench) run in this process after the timed region",
+                "kernel_ms": kern["ms_per_launch"], "kernel_share_of_step": kern["ms_per_launch"] * 4 / (total_ms / args.steps),
+                "fp32": {"achieved_tflops": k_rate * 13 / 1e12, "ffma_peak_tflops": 2 * ceil["ffma_per_s"] / 1e12,
+                         "note": "13 flop/pair (SURVEY 8d); FFMA micro-benchmark peak"},
+                "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (kern["ms_per_launch"] * 1e-3) / 1e9,
+                        "peak_gbs": hbm_peak, "frac": alg_bytes / (kern["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"},
+                "traffic": traffic,
+            },
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_pass(L, ops, torch, dev, x, y, h_a, h_b, inv, center, eps, p, flush, reps, world, rank):
+    """Time the partial-reduction kernel alone (pack and finalize outside the events)."""
+    from geomloss_b200.distributed import shard_bounds
+
+    N, D = x.shape
+    lo, hi = shard_bounds(y.shape[0], rank, world)
+    ys, ha, hb = y[lo:hi], h_a[lo:hi], h_b[lo:hi]
+    M = ys.shape[0]
+    nsplit = L.b200ot_softmin_num_splits(N, M, D)
+    cols = torch.empty(L.b200ot_packed_cols_floats(M, D, 1), dtype=torch.float32, device=dev)
+    part = torch.empty(nsplit * N * 2, dtype=torch.float32, device=dev)
+    st = ops._stream(dev)
+    from geomloss_b200 import _lib
+
+    _lib.check(L.b200ot_softmin_pack(ops._ptr(ys), ops._ptr(ha), ops._ptr(hb), float(inv), ops._ptr(center), M, D, p,
+                                     float(eps), ops._ptr(cols), st), "pack")
+    times = []
+    for r in range(reps + 1):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(L.b200ot_softmin_partial(ops._ptr(x), ops._ptr(center), ops._ptr(cols), ops._ptr(part), nsplit, N, M,
+                                            D, p, float(eps), st), "partial")
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if r > 0:
+            times.append(e0.elapsed_time(e1))
+    ms = sum(times) / len(times)
+    return {"ms_per_launch": ms, "pairs_per_s": float(N) * M / (ms * 1e-3)}
+
+
+def pipe_ceilings(L, ops, torch, dev):
+    import ctypes
+
+    from geomloss_b200 import _lib
+
+    sink = torch.zeros(256, dtype=torch.float32, device=dev)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    out = {}
+    for name, which in (("mufu_ex2_per_s", 0), ("ffma_per_s", 1)):
+        ops_per = ctypes.c_int32(0)
+        iters, blocks = 8192, sms * 8
+        best = None
+        for r in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(L.b200ot_ubench(which, iters, blocks, ops._ptr(sink), ctypes.byref(ops_per), ops._stream(dev)),
+                       "ubench")
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1)
+            if r > 0 and (best is None or ms < best):
+                best = ms
+        out[name] = float(blocks) * 256 * iters * ops_per.value / (best * 1e-3)
+    return out
+
+
+def cpu_baseline(args):
+    import torch
+
+    n = args.cpu_n
+    O, eps, a_log, C, pots = dense_iteration_state(n, args.blur)
+    with torch.no_grad():
+        pots = dense_iteration(O, eps, a_log, C, pots)
+        t0 = time.perf_counter()
+        it = 0
+        while True:
+            pots = dense_iteration(O, eps, a_log, C, pots)
+            it += 1
+            dt = time.perf_counter() - t0
+            if dt > 10.0 or it >= 50:
+                break
+    cores = torch.get_num_threads()
+    return {"value": 4.0 * n * n * it / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{it} dense symmetric Sinkhorn iterations (4 softmins each) at N=M={n}, D=3, blur={args.blur}, "
+                      f"oracle port of the reference's tensorized path, torch CPU {cores} threads, {cpu_model()}, "
+                      f"{dt:.1f} s"}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -36,22 +36,35 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _compile_one(src: str, obj: str, verbose: bool):
+    cmd = [_nvcc(), "-c", *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, src, "-o", obj]
+    if verbose:
+        cmd[1:1] = ["-Xptxas", "-v"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    return src, res.returncode, res.stdout + res.stderr
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA translation unit into geomloss_b200/libb200ot.so; returns its path."""
+    """Compile every CUDA translation unit (in parallel) and link geomloss_b200/libb200ot.so; returns its path."""
     if not force and not _stale():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
+
+    objdir = os.path.join(ROOT, "build", "obj")
+    os.makedirs(objdir, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc(), "-shared", *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, *srcs, "-o",
-           LIB_PATH + ".tmp"]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd))
+    objs = [os.path.join(objdir, os.path.basename(s)[:-3] + ".o") for s in srcs]
+    with ThreadPoolExecutor(max_workers=len(srcs)) as pool:
+        results = list(pool.map(lambda so: _compile_one(so[0], so[1], verbose), zip(srcs, objs)))
+    for src, rc, log in results:
+        if verbose:
+            print(log)
+        if rc != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{log}")
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *objs, "-o", LIB_PATH + ".tmp"]
     res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose:
-        print(res.stdout, res.stderr)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     os.replace(LIB_PATH + ".tmp", LIB_PATH)
     return LIB_PATH
 

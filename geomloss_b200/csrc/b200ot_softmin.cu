@@ -112,6 +112,11 @@ static int softmin_partial_impl(const float* x, const float* center, const float
     case 1: return partial_for_d<1>(p, x, center, scale, clampq, cols, part, pl, N, st);
     case 2: return partial_for_d<2>(p, x, center, scale, clampq, cols, part, pl, N, st);
     case 3: return partial_for_d<3>(p, x, center, scale, clampq, cols, part, pl, N, st);
+    case 4: return partial_for_d<4>(p, x, center, scale, clampq, cols, part, pl, N, st);
+    case 5: return partial_for_d<5>(p, x, center, scale, clampq, cols, part, pl, N, st);
+    case 6: return partial_for_d<6>(p, x, center, scale, clampq, cols, part, pl, N, st);
+    case 7: return partial_for_d<7>(p, x, center, scale, clampq, cols, part, pl, N, st);
+    case 8: return partial_for_d<8>(p, x, center, scale, clampq, cols, part, pl, N, st);
     default: return B200OT_EINVAL;
   }
 }

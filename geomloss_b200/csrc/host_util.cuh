@@ -18,7 +18,7 @@ void set_last_cuda_error(cudaError_t e, const char* where);
 int num_sms();
 
 // Dimensions served by the CUDA-core (register tile) kernels that are instantiated in this build.
-inline bool supported_simt_dim(int D) { return D >= 1 && D <= 3; }
+inline bool supported_simt_dim(int D) { return D >= 1 && D <= B200OT_MAX_D; }
 
 // Coordinate scale of the softmin kernels: the log2-domain exponent is H - |X-Y|^2/2 (p = 2) or
 // H - |X-Y| (p = 1) with X = scale * (x - c).

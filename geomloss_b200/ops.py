@@ -14,7 +14,7 @@ import torch
 from . import _lib
 
 KERNEL_KINDS = {"gaussian": 0, "laplacian": 1, "energy": 2}
-MAX_D = 3  # dimensions instantiated in this build of libb200ot.so (supported_simt_dim in csrc/host_util.cuh)
+MAX_D = 8  # dimensions instantiated in this build of libb200ot.so (supported_simt_dim in csrc/host_util.cuh)
 
 # Number of kernels of libb200ot.so enqueued so far by this process (bench.py reports the delta over its
 # timed region as `gpu_launches`).  Every one-call entry point is pack + partial reduction + finalize.

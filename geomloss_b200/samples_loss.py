@@ -92,6 +92,12 @@ class SamplesLoss(Module):
                 F, G = values
                 return F.view(1, -1), G.view(1, -1)  # the reference's (1,N) shape for unbatched input
             return values
+        if self.loss == "sinkhorn" and kw["diameter"] is None:
+            # the reference measures ONE diameter over the flattened batch (sinkhorn_divergence.py:156-158),
+            # so all batch elements share the same eps-schedule
+            from .sinkhorn import max_diameter
+
+            kw["diameter"] = max_diameter(x.reshape(-1, D), y.reshape(-1, D))
         per_batch = [routine(a[k], x[k], b[k], y[k], **kw) for k in range(B)]
         if self.potentials:
             F = torch.stack([f for f, _ in per_batch])

@@ -37,7 +37,7 @@ extern "C" {
 #endif
 
 #define B200OT_VERSION 100 /* 0.1.0 */
-#define B200OT_MAX_D 16    /* CUDA-core (register-tile) kernels; larger D is routed to the tensor-core path */
+#define B200OT_MAX_D 8     /* dimensions served by the CUDA-core (register tile) kernels of this build */
 
 /* error codes */
 #define B200OT_OK 0

@@ -105,28 +105,32 @@ def main():
                     kw = dict(loss="sinkhorn", p=p, blur=0.1 if p == 2 else 0.05, reach=reach, debias=debias,
                               scaling=0.6)
                     r = run_loss(a_, x_, b_, y_, **kw)
-                    r64 = run_loss(a_.double(), x_.double(), b_.double(), y_.double(), grads=False, **kw)
+                    # the same reference code on the same (fp32-representable) inputs, evaluated in fp64:
+                    # the fp32 run has visible artefacts for p=1 (noisy sqrt(clamp) on near-zero distances)
+                    r64 = run_loss(a_.double(), x_.double(), b_.double(), y_.double(), **kw)
                     cases.append((kw, n, m, d))
-                    arrays = dict(a=np32(a_), x=np32(x_), b=np32(b_), y=np32(y_), value_f64=r64["value"],
+                    arrays = dict(a=np32(a_), x=np32(x_), b=np32(b_), y=np32(y_),
                                   p=np.int64(p), blur=np.float64(kw["blur"]),
                                   reach=np.float64(-1 if reach is None else reach), debias=np.int64(debias),
-                                  scaling=np.float64(0.6), **r)
+                                  scaling=np.float64(0.6), **r, **{k + "_f64": v for k, v in r64.items()})
                     save(f"sinkhorn_case{idx:02d}", **arrays)
                     idx += 1
 
     # ---- batched input (B=2) -----------------------------------------------------------------
     a_, x_, b_, y_ = clouds(7, 40, 30, 3, weights="random", batch=2)
     r = run_loss(a_, x_, b_, y_, loss="sinkhorn", p=2, blur=0.1)
-    save("sinkhorn_batched", a=np32(a_), x=np32(x_), b=np32(b_), y=np32(y_), **r)
+    r64 = run_loss(a_.double(), x_.double(), b_.double(), y_.double(), loss="sinkhorn", p=2, blur=0.1)
+    save("sinkhorn_batched", a=np32(a_), x=np32(x_), b=np32(b_), y=np32(y_), **r,
+         **{k + "_f64": v for k, v in r64.items()})
 
     # ---- kernel MMDs ----------------------------------------------------------------------------
     for k, name in enumerate(["gaussian", "laplacian", "energy"]):
         for j, (n, m, d, blur) in enumerate([(48, 61, 3, 0.3), (33, 20, 5, 0.7)]):
             a_, x_, b_, y_ = clouds(500 + 10 * k + j, n, m, d, weights="random")
             r = run_loss(a_, x_, b_, y_, loss=name, blur=blur)
-            r64 = run_loss(a_.double(), x_.double(), b_.double(), y_.double(), grads=False, loss=name, blur=blur)
+            r64 = run_loss(a_.double(), x_.double(), b_.double(), y_.double(), loss=name, blur=blur)
             save(f"kernel_{name}_{j}", a=np32(a_), x=np32(x_), b=np32(b_), y=np32(y_), blur=np.float64(blur),
-                 value_f64=r64["value"], **r)
+                 **r, **{k + "_f64": v for k, v in r64.items()})
 
     # ---- operator level: softmin_tensorized on arbitrary h -------------------------------------
     a_, x_, b_, y_ = clouds(900, 70, 90, 3, weights="random")
@@ -135,9 +139,12 @@ def main():
     ops = {}
     for p in (1, 2):
         C = ref_ss.cost_routines[p](x_.unsqueeze(0), y_.unsqueeze(0))
+        C64 = ref_ss.cost_routines[p](x_.double().unsqueeze(0), y_.double().unsqueeze(0))
         for e, eps in enumerate([1.0, 0.05, 0.003]):
             h = ref_sd.log_weights(b_) + pot / eps
             ops[f"softmin_p{p}_eps{e}"] = np32(ref_ss.softmin_tensorized(eps, C, h.unsqueeze(0)))[0]
+            h64 = ref_sd.log_weights(b_.double()) + pot.double() / eps
+            ops[f"softmin_p{p}_eps{e}_f64"] = np32(ref_ss.softmin_tensorized(eps, C64, h64.unsqueeze(0)))[0]
     save("softmin_operator", x=np32(x_), y=np32(y_), b=np32(b_), pot=np32(pot),
          eps=np.array([1.0, 0.05, 0.003]), **ops)
 

@@ -3,9 +3,12 @@
   (b) the CPU oracle (oracle/geomloss_oracle.py, itself pinned to the goldens) on seeded inputs,
   (c) size-independent properties at BASELINE.json's full size (N = M = 1e6).
 
-Tolerances (fp32 engine vs fp32 reference): loss within 1e-4 relative,
-potentials within 1e-5 absolute on unit-cube data — the tests below hold the engine to tighter bounds
-where the reference's own fp32-vs-fp64 gap (~4e-7 relative) allows.
+Tolerances: loss within 1e-4 relative, potentials within 1e-5 absolute on
+unit-cube data.  Every golden file holds the reference's output twice: its fp32 run and its fp64 run on
+the same inputs.  The fp64 run is the primary target (it is the reference algorithm without rounding
+noise); the fp32 run is checked at the level of the reference's own fp32-vs-fp64 gap, which is ~4e-7
+for p=2 but ~1e-4..1e-2 for p=1 / laplacian / energy, where its sqrt(clamp(|x|^2-2x.y+|y|^2)) is noisy
+for near-zero distances.
 """
 import numpy as np
 import pytest
@@ -48,14 +51,17 @@ def test_softmin_operator_vs_reference_golden():
     for p in (1, 2):
         for e, eps in enumerate(g["eps"]):
             eps = float(eps)
-            ref = g[f"softmin_p{p}_eps{e}"]
+            ref32, ref64 = g[f"softmin_p{p}_eps{e}"], g[f"softmin_p{p}_eps{e}_f64"]
             out, _ = ops.softmin_raw(eps, x, y, log_weights(b), pot, 1.0 / eps, p=p,
                                      center=ops.default_center(x, y))
-            tol = 2e-6 * max(1.0, np.abs(ref).max())
-            np.testing.assert_allclose(out.cpu().numpy(), ref, atol=tol)
+            tol = 1e-6 * max(1.0, np.abs(ref64).max())
+            np.testing.assert_allclose(out.cpu().numpy(), ref64, atol=tol)
+            # the fp32 reference is itself only this close to its fp64 run
+            gap = np.abs(ref32 - ref64).max()
+            np.testing.assert_allclose(out.cpu().numpy(), ref32, atol=tol + 1.5 * gap)
             # without the centring vector the result must be the same operator
             out2, _ = ops.softmin_raw(eps, x, y, log_weights(b) + pot / eps, p=p)
-            np.testing.assert_allclose(out2.cpu().numpy(), ref, atol=4 * tol)
+            np.testing.assert_allclose(out2.cpu().numpy(), ref64, atol=4 * tol)
 
 
 @pytest.mark.parametrize("p", [1, 2])
@@ -137,7 +143,7 @@ def test_kernel_conv_vs_oracle(kind):
             out = ops.kernel_conv_raw(kind, x.to(DEV), y.to(DEV), w.to(DEV), blur,
                                       center=ops.default_center(x.to(DEV), y.to(DEV)))
             scale = max(1e-3, np.abs(ref).max())
-            np.testing.assert_allclose(out.cpu().numpy(), ref, atol=5e-6 * scale + 2e-6 * w.abs().sum().item() / m)
+            np.testing.assert_allclose(out.cpu().numpy(), ref, atol=5e-6 * scale + 2e-7 * w.abs().sum().item())
 
 
 @pytest.mark.parametrize("kind", ["gaussian", "laplacian", "energy"])
@@ -209,17 +215,20 @@ def test_sinkhorn_cases(name):
     val = SamplesLoss(**kw)(ag, xg, bg, yg)
     ref = float(g["value_f64"])
     assert abs(val.item() - ref) <= 1e-4 * abs(ref) + 1e-7, (val.item(), ref)
+    # fp32 reference: within its own distance to the fp64 run (+ the stated bar)
+    gap = abs(float(g["value"]) - ref)
+    assert abs(val.item() - float(g["value"])) <= 1e-4 * abs(ref) + 1.5 * gap + 1e-7
     ga, gx, gb, gy = torch.autograd.grad(val, [ag, xg, bg, yg])
     for got, key in ((ga, "grad_a"), (gb, "grad_b"), (gx, "grad_x"), (gy, "grad_y")):
-        r = g[key]
+        r = g[key + "_f64"]
         np.testing.assert_allclose(got.cpu().numpy(), r, atol=1e-4 * max(np.abs(r).max(), 1e-3), err_msg=key)
     F, G = SamplesLoss(potentials=True, **kw)(a, x, b, y)
-    np.testing.assert_allclose(F.cpu().numpy(), g["pot_f"], atol=1e-5 * max(1.0, np.abs(g["pot_f"]).max()))
-    np.testing.assert_allclose(G.cpu().numpy(), g["pot_g"], atol=1e-5 * max(1.0, np.abs(g["pot_g"]).max()))
+    np.testing.assert_allclose(F.cpu().numpy(), g["pot_f_f64"], atol=1e-5 * max(1.0, np.abs(g["pot_f_f64"]).max()))
+    np.testing.assert_allclose(G.cpu().numpy(), g["pot_g_f64"], atol=1e-5 * max(1.0, np.abs(g["pot_g_f64"]).max()))
 
 
 def dim_supported(d):
-    return d <= 3
+    return d <= 8
 
 
 def test_sinkhorn_batched():
@@ -229,11 +238,12 @@ def test_sinkhorn_batched():
     a, x, b, y = (cu(g[k]) for k in "axby")
     val = SamplesLoss("sinkhorn", p=2, blur=0.1)(a, x, b, y)
     assert val.shape == (2,)
+    np.testing.assert_allclose(val.cpu().numpy(), g["value_f64"], rtol=1e-4)
     np.testing.assert_allclose(val.cpu().numpy(), g["value"], rtol=1e-4)
     F, G = SamplesLoss("sinkhorn", p=2, blur=0.1, potentials=True)(a, x, b, y)
     assert F.shape == (2, 40) and G.shape == (2, 30)
-    np.testing.assert_allclose(F.cpu().numpy(), g["pot_f"], atol=1e-5)
-    np.testing.assert_allclose(G.cpu().numpy(), g["pot_g"], atol=1e-5)
+    np.testing.assert_allclose(F.cpu().numpy(), g["pot_f_f64"], atol=1e-5)
+    np.testing.assert_allclose(G.cpu().numpy(), g["pot_g_f64"], atol=1e-5)
     # weights given as (B,N,1)
     v2 = SamplesLoss("sinkhorn", p=2, blur=0.1)(a.unsqueeze(-1), x, b.unsqueeze(-1), y)
     np.testing.assert_allclose(v2.cpu().numpy(), val.cpu().numpy(), rtol=1e-6)
@@ -259,11 +269,11 @@ def test_kernel_losses(name):
     assert abs(val.item() - ref) <= 1e-4 * abs(ref) + 2e-7, (val.item(), ref)
     ga, gx, gb, gy = torch.autograd.grad(val, [ag, xg, bg, yg])
     for got, key in ((ga, "grad_a"), (gb, "grad_b"), (gx, "grad_x"), (gy, "grad_y")):
-        r = g[key]
-        np.testing.assert_allclose(got.cpu().numpy(), r, atol=2e-4 * max(np.abs(r).max(), 1e-3), err_msg=key)
+        r = g[key + "_f64"]
+        np.testing.assert_allclose(got.cpu().numpy(), r, atol=1e-4 * max(np.abs(r).max(), 1e-3), err_msg=key)
     F, G = SamplesLoss(kind, blur=blur, potentials=True)(a, x, b, y)
-    np.testing.assert_allclose(F.cpu().numpy(), g["pot_f"], atol=2e-4 * np.abs(g["pot_f"]).max())
-    np.testing.assert_allclose(G.cpu().numpy(), g["pot_g"], atol=2e-4 * np.abs(g["pot_g"]).max())
+    np.testing.assert_allclose(F.cpu().numpy(), g["pot_f_f64"], atol=2e-5 * np.abs(g["pot_f_f64"]).max())
+    np.testing.assert_allclose(G.cpu().numpy(), g["pot_g_f64"], atol=2e-5 * np.abs(g["pot_g_f64"]).max())
     # dL/da is the potential
     np.testing.assert_allclose(ga.cpu().numpy(), F.cpu().numpy().reshape(-1), atol=1e-6)
 
