@@ -10,6 +10,8 @@
 #include "plan.cuh"
 #include "rowsum.cuh"
 
+#include <type_traits>
+
 namespace b200ot {
 
 // part: (n_split, N, D+1) with [0] = sum w, [1+k] = sum w Y_k (p=2, scaled centred coords) or sum w u_k (p=1)
@@ -55,7 +57,9 @@ static int launch_rowsum(const ReducePlan& pl, cudaStream_t st, const float* x, 
     return launch_reduce<C>(rowsum_partial_kernel<C>, pl, st, x, center, scale, clampq, cols, lse2, part, N,
                             pl.ntiles, pl.tiles_per_split);
   }
-  using C = RowSumCfg<MODE, D, kBigR, kBigNT, kBigTJ, 3, 2>;
+  // D >= 5: one row per thread (same 512 rows per CTA) keeps the 2 x (D+1) accumulator pairs in registers
+  using C = std::conditional_t<(D <= 4), RowSumCfg<MODE, D, kBigR, kBigNT, kBigTJ, 3, 2>,
+                               RowSumCfg<MODE, D, 1, kBigR * kBigNT, kBigTJ, 3, 1>>;
   return launch_reduce<C>(rowsum_partial_kernel<C>, pl, st, x, center, scale, clampq, cols, lse2, part, N, pl.ntiles,
                           pl.tiles_per_split);
 }

@@ -49,7 +49,7 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
 }
 
 template <int D_, int R_, int P_, bool DIRECT_, unsigned PMASK_ = 0u, int NT_ = 256, int TJ_ = 1024,
-          int STAGES_ = 3, int CH_ = 4, int MINB_ = 2>
+          int STAGES_ = 3, int CH_ = 4, int MINB_ = 2, bool GUARD_ = false>
 struct SoftminCfg {
   static constexpr int D = D_;            // ambient dimension
   static constexpr int R = R_;            // rows per consumer thread
@@ -61,6 +61,8 @@ struct SoftminCfg {
   static constexpr int STAGES = STAGES_;
   static constexpr int CH = CH_;          // column pairs per chunk (running max refreshed once per chunk)
   static constexpr int MINB = MINB_;      // CTAs per SM the register budget is planned for
+  static constexpr bool GUARD = GUARD_;   // detect an outdated max from the chunk SUM (> 2^64) instead of
+                                          // tracking the chunk max with one FMNMX3 per column pair
   static constexpr int NEXTRA = 1;
   static constexpr int NF2 = ((D + NEXTRA + 1) / 2) * 2;
   static constexpr int TILE_FLOATS = (TJ / 2) * NF2 * 2;
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const float2 t = pair_exponent<C>(X[r], S, clampq);
-          cm[r] = fmax3(cm[r], t.x, t.y);
+          if constexpr (!C::GUARD) cm[r] = fmax3(cm[r], t.x, t.y);
           const float2 a = __fadd2_rn(t, nm2[r]);
           float2 e;
           if ((C::PMASK >> c) & 1u) {
@@ -229,8 +231,25 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
       }
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        if (cm[r] > m[r] + kLazy) {
+        bool stale;
+        if constexpr (C::GUARD) {
+          // a term above 2^kLazy (or an overflow to +inf) shows up in the chunk sum
+          stale = !(cs[r].x + cs[r].y <= 1.8446744e19f);
+        } else {
+          stale = cm[r] > m[r] + kLazy;
+        }
+        if (stale) {
           // rare: the chunk overshoots the stale max — rebase the row on the chunk max and redo the chunk
+          if constexpr (C::GUARD) {
+            cm[r] = kNegBig;
+#pragma unroll 1
+            for (int c = 0; c < CH; ++c) {
+              float2 S[NF2];
+              load_packet<NF2>(tp, jp + c, S);
+              const float2 t = pair_exponent<C>(X[r], S, clampq);
+              cm[r] = fmax3(cm[r], t.x, t.y);
+            }
+          }
           const float sc = ex2_approx(m[r] - cm[r]);
           s2[r] = __fmul2_rn(s2[r], dup2(sc));
           ts2[r] = __fmul2_rn(ts2[r], dup2(sc));

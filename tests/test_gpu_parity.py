@@ -65,8 +65,8 @@ def test_softmin_operator_vs_reference_golden():
 
 
 @pytest.mark.parametrize("p", [1, 2])
-@pytest.mark.parametrize("shape", [(1, 1, 3), (3, 1, 2), (1, 5, 1), (257, 131, 3), (130, 1025, 2), (5000, 4099, 3),
-                                   (20011, 9973, 3)])
+@pytest.mark.parametrize("shape", [(1, 1, 3), (3, 1, 2), (1, 5, 1), (257, 131, 3), (130, 1025, 2), (2100, 4099, 3),
+                                   (4611, 5003, 3), (700, 300, 5), (300, 4200, 8)])
 def test_softmin_vs_oracle_shapes(p, shape):
     """Ragged sizes around the tile boundaries (2-column packets, 256/1024-column tiles, 128/512-row CTAs),
     both kernel variants (small / big), against the fp64 oracle."""
@@ -79,7 +79,7 @@ def test_softmin_vs_oracle_shapes(p, shape):
     y = torch.rand(m, d, generator=g) * 1.1 - 0.05
     h = torch.randn(m, generator=g) * 2.0 - np.log(m)
     for eps in (0.5, 0.01, 5e-4):
-        ref = O.softmin_points(eps, x.double(), y.double(), h.double(), p=p).numpy()
+        ref = O.softmin_points(eps, x.double(), y.double(), h.double(), p=p, row_block=512).numpy()
         out, lse2 = ops.softmin_raw(eps, x.to(DEV), y.to(DEV), h.to(DEV), p=p,
                                     center=ops.default_center(x.to(DEV), y.to(DEV)), want_lse2=True)
         got = out.cpu().numpy()
@@ -135,7 +135,7 @@ def test_kernel_conv_vs_oracle(kind):
     from oracle import geomloss_oracle as O
 
     g = torch.Generator().manual_seed(13)
-    for (n, m, d) in [(1, 1, 3), (333, 777, 3), (6000, 4500, 2), (100, 9000, 1)]:
+    for (n, m, d) in [(1, 1, 3), (333, 777, 3), (4200, 4500, 2), (100, 9000, 1), (500, 600, 6)]:
         x, y = torch.rand(n, d, generator=g), torch.rand(m, d, generator=g)
         w = torch.randn(m, generator=g)
         for blur in (0.05, 0.5):
@@ -279,20 +279,26 @@ def test_kernel_losses(name):
 
 
 def test_mid_size_loss_vs_oracle():
-    """N=6000, M=5000 (big-kernel variant, ragged): loss and potentials against the dense CPU oracle."""
+    """N=4300, M=4100 (big-kernel variant, ragged): loss and potentials against the dense CPU oracle."""
     from geomloss_b200 import SamplesLoss
     from oracle import geomloss_oracle as O
 
     g = torch.Generator().manual_seed(23)
-    x, y = torch.rand(6000, 3, generator=g), torch.rand(5000, 3, generator=g)
-    for kw in (dict(blur=0.05, scaling=0.5), dict(blur=0.01, scaling=0.7), dict(blur=0.05, p=1, scaling=0.5),
+    x, y = torch.rand(4300, 3, generator=g), torch.rand(4100, 3, generator=g)
+    for kw in (dict(blur=0.05, scaling=0.5), dict(blur=0.01, scaling=0.6), dict(blur=0.05, p=1, scaling=0.5),
                dict(blur=0.05, reach=0.5, scaling=0.5)):
-        ref = O.samples_loss(x.double(), y.double(), loss="sinkhorn", **kw).item()
-        val = SamplesLoss("sinkhorn", **kw)(x.to(DEV), y.to(DEV)).item()
-        assert abs(val - ref) <= 1e-4 * abs(ref), (kw, val, ref)
+        # one dense fp64 oracle run gives both the potentials and (through the value formula) the loss
+        a = torch.full((1, 4300), 1 / 4300, dtype=torch.float64)
+        b = torch.full((1, 4100), 1 / 4100, dtype=torch.float64)
         Fr, Gr = O.samples_loss(x.double(), y.double(), loss="sinkhorn", potentials=True, **kw)
         F, G = SamplesLoss("sinkhorn", potentials=True, **kw)(x.to(DEV), y.to(DEV))
         assert (F.cpu().double() - Fr).abs().max() < 1e-5 and (G.cpu().double() - Gr).abs().max() < 1e-5
+        val = SamplesLoss("sinkhorn", **kw)(x.to(DEV), y.to(DEV)).item()
+        if kw.get("reach") is None:  # balanced + debiased: value = <a, F> + <b, G>
+            ref = ((a * Fr).sum() + (b * Gr).sum()).item()
+        else:
+            ref = O.samples_loss(x.double(), y.double(), loss="sinkhorn", **kw).item()
+        assert abs(val - ref) <= 1e-4 * abs(ref), (kw, val, ref)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -321,7 +327,7 @@ def test_full_size_softmin_properties(million):
     torch.cuda.synchronize()
     assert torch.isfinite(out).all()
     # (1) sampled rows against an fp64 brute force
-    idx = torch.linspace(0, n - 1, 24).long()
+    idx = torch.linspace(0, n - 1, 12).long()
     h64 = h_a.double() + pot.double() / eps
     for i in idx.tolist():
         t = h64 - ((x[i].double() - y.double()) ** 2).sum(1) / (2 * eps)

@@ -385,6 +385,15 @@ int main(int argc, char** argv) {
   run_variant<SoftminCfg<3, 4, 2, false, 0u, 256, 1024, 3, 8, 2>>("expand R4 CH8", P, reps);
   run_variant<SoftminCfg<3, 2, 2, false, 0u, 256, 1024, 3, 8, 2>>("expand R2 CH8", P, reps);
   run_variant<SoftminCfg<3, 2, 2, false, 0u, 256, 1024, 3, 4, 3>>("expand R2 CH4 occ3", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0u, 256, 1024, 3, 4, 3, true>>("expand R2 CH4 occ3 guard", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0u, 256, 1024, 3, 8, 3, true>>("expand R2 CH8 occ3 guard", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0u, 256, 1024, 3, 4, 4, true>>("expand R2 CH4 occ4 guard", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0u, 256, 1024, 3, 2, 4, true>>("expand R2 CH2 occ4 guard", P, reps);
+  run_variant<SoftminCfg<3, 3, 2, false, 0u, 256, 1024, 3, 4, 3, true>>("expand R3 CH4 occ3 guard", P, reps);
+  run_variant<SoftminCfg<3, 4, 2, false, 0u, 256, 1024, 3, 4, 2, true>>("expand R4 CH4 occ2 guard", P, reps);
+  run_variant<SoftminCfg<3, 4, 2, false, 0u, 128, 1024, 3, 4, 5, true>>("expand R4 NT128 CH4 occ5 guard", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x1u, 256, 1024, 3, 8, 3, true>>("expand R2 CH8 occ3 guard poly1/8", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x1u, 256, 1024, 3, 4, 3>>("expand R2 CH4 occ3 poly1/4", P, reps);
   run_variant<SoftminCfg<3, 2, 2, false, 0u, 128, 1024, 3, 8, 4>>("expand R2 NT128 CH8 occ4", P, reps);
   run_variant<SoftminCfg<3, 2, 2, false, 0u, 128, 1024, 3, 4, 6>>("expand R2 NT128 CH4 occ6", P, reps);
   run_variant<SoftminCfg<3, 1, 2, false, 0u, 256, 1024, 3, 8, 4>>("expand R1 NT256 CH8 occ4", P, reps);
