@@ -9,6 +9,7 @@
 #include "pack.cuh"
 #include "plan.cuh"
 #include "rowsum.cuh"
+#include "tcconv.cuh"
 
 #include <type_traits>
 
@@ -122,6 +123,73 @@ static int conv_pack(const float* y, const float* w, const float* center, int64_
   return B200OT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// tensor-core path (gaussian, 8 < D <= 64): see tcconv.cuh
+// ---------------------------------------------------------------------------------------------------
+constexpr int kTcBN = 128;    // columns per MMA tile
+constexpr int kTcEpi = 8;     // epilogue warps
+using TcConvCfg = TcCfg<kTcBN, kTcEpi>;
+
+struct TcPlan {
+  int kp, nstage, n_split, tiles_per_split;
+  int64_t a_tiles, b_tiles, a_bytes, b_bytes, smem;
+  int64_t off_b, off_part, total;
+};
+
+static bool tc_supported_dim(int D) { return D > B200OT_MAX_D && D <= 64; }
+
+static TcPlan make_tc_plan(int64_t N, int64_t M, int D) {
+  TcPlan p;
+  p.kp = tc_kp(D);
+  p.a_tiles = ceil_div64(N, kTcM);
+  p.b_tiles = ceil_div64(M, kTcBN);
+  p.a_bytes = tc_a_img_bytes(p.kp);
+  p.b_bytes = tc_b_img_bytes(p.kp, kTcBN);
+  const int64_t bar_bytes = 8 * (1 + 2 * kTcMaxStage + 2 * 2) + 16;
+  const int64_t avail = 227 * 1024 - bar_bytes - 1024;  // the row operand lives in TMEM, not in shared memory
+  int64_t ns = avail / p.b_bytes;
+  p.nstage = (int)(ns > kTcMaxStage ? kTcMaxStage : ns);
+  p.smem = p.nstage * p.b_bytes + bar_bytes;
+  int64_t want = ceil_div64((int64_t)num_sms() * 4, p.a_tiles);
+  if (want < 1) want = 1;
+  if (want > 64) want = 64;
+  if (want > p.b_tiles) want = p.b_tiles;
+  p.tiles_per_split = (int)ceil_div64(p.b_tiles, want);
+  p.n_split = (int)ceil_div64(p.b_tiles, p.tiles_per_split);
+  p.off_b = round_up64(p.a_tiles * p.a_bytes, 256);
+  p.off_part = p.off_b + round_up64(p.b_tiles * p.b_bytes, 256);
+  p.total = p.off_part + round_up64((int64_t)p.n_split * (kTcEpi / 4) * N * 4, 256);
+  return p;
+}
+
+static int conv_fwd_tc(const float* x, const float* y, const float* w, const float* center, float* out, int64_t N,
+                       int64_t M, int D, float blur, void* scratch, cudaStream_t st) {
+  const TcPlan p = make_tc_plan(N, M, D);
+  if (p.nstage < 1) return B200OT_EINVAL;
+  unsigned char* base = reinterpret_cast<unsigned char*>(scratch);
+  unsigned char* a_imgs = base;
+  unsigned char* b_imgs = base + p.off_b;
+  float* part = reinterpret_cast<float*>(base + p.off_part);
+  const float scale = sqrtf(kLog2e) / blur;
+  const int threads = 128;
+  tc_pack_kernel<<<(unsigned)ceil_div64(p.a_tiles * kTcM, threads), threads, 0, st>>>(
+      x, nullptr, center, scale, N, D, p.kp, kTcM, 0, a_imgs);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  tc_pack_kernel<<<(unsigned)ceil_div64(p.b_tiles * kTcBN, threads), threads, 0, st>>>(
+      y, w, center, scale, M, D, p.kp, kTcBN, 1, b_imgs);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  auto kern = gauss_tc_kernel<TcConvCfg>;
+  B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  dim3 grid((unsigned)p.a_tiles, (unsigned)p.n_split);
+  kern<<<grid, TcConvCfg::THREADS, (size_t)p.smem, st>>>(a_imgs, b_imgs, part, N, p.kp, (int)p.b_tiles,
+                                                        p.tiles_per_split, p.nstage);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  conv_fwd_finalize_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, st>>>(part, p.n_split * (kTcEpi / 4), 1.f, out,
+                                                                       N);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  return B200OT_OK;
+}
+
 }  // namespace b200ot
 
 using namespace b200ot;
@@ -130,6 +198,7 @@ extern "C" {
 
 B200OT_API int64_t b200ot_kernel_conv_scratch_bytes(int64_t N, int64_t M, int32_t D) {
   if (N <= 0 || M <= 0 || D <= 0) return 0;
+  if (tc_supported_dim(D)) return make_tc_plan(N, M, D).total;
   const ReducePlan pl = make_plan(N, M);
   const int64_t cols = b200ot_packed_cols_floats(M, D, 2) * 4;
   const int64_t part = (int64_t)pl.n_split * N * 4 * (D + 1);
@@ -139,11 +208,14 @@ B200OT_API int64_t b200ot_kernel_conv_scratch_bytes(int64_t N, int64_t M, int32_
 B200OT_API int b200ot_kernel_conv_fwd(const float* x, const float* y, const float* w, const float* center,
                                       float* out, int64_t N, int64_t M, int32_t D, int32_t kind, float blur,
                                       void* scratch, int64_t scratch_bytes, void* stream) {
-  if (!x || !y || !w || !out || !scratch || N <= 0 || M <= 0 || !supported_simt_dim(D) || kind < 0 || kind > 2)
+  const bool tc = (kind == B200OT_KERNEL_GAUSSIAN) && tc_supported_dim(D);
+  if (!x || !y || !w || !out || !scratch || N <= 0 || M <= 0 || (!supported_simt_dim(D) && !tc) || kind < 0 ||
+      kind > 2)
     return B200OT_EINVAL;
   if (kind != B200OT_KERNEL_ENERGY && !(blur > 0.f)) return B200OT_EINVAL;
   if (((uintptr_t)scratch) & 15) return B200OT_EALIGN;
   if (scratch_bytes < b200ot_kernel_conv_scratch_bytes(N, M, D)) return B200OT_ESCRATCH;
+  if (tc) return conv_fwd_tc(x, y, w, center, out, N, M, D, blur, scratch, (cudaStream_t)stream);
   const ReducePlan pl = make_plan(N, M);
   const ConvScales cs = conv_scales(kind, blur);
   float* cols = reinterpret_cast<float*>(scratch);

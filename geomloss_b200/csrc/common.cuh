@@ -100,7 +100,7 @@ __device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
 // Arguments below -126 flush to 0.  Used to off-load a fraction of the exponentials from the
 // 16-lane/SM MUFU unit to the 128-lane/SM FMA unit.
 __device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -126.0f);
+  x = fminf(fmaxf(x, -126.0f), 127.0f);
   const float magic = 12582912.0f;  // 1.5 * 2^23
   float t = x + magic;              // round-to-nearest integer lives in the low mantissa bits
   float n = t - magic;

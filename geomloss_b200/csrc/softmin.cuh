@@ -28,10 +28,13 @@
 
 namespace b200ot {
 
-// 2^x on a pair, FMA pipe only (see ex2_poly in common.cuh for the scalar derivation).
+// 2^x on a pair, FMA pipe only (see ex2_poly in common.cuh for the scalar derivation).  Arguments are
+// clamped to [-126, 127]: below, the result is ~2^-126 (the MUFU path flushes to 0; both are far below one
+// ulp of any row sum); above, 2^127 makes the chunk sum overflow the 2^64 guard of the lazy max, exactly
+// like the +inf of the MUFU path, so an outdated max is always detected.
 __device__ __forceinline__ float2 ex2_poly2(float2 x) {
-  x.x = fmaxf(x.x, -126.0f);
-  x.y = fmaxf(x.y, -126.0f);
+  x.x = fminf(fmaxf(x.x, -126.0f), 127.0f);
+  x.y = fminf(fmaxf(x.y, -126.0f), 127.0f);
   const float2 magic = dup2(12582912.0f);
   float2 t = __fadd2_rn(x, magic);
   float2 n = __fadd2_rn(t, dup2(-12582912.0f));

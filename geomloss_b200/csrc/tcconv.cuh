@@ -1,0 +1,275 @@
+// b200ot — gaussian kernel convolution on the 5th-gen tensor cores, for dimensions where -2 x.y^T is a
+// real dense contraction (8 < D <= 64):
+//     out_i = sum_j w_j exp(-|x_i - y_j|^2 / (2 blur^2)) = sum_j w_j 2^( X_i.Y_j - |X_i|^2/2 - |Y_j|^2/2 )
+// Reference semantics: gaussian_kernel + the matvecs of kernel_loss
+// (src/geomloss/_legacy/kernel_samples.py:62-68, :116-137).
+//
+// The whole exponent is produced by tcgen05.mma into TMEM:
+//   * each operand is split into three bf16 terms X = h + m + l and stored ONCE as [h | m | l] along K;
+//     the six cross products that matter (hh, hm, mh, hl, mm, lh: error ~2^-24 |X||Y|) are formed by
+//     pointing the A and B shared-memory descriptors at the matching segments — no duplicated data in
+//     shared memory or L2, 6*Dk/16 MMA instructions per tile, fp32 accumulation;
+//   * one extra 16-wide K chunk carries the rank-one terms:  A: [1,1,1, r_h,r_m,r_l, 0..],
+//     B: [c_h,c_m,c_l, 1,1,1, 0..] with r = -|X|^2/2, c = -|Y|^2/2 split in three bf16 terms,
+//   so the epilogue is  tcgen05.ld -> MUFU.EX2 -> FFMA with the column weight  and nothing else.
+//
+// Operand tiles are pre-packed in global memory by tc_pack_kernel in the exact image the UMMA descriptors
+// expect (K-major, no swizzle: for every 8-element K chunk the 16-byte pieces of all rows are
+// contiguous), so a column tile is ONE 1-D bulk-TMA copy; the column weights ride at the end of the image.
+// The ROW operand of a CTA is staged once into TMEM (tcgen05.st, lane = row, two bf16 per 32-bit column) and
+// the MMAs run in TS mode: at M = 128 an SS-mode MMA needs 128 B/clk of shared-memory reads — the whole
+// shared-memory bandwidth of the SM — and measured 1.34e12 pairs/s at D = 64; TS mode halves that and
+// reaches 1.58e12 (1.27 PFLOP/s of bf16 MMA work, profiles/r01_conv_bench.jsonl).
+// CTA = TMA warp + MMA warp (one elected thread issues) + NEPI epilogue warps; smem ring of column tiles
+// with full/empty mbarriers; two accumulator buffers in TMEM so that the MMAs of tile t+1 overlap the
+// exponentials of tile t.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace b200ot {
+
+constexpr int kTcM = 128;  // rows per CTA tile = M of the MMA
+
+__host__ __device__ inline int tc_dk(int D) { return ((D + 15) / 16) * 16; }
+// K extent of an operand image: three split terms + one 16-wide chunk of rank-one terms
+__host__ __device__ inline int tc_kp(int D) { return 3 * tc_dk(D) + 16; }
+__host__ __device__ inline int64_t tc_a_img_bytes(int kp) { return (int64_t)kTcM * kp * 2; }
+__host__ __device__ inline int64_t tc_b_img_bytes(int kp, int bn) { return (int64_t)bn * kp * 2 + (int64_t)bn * 4; }
+
+// ---------------------------------------------------------------------------------------------------
+// pack: one thread per (padded) point; writes its 16-byte piece of every K chunk of its tile image
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 pack8_bf16(const __nv_bfloat16* src) {
+  uint4 v;
+  v.x = (uint32_t)__bfloat16_as_ushort(src[0]) | ((uint32_t)__bfloat16_as_ushort(src[1]) << 16);
+  v.y = (uint32_t)__bfloat16_as_ushort(src[2]) | ((uint32_t)__bfloat16_as_ushort(src[3]) << 16);
+  v.z = (uint32_t)__bfloat16_as_ushort(src[4]) | ((uint32_t)__bfloat16_as_ushort(src[5]) << 16);
+  v.w = (uint32_t)__bfloat16_as_ushort(src[6]) | ((uint32_t)__bfloat16_as_ushort(src[7]) << 16);
+  return v;
+}
+
+static __global__ void tc_pack_kernel(const float* __restrict__ pts, const float* __restrict__ w,
+                                      const float* __restrict__ center, float scale, int64_t n, int D, int kp,
+                                      int tile, int is_cols, unsigned char* __restrict__ out) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t npad = ((n + tile - 1) / tile) * tile;
+  if (p >= npad) return;
+  const int64_t t = p / tile;
+  const int pt = (int)(p % tile);
+  const int64_t img_bytes = (int64_t)tile * kp * 2 + (is_cols ? (int64_t)tile * 4 : 0);
+  unsigned char* img = out + t * img_bytes;
+  const int dk = tc_dk(D);
+  const bool live = p < n;
+  float sq = 0.f;
+  for (int kc = 0; kc < dk / 8; ++kc) {
+    __nv_bfloat16 term[3][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int d = kc * 8 + k;
+      float X = 0.f;
+      if (live && d < D) X = scale * (pts[p * D + d] - (center ? center[d] : 0.f));
+      sq = fmaf(X, X, sq);
+      const __nv_bfloat16 h = __float2bfloat16_rn(X);
+      const float r1 = X - __bfloat162float(h);
+      const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+      term[0][k] = h;
+      term[1][k] = m;
+      term[2][k] = __float2bfloat16_rn(r1 - __bfloat162float(m));
+    }
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+      *reinterpret_cast<uint4*>(img + ((int64_t)(s * (dk / 8) + kc) * tile + pt) * 16) = pack8_bf16(term[s]);
+  }
+  // rank-one chunk (16 wide): rows [1,1,1, r_h,r_m,r_l, 0..]   columns [c_h,c_m,c_l, 1,1,1, 0..]
+  {
+    const float r = live ? -0.5f * sq : 0.f;
+    const __nv_bfloat16 rh = __float2bfloat16_rn(r);
+    const float q1 = r - __bfloat162float(rh);
+    const __nv_bfloat16 rm = __float2bfloat16_rn(q1);
+    const __nv_bfloat16 rl = __float2bfloat16_rn(q1 - __bfloat162float(rm));
+    const uint32_t one = 0x3F80u;  // bf16 1.0
+    const uint32_t a = __bfloat16_as_ushort(rh), b = __bfloat16_as_ushort(rm), c = __bfloat16_as_ushort(rl);
+    uint4 v;
+    if (is_cols) {
+      v.x = a | (b << 16);
+      v.y = c | (one << 16);
+      v.z = one | (one << 16);
+    } else {
+      v.x = one | (one << 16);
+      v.y = one | (a << 16);
+      v.z = b | (c << 16);
+    }
+    v.w = 0u;
+    const int chunk = 3 * (dk / 8);
+    *reinterpret_cast<uint4*>(img + ((int64_t)chunk * tile + pt) * 16) = v;
+    *reinterpret_cast<uint4*>(img + ((int64_t)(chunk + 1) * tile + pt) * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (is_cols) reinterpret_cast<float*>(img + (int64_t)tile * kp * 2)[pt] = (live && w) ? w[p] : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the reduction kernel
+// ---------------------------------------------------------------------------------------------------
+constexpr int kTcMaxStage = 4;
+
+template <int BN_, int NEPI_>
+struct TcCfg {
+  static constexpr int BN = BN_;          // columns per tile = N of the MMA
+  static constexpr int NEPI = NEPI_;      // epilogue warps (4 or 8)
+  static constexpr int NACC = 2;          // accumulator buffers in TMEM
+  static constexpr int THREADS = 64 + 32 * NEPI;
+  static constexpr int A_COL0 = NACC * BN;  // the row operand lives in TMEM behind the accumulators
+  static constexpr int A_COLS = 128;        // up to kp = 256 bf16 per row (D <= 64: kp = 208)
+  static constexpr int TMEM_COLS = (A_COL0 + A_COLS <= 256) ? 256 : 512;
+  static_assert(NEPI == 4 || NEPI == 8, "epilogue warps come in groups of four (one per TMEM lane quarter)");
+  static_assert(BN % 64 == 0 && BN <= 256, "unsupported column tile");
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 1)
+    gauss_tc_kernel(const unsigned char* __restrict__ a_imgs, const unsigned char* __restrict__ b_imgs,
+                    float* __restrict__ part, int64_t N, int kp, int ntiles_b, int tiles_per_split, int NSTAGE) {
+  constexpr int BN = C::BN, NEPI = C::NEPI, NACC = C::NACC;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int a_bytes = kTcM * kp * 2;
+  const int b_bytes = BN * kp * 2 + BN * 4;
+  unsigned char* sb = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * b_bytes);
+  uint64_t* bar_a = bars;
+  uint64_t* full_b = bars + 1;
+  uint64_t* empty_b = full_b + kTcMaxStage;
+  uint64_t* tmem_full = empty_b + kTcMaxStage;
+  uint64_t* tmem_empty = tmem_full + NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + NACC);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_tile = blockIdx.x;
+  const int split = blockIdx.y;
+  const int t0 = split * tiles_per_split;
+  const int t1 = min(ntiles_b, t0 + tiles_per_split);
+  const int nt = t1 - t0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_a, 4);  // the four lane quarters of the row operand
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full_b[s], 1);
+      mbar_init(&empty_b[s], 1 + NEPI);  // MMA completion + every epilogue warp (it reads the weights)
+    }
+    for (int a = 0; a < NACC; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], NEPI);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int k = 0; k < nt; ++k) {
+        const int st = k % NSTAGE;
+        if (k >= NSTAGE) mbar_wait(&empty_b[st], ((k / NSTAGE) + 1) & 1);
+        mbar_arrive_expect_tx(&full_b[st], b_bytes);
+        tma_load_1d(sb + st * b_bytes, b_imgs + (int64_t)(t0 + k) * b_bytes, b_bytes, &full_b[st]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kTcM, BN);
+      mbar_wait(bar_a, 0);
+      tc_fence_after();
+      for (int k = 0; k < nt; ++k) {
+        const int st = k % NSTAGE, acc = k % NACC;
+        mbar_wait(&full_b[st], (k / NSTAGE) & 1);
+        if (k >= NACC) mbar_wait(&tmem_empty[acc], ((k / NACC) + 1) & 1);
+        tc_fence_after();
+        const uint32_t a_tmem = tmem_base + C::A_COL0, b_addr = smem_u32(sb + st * b_bytes);
+        const uint32_t d_addr = tmem_base + acc * BN;
+        // rank-one chunk first (overwrites the accumulator), then the six split cross products
+        const int seg = (kp - 16) / 3 / 8;  // 8-element chunks per split term
+        {
+          const uint64_t db = make_smem_desc(b_addr + 3 * seg * (BN * 16), BN * 16, 128);
+          umma_bf16_ts(d_addr, a_tmem + 3 * seg * 4, db, idesc, false);  // 4 TMEM columns per 8-element chunk
+        }
+#pragma unroll
+        for (int prod = 0; prod < 6; ++prod) {
+          // (A term, B term): hh, hm, mh, hl, mm, lh
+          const int ta = (0x210100 >> (4 * prod)) & 0xF, tb = (0x012010 >> (4 * prod)) & 0xF;
+          for (int kk = 0; kk < seg / 2; ++kk) {
+            const uint64_t db = make_smem_desc(b_addr + (tb * seg + 2 * kk) * (BN * 16), BN * 16, 128);
+            umma_bf16_ts(d_addr, a_tmem + (ta * seg + 2 * kk) * 4, db, idesc, true);
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+        umma_commit(&empty_b[st]);     // operand slot consumed
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> exp2 -> weighted row sums =====
+    const int ew = warp - 2;
+    const int quarter = warp & 3;              // TMEM lanes this warp may touch: 32*quarter .. +31
+    const int half = ew / 4;                   // column share when two warps cover one lane quarter
+    constexpr int NH = NEPI / 4;
+    constexpr int CW = BN / NH;                // columns per warp per tile
+    const int64_t row = (int64_t)row_tile * kTcM + quarter * 32 + lane;
+    if (ew < 4) {
+      // stage this CTA's row operand into TMEM once: thread = row (TMEM lane), 16 bf16 (8 columns) at a time
+      const unsigned char* src = a_imgs + (int64_t)row_tile * a_bytes + (quarter * 32 + lane) * 16;
+      for (int c2 = 0; c2 < kp / 16; ++c2) {
+        const uint4 lo = *reinterpret_cast<const uint4*>(src + (int64_t)(2 * c2) * kTcM * 16);
+        const uint4 hi = *reinterpret_cast<const uint4*>(src + (int64_t)(2 * c2 + 1) * kTcM * 16);
+        const uint32_t r[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        tmem_st8(tmem_base + ((uint32_t)(quarter * 32) << 16) + C::A_COL0 + c2 * 8, r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a);
+    }
+    float acc0 = 0.f, acc1 = 0.f;
+    for (int k = 0; k < nt; ++k) {
+      const int st = k % NSTAGE, acc = k % NACC;
+      mbar_wait(&tmem_full[acc], (k / NACC) & 1);
+      tc_fence_after();
+      const float* wts = reinterpret_cast<const float*>(sb + st * b_bytes + BN * kp * 2);
+      float ts0 = 0.f, ts1 = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < CW; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * CW + c0, v);
+        const float4* w4 = reinterpret_cast<const float4*>(wts + half * CW + c0);
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const float4 w = w4[c / 4];
+          ts0 = fmaf(ex2_approx(v[c + 0]), w.x, ts0);
+          ts1 = fmaf(ex2_approx(v[c + 1]), w.y, ts1);
+          ts0 = fmaf(ex2_approx(v[c + 2]), w.z, ts0);
+          ts1 = fmaf(ex2_approx(v[c + 3]), w.w, ts1);
+        }
+      }
+      acc0 += ts0;
+      acc1 += ts1;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&tmem_empty[acc]);
+        mbar_arrive(&empty_b[st]);
+      }
+    }
+    // two warps may share a row (NEPI = 8): combine through global atomics-free layout [split][half][N]
+    if (row < N) part[((int64_t)split * NH + half) * N + row] = acc0 + acc1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+}  // namespace b200ot

@@ -48,14 +48,19 @@ def _f32c(t, name):
     return t.contiguous()
 
 
-def _check_clouds(x, y):
+MAX_D_TC = 64  # gaussian kernel convolution, forward: tensor-core path for 8 < D <= 64
+
+
+def _check_clouds(x, y, max_d=None):
+    max_d = MAX_D if max_d is None else max_d
     if x.dim() != 2 or y.dim() != 2 or x.shape[1] != y.shape[1]:
         raise ValueError(f"expected x:(N,D), y:(M,D); got {tuple(x.shape)}, {tuple(y.shape)}")
     if x.shape[0] == 0 or y.shape[0] == 0:
         raise ValueError("empty point cloud")
-    if x.shape[1] > MAX_D:
-        raise NotImplementedError(f"D = {x.shape[1]} > {MAX_D}: only D <= {MAX_D} kernels are instantiated in this "
-                                  "build (the large-D tensor-core path is not built yet)")
+    if x.shape[1] > max_d:
+        raise NotImplementedError(f"D = {x.shape[1]} > {max_d}: not instantiated in this build (CUDA-core kernels "
+                                  f"serve D <= {MAX_D}; the tensor-core path serves the gaussian forward up to "
+                                  f"D = {MAX_D_TC})")
     if x.device != y.device:
         raise ValueError("x and y must be on the same device")
 
@@ -175,7 +180,7 @@ def softmin(eps, x, y, h_a, h_b=None, h_scale_b=0.0, *, p=2, center=None, scale_
 def kernel_conv_raw(kind, x, y, w, blur, *, center=None):
     """out_i = sum_j k(x_i, y_j) w_j, no autograd."""
     x, y, w, center = _f32c(x, "x"), _f32c(y, "y"), _f32c(w, "w"), _f32c(center, "center")
-    _check_clouds(x, y)
+    _check_clouds(x, y, MAX_D_TC if kind == "gaussian" else MAX_D)
     N, D = x.shape
     M = y.shape[0]
     if w.numel() != M:
@@ -196,6 +201,7 @@ def kernel_conv_raw(kind, x, y, w, blur, *, center=None):
 def kernel_conv_grad_rows(kind, x, y, w, blur, grad_out, *, center=None):
     x, y, w, center = _f32c(x, "x"), _f32c(y, "y"), _f32c(w, "w"), _f32c(center, "center")
     grad_out = _f32c(grad_out, "grad_out")
+    _check_clouds(x, y)  # row gradients: CUDA-core kernels only (D <= MAX_D)
     N, D = x.shape
     M = y.shape[0]
     dev = x.device

@@ -133,6 +133,8 @@ B200OT_API int b200ot_softmin_bwd_finalize(const float* part, int32_t n_part, co
 /* ---------------------------------------------------------------------------------------------
  * Kernel convolution  —  out_i = sum_j k(x_i, y_j) * w_j      (kernel_samples.py:128-137)
  * ------------------------------------------------------------------------------------------- */
+/* Gaussian forward additionally accepts 8 < D <= 64: that range runs on the tensor cores (tcgen05, bf16x3
+ * split operands, exponent accumulated in TMEM); other kinds / the gradients are limited to D <= B200OT_MAX_D. */
 B200OT_API int64_t b200ot_kernel_conv_scratch_bytes(int64_t N, int64_t M, int32_t D);
 
 B200OT_API int b200ot_kernel_conv_fwd(const float* x, const float* y, const float* w, const float* center, float* out,

@@ -146,6 +146,30 @@ def test_kernel_conv_vs_oracle(kind):
             np.testing.assert_allclose(out.cpu().numpy(), ref, atol=5e-6 * scale + 2e-7 * w.abs().sum().item())
 
 
+@pytest.mark.parametrize("shape", [(300, 500, 16), (129, 65, 33), (1000, 2100, 64), (4000, 3000, 64)])
+def test_gaussian_conv_tensor_core_path(shape):
+    """8 < D <= 64: the exponent comes from tcgen05.mma (bf16x3 split operands, fp32 accumulate in TMEM)."""
+    from geomloss_b200 import ops
+    from oracle import geomloss_oracle as O
+
+    n, m, d = shape
+    g = torch.Generator().manual_seed(n + d)
+    x, y = torch.rand(n, d, generator=g), torch.rand(m, d, generator=g)
+    w = torch.rand(m, generator=g) / m
+    for blur in (2.0, 0.7):  # at D=64, ~unit-cube data, smaller blurs underflow every off-diagonal term
+        ref = O.kernel_conv_points("gaussian", x.double(), y.double(), w.double(), blur).numpy()
+        out = ops.kernel_conv_raw("gaussian", x.to(DEV), y.to(DEV), w.to(DEV), blur,
+                                  center=ops.default_center(x.to(DEV), y.to(DEV))).cpu().numpy()
+        np.testing.assert_allclose(out, ref, rtol=2e-5, atol=1e-30, err_msg=f"blur={blur}")
+    # BASELINE configs[2] regime (blur = .05 at D = 64): |x/blur|^2 ~ 1e4, every off-diagonal term underflows and
+    # the diagonal exponent is a cancellation of three O(6000) numbers; fp32 accumulation (the reference's own
+    # fp32 expansion has ~1e-3 error here, SURVEY.md 8d) bounds the accuracy, the result must stay ~1
+    out = ops.kernel_conv_raw("gaussian", x.to(DEV), x.to(DEV), torch.ones(n, device=DEV), 0.05,
+                              center=ops.default_center(x.to(DEV), x.to(DEV))).cpu().numpy()
+    ref = O.kernel_conv_points("gaussian", x.double(), x.double(), torch.ones(n).double(), 0.05).numpy()
+    np.testing.assert_allclose(out, ref, rtol=2e-2)
+
+
 @pytest.mark.parametrize("kind", ["gaussian", "laplacian", "energy"])
 def test_kernel_conv_gradients_vs_autograd(kind):
     """Row, column and weight gradients of out = K(x,y) @ w against dense fp64 autograd of the oracle."""

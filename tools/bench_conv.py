@@ -1,0 +1,37 @@
+"""Time the kernel-convolution entry points (CUDA events, L2 flushed between reps).
+    python tools/bench_conv.py [N] [D ...]
+"""
+import json
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from geomloss_b200 import ops  # noqa: E402
+
+dev = "cuda:0"
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
+dims = [int(a) for a in sys.argv[2:]] or [3, 16, 32, 64]
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+for D in dims:
+    g = torch.Generator().manual_seed(D)
+    x = torch.rand(N, D, generator=g).to(dev)
+    y = torch.rand(N, D, generator=g).to(dev)
+    w = torch.full((N,), 1.0 / N, device=dev)
+    c = ops.default_center(x, y)
+    for kind in (("gaussian",) if D > 8 else ("gaussian", "laplacian", "energy")):
+        blur = 2.0 if D > 8 else 0.1
+        ops.kernel_conv_raw(kind, x, y, w, blur, center=c)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = ops.kernel_conv_raw(kind, x, y, w, blur, center=c)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = min(ts)
+        print(json.dumps({"conv": kind, "N": N, "M": N, "D": D, "ms": round(ms, 3),
+                          "Tpairs_s": round(N * N / (ms * 1e-3) / 1e12, 3), "sum": float(out.sum())}))
