@@ -9,6 +9,7 @@ Operator level (the reference's softmin seam):  ``geomloss_b200.ops.softmin`` / 
 C ABI: ``include/b200ot.h`` (``geomloss_b200/libb200ot.so``, built by ``__graft_entry__.build()``).
 """
 from .samples_loss import SamplesLoss  # noqa: F401
+from .sinkhorn_images import sinkhorn_divergence  # noqa: F401  (the reference exports the IMAGE routine here)
 
 __version__ = "0.1.0"
-__all__ = ["SamplesLoss"]
+__all__ = ["SamplesLoss", "sinkhorn_divergence"]

@@ -44,6 +44,8 @@ _SIGNATURES = {
                                          c_int64, _P]),
     "b200ot_kernel_conv_bwd_x": (c_int32, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int32, c_int32, c_float, _P,
                                            c_int64, _P]),
+    "b200ot_softmin_grid": (c_int32, [_P, _P, c_float, _P, c_float, c_float, _P, c_int64, c_int32, c_int32, c_int32,
+                                      c_float, _P]),
     "b200ot_ubench": (c_int32, [c_int32, c_int32, c_int32, _P, ctypes.POINTER(c_int32), _P]),
 }
 

@@ -1,0 +1,214 @@
+// b200ot — separable soft-C-transform on regular grids (images / volumes).
+// Reference semantics: softmin_grid (src/geomloss/_legacy/utils.py:190-279), called by the image Sinkhorn
+// loop (src/geomloss/_legacy/sinkhorn_images.py:26-202): for a (batch, N, N[, N]) array h and the cost
+// |x - y|^p / p on the pixel grid x = arange(N)/N, the softmin over the whole grid factorises into one
+// 1-D log-sum-exp per axis,
+//     out[.., i, ..] = log sum_j exp( in[.., j, ..] - k(x_i - x_j) ),   k(d) = d^2/(2 eps)  (p = 2),  |d|/eps  (p = 1)
+// applied along every axis in turn, followed by a multiplication by -eps.
+//
+// One pass = one launch of grid_pass_kernel over the tensor viewed as [outer][N][inner]: a CTA loads a
+// tile of 32 lines (all N entries along the axis) into shared memory with coalesced accesses — along the
+// contiguous direction for the strided passes, transposed for the last axis — then every thread owns 8
+// outputs of one line at a time and sweeps the N inputs (conflict-free LDS, lanes = lines): direct
+// differences on the integer grid (exact), lazy-max log-sum-exp in the log2 domain with the same 2^64 sum
+// guard as softmin.cuh, 1 MUFU.EX2 per (output, input) pair.  Results are staged in a second shared tile
+// and written back with the access pattern of the load, so passes run in place.
+// Work per pass: N^(dim+1) pairs -> SFU-bound like the point-cloud softmin (256^3: 4.3e9 pairs, ~1 ms);
+// HBM traffic 2 x 4 N^dim bytes per pass.
+#include <math.h>
+
+#include "b200ot.h"
+#include "common.cuh"
+#include "host_util.cuh"
+
+namespace b200ot {
+
+constexpr int kGridTW = 32;  // lines per CTA tile (one per lane)
+constexpr int kGridRS = kGridTW + 1;
+constexpr int kGridR = 8;  // outputs per thread per sweep
+constexpr int kGridWarps = 8;
+
+struct GridPassArgs {
+  const float* h_a;      // first pass: input = in_scale * (h_a + h_scale_b * h_b); later passes read `out` in place
+  const float* h_b;      // nullable
+  const float* out_old;  // last pass only, nullable
+  float* out;
+  float h_scale_b, in_scale, alpha_old, beta, out_scale, xscale;
+  int N, first, last;
+  int64_t outer, inner;
+};
+
+template <int P>
+__global__ void __launch_bounds__(kGridWarps * 32) grid_pass_kernel(GridPassArgs A) {
+  extern __shared__ float smem_f[];
+  float* tile = smem_f;                      // [N][33] inputs
+  float* otile = smem_f + A.N * kGridRS;     // [N][33] outputs
+  const int N = A.N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool last_axis = (A.inner == 1);
+  int64_t o, w0;
+  int nw;  // live lines in this tile
+  if (last_axis) {
+    o = (int64_t)blockIdx.x * kGridTW;
+    w0 = 0;
+    nw = (int)min((int64_t)kGridTW, A.outer - o);
+  } else {
+    const int64_t tiles_in = (A.inner + kGridTW - 1) / kGridTW;
+    o = blockIdx.x / tiles_in;
+    w0 = (blockIdx.x % tiles_in) * kGridTW;
+    nw = (int)min((int64_t)kGridTW, A.inner - w0);
+  }
+
+  // ---- load ----
+  for (int idx = threadIdx.x; idx < N * kGridTW; idx += blockDim.x) {
+    int j, w;
+    if (last_axis) {
+      w = idx / N;
+      j = idx % N;
+    } else {
+      j = idx / kGridTW;
+      w = idx % kGridTW;
+    }
+    float v = -INFINITY;
+    if (w < nw) {
+      const int64_t gi = last_axis ? ((o + w) * N + j) : ((o * N + j) * A.inner + w0 + w);
+      if (A.first) {
+        v = A.h_a[gi];
+        if (A.h_b) v = fmaf(A.h_scale_b, A.h_b[gi], v);
+        v *= A.in_scale;
+      } else {
+        v = A.out[gi];
+      }
+    }
+    tile[j * kGridRS + w] = v;
+  }
+  __syncthreads();
+
+  // ---- sweep: warp g owns outputs [g*per_warp, (g+1)*per_warp) of every line of the tile ----
+  const int per_warp = (N + kGridWarps - 1) / kGridWarps;
+  const int i_end = min(N, (warp + 1) * per_warp);
+  for (int ib = warp * per_warp; ib < i_end; ib += kGridR) {
+    float xi[kGridR], m[kGridR], s[kGridR];
+#pragma unroll
+    for (int r = 0; r < kGridR; ++r) {
+      xi[r] = A.xscale * (float)(ib + r);
+      m[r] = kNegBig;
+      s[r] = 0.f;
+    }
+    for (int j0 = 0; j0 < N; j0 += 8) {
+      float a[8], xj[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        a[c] = (j0 + c < N) ? tile[(j0 + c) * kGridRS + lane] : -INFINITY;
+        xj[c] = A.xscale * (float)(j0 + c);
+      }
+#pragma unroll
+      for (int r = 0; r < kGridR; ++r) {
+        float t[8];
+        float cs = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float d = xi[r] - xj[c];
+          t[c] = (P == 2) ? fmaf(-d, d, a[c]) : a[c] - fabsf(d);
+          cs += ex2_approx(t[c] - m[r]);
+        }
+        if (!(cs <= 1.8446744e19f)) {
+          // outdated max (or first chunk): rebase on this chunk's max and redo it
+          float cm = t[0];
+#pragma unroll
+          for (int c = 1; c < 8; ++c) cm = fmaxf(cm, t[c]);
+          cs = 0.f;
+          if (cm > kNegBig) {  // otherwise every input of the chunk is -inf: nothing to add
+            s[r] *= ex2_approx(m[r] - cm);
+            m[r] = cm;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) cs += ex2_approx(t[c] - cm);
+          }
+        }
+        s[r] += cs;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kGridR; ++r) {
+      const int i = ib + r;
+      if (i < i_end) {
+        int e = 0;
+        const float f = frexpf(s[r], &e);  // log2(s) = e + log2(f), f in [0.5, 1): exact exponent, accurate mantissa
+        otile[i * kGridRS + lane] = (s[r] > 0.f) ? (m[r] + (float)e) + log2f(f) : -INFINITY;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- store (same access pattern as the load) ----
+  for (int idx = threadIdx.x; idx < N * kGridTW; idx += blockDim.x) {
+    int j, w;
+    if (last_axis) {
+      w = idx / N;
+      j = idx % N;
+    } else {
+      j = idx / kGridTW;
+      w = idx % kGridTW;
+    }
+    if (w >= nw) continue;
+    const int64_t gi = last_axis ? ((o + w) * N + j) : ((o * N + j) * A.inner + w0 + w);
+    float v = otile[j * kGridRS + w];
+    if (A.last) {
+      v = A.beta * (A.out_scale * v);
+      if (A.out_old) v = fmaf(A.alpha_old, A.out_old[gi], v);
+    }
+    A.out[gi] = v;
+  }
+}
+
+}  // namespace b200ot
+
+using namespace b200ot;
+
+extern "C" {
+
+B200OT_API int b200ot_softmin_grid(const float* h_a, const float* h_b, float h_scale_b, const float* out_old,
+                                   float alpha_old, float beta, float* out, int64_t batch, int32_t N, int32_t dim,
+                                   int32_t p, float eps, void* stream) {
+  if (!h_a || !out || batch <= 0 || N <= 0 || N > 1024 || dim < 1 || dim > 3 || (p != 1 && p != 2) || !(eps > 0.f))
+    return B200OT_EINVAL;
+  if (out == h_a || out == h_b || (out_old && out == out_old)) return B200OT_EINVAL;  // passes run in place on `out`
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t total = batch;
+  for (int d = 0; d < dim; ++d) total *= N;
+  // pixel coordinates x = arange(N)/N, scaled so that the log2-domain exponent is in - (X_i - X_j)^2  (p = 2)
+  // or in - |X_i - X_j|  (p = 1)                                                          (utils.py:235-242)
+  const float xscale = (p == 2 ? sqrtf(kLog2e / (2.0f * eps)) : kLog2e / eps) / (float)N;
+  const size_t smem = (size_t)2 * N * kGridRS * sizeof(float);
+  auto kern = (p == 2) ? grid_pass_kernel<2> : grid_pass_kernel<1>;
+  B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // pass order of the reference: last axis first, then the others (the passes commute mathematically)
+  for (int k = 0; k < dim; ++k) {
+    const int axis = dim - 1 - k;  // 0 .. dim-1 within the (N, .., N) block
+    GridPassArgs a;
+    a.h_a = h_a;
+    a.h_b = h_b;
+    a.out_old = out_old;
+    a.out = out;
+    a.h_scale_b = h_scale_b;
+    a.in_scale = kLog2e;
+    a.alpha_old = alpha_old;
+    a.beta = beta;
+    a.out_scale = -eps * kLn2;
+    a.xscale = xscale;
+    a.N = N;
+    a.first = (k == 0);
+    a.last = (k == dim - 1);
+    int64_t inner = 1;
+    for (int d = axis + 1; d < dim; ++d) inner *= N;
+    a.inner = inner;
+    a.outer = total / ((int64_t)N * inner);
+    const int64_t blocks =
+        (inner == 1) ? ceil_div64(a.outer, kGridTW) : a.outer * ceil_div64(inner, kGridTW);
+    kern<<<(unsigned)blocks, kGridWarps * 32, smem, st>>>(a);
+    B200OT_CUDA_TRY(cudaGetLastError());
+  }
+  return B200OT_OK;
+}
+
+}  // extern "C"

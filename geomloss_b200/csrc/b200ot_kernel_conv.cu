@@ -136,7 +136,7 @@ struct TcPlan {
   int64_t off_b, off_part, total;
 };
 
-static bool tc_supported_dim(int D) { return D > B200OT_MAX_D && D <= 64; }
+bool tc_supported_dim(int D) { return D > B200OT_MAX_D && D <= 64; }
 
 static TcPlan make_tc_plan(int64_t N, int64_t M, int D) {
   TcPlan p;
@@ -158,8 +158,40 @@ static TcPlan make_tc_plan(int64_t N, int64_t M, int D) {
   p.n_split = (int)ceil_div64(p.b_tiles, p.tiles_per_split);
   p.off_b = round_up64(p.a_tiles * p.a_bytes, 256);
   p.off_part = p.off_b + round_up64(p.b_tiles * p.b_bytes, 256);
-  p.total = p.off_part + round_up64((int64_t)p.n_split * (kTcEpi / 4) * N * 4, 256);
+  p.total = p.off_part + round_up64((int64_t)p.n_split * (kTcEpi / 4) * N * 8, 256);  // (m, s) pairs at most
   return p;
+}
+
+int64_t tc_scratch_bytes(int64_t N, int64_t M, int D) { return make_tc_plan(N, M, D).total; }
+
+// Tensor-core softmin partials (p = 2): packs both clouds, runs the reduction, leaves n_part (m, s) sets in
+// `*part_out` (inside scratch) for b200ot_softmin_finalize.
+int softmin_partial_tc(const float* x, const float* y, const float* h_a, const float* h_b, float h_scale_b,
+                       const float* center, int64_t N, int64_t M, int D, float eps, void* scratch,
+                       float** part_out, int* n_part_out, cudaStream_t st) {
+  const TcPlan p = make_tc_plan(N, M, D);
+  if (p.nstage < 1) return B200OT_EINVAL;
+  unsigned char* base = reinterpret_cast<unsigned char*>(scratch);
+  unsigned char* a_imgs = base;
+  unsigned char* b_imgs = base + p.off_b;
+  float* part = reinterpret_cast<float*>(base + p.off_part);
+  const float scale = softmin_coord_scale(2, eps);
+  const int threads = 128;
+  tc_pack_kernel<<<(unsigned)ceil_div64(p.a_tiles * kTcM, threads), threads, 0, st>>>(
+      x, nullptr, nullptr, nullptr, 0.f, 0.f, center, scale, N, D, p.kp, kTcM, 0, a_imgs);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  tc_pack_kernel<<<(unsigned)ceil_div64(p.b_tiles * kTcBN, threads), threads, 0, st>>>(
+      y, nullptr, h_a, h_b, h_scale_b, kLog2e, center, scale, M, D, p.kp, kTcBN, 1, b_imgs);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  auto kern = tc_reduce_kernel<TcConvCfg, 1>;
+  B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  dim3 grid((unsigned)p.a_tiles, (unsigned)p.n_split);
+  kern<<<grid, TcConvCfg::THREADS, (size_t)p.smem, st>>>(a_imgs, b_imgs, part, N, p.kp, (int)p.b_tiles,
+                                                        p.tiles_per_split, p.nstage);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  *part_out = part;
+  *n_part_out = p.n_split * (kTcEpi / 4);
+  return B200OT_OK;
 }
 
 static int conv_fwd_tc(const float* x, const float* y, const float* w, const float* center, float* out, int64_t N,
@@ -173,12 +205,12 @@ static int conv_fwd_tc(const float* x, const float* y, const float* w, const flo
   const float scale = sqrtf(kLog2e) / blur;
   const int threads = 128;
   tc_pack_kernel<<<(unsigned)ceil_div64(p.a_tiles * kTcM, threads), threads, 0, st>>>(
-      x, nullptr, center, scale, N, D, p.kp, kTcM, 0, a_imgs);
+      x, nullptr, nullptr, nullptr, 0.f, 0.f, center, scale, N, D, p.kp, kTcM, 0, a_imgs);
   B200OT_CUDA_TRY(cudaGetLastError());
   tc_pack_kernel<<<(unsigned)ceil_div64(p.b_tiles * kTcBN, threads), threads, 0, st>>>(
-      y, w, center, scale, M, D, p.kp, kTcBN, 1, b_imgs);
+      y, w, nullptr, nullptr, 0.f, 0.f, center, scale, M, D, p.kp, kTcBN, 1, b_imgs);
   B200OT_CUDA_TRY(cudaGetLastError());
-  auto kern = gauss_tc_kernel<TcConvCfg>;
+  auto kern = tc_reduce_kernel<TcConvCfg, 0>;
   B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   dim3 grid((unsigned)p.a_tiles, (unsigned)p.n_split);
   kern<<<grid, TcConvCfg::THREADS, (size_t)p.smem, st>>>(a_imgs, b_imgs, part, N, p.kp, (int)p.b_tiles,

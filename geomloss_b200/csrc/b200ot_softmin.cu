@@ -144,6 +144,7 @@ B200OT_API int32_t b200ot_softmin_num_splits(int64_t N, int64_t M, int32_t D) {
 
 B200OT_API int64_t b200ot_softmin_scratch_bytes(int64_t N, int64_t M, int32_t D) {
   if (N <= 0 || M <= 0 || D <= 0) return 0;
+  if (tc_supported_dim(D)) return tc_scratch_bytes(N, M, D);
   const ReducePlan pl = make_plan(N, M);
   const int64_t cols = b200ot_packed_cols_floats(M, D, 1) * 4;
   // forward partials are (m, s) pairs; the backward pass keeps D+1 sums per (split, row)
@@ -197,11 +198,20 @@ B200OT_API int b200ot_softmin_fwd(const float* x, const float* y, const float* h
                                   float h_scale_b, const float* center, const float* out_old, float alpha_old,
                                   float beta, float* out, float* lse2_out, int64_t N, int64_t M, int32_t D,
                                   int32_t p, float eps, void* scratch, int64_t scratch_bytes, void* stream) {
-  if (!x || !y || !h_a || !scratch || N <= 0 || M <= 0 || !supported_simt_dim(D) || (p != 1 && p != 2) ||
+  const bool tc = tc_supported_dim(D) && p == 2;  // 8 < D <= 64: exponent from the tensor cores (tcconv.cuh)
+  if (!x || !y || !h_a || !scratch || N <= 0 || M <= 0 || (!supported_simt_dim(D) && !tc) || (p != 1 && p != 2) ||
       !(eps > 0.f) || (!out && !lse2_out))
     return B200OT_EINVAL;
   if (((uintptr_t)scratch) & 15) return B200OT_EALIGN;
   if (scratch_bytes < b200ot_softmin_scratch_bytes(N, M, D)) return B200OT_ESCRATCH;
+  if (tc) {
+    float* tc_part = nullptr;
+    int n_part = 0;
+    const int rc = softmin_partial_tc(x, y, h_a, h_b, h_scale_b, center, N, M, D, eps, scratch, &tc_part, &n_part,
+                                      (cudaStream_t)stream);
+    if (rc) return rc;
+    return b200ot_softmin_finalize(tc_part, n_part, out_old, alpha_old, beta, out, lse2_out, N, eps, stream);
+  }
   const ReducePlan pl = make_plan(N, M);
   float* cols = reinterpret_cast<float*>(scratch);
   float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) +

@@ -30,6 +30,13 @@ inline float softmin_coord_scale(int p, float eps) {
 int softmin_pack_impl(const float* y, const float* h_a, const float* h_b, float h_scale_b, const float* center,
                       int64_t M, int D, int p, float eps, float* cols_out, cudaStream_t st);
 
+// Tensor-core (tcgen05) path for 8 < D <= 64, defined in b200ot_kernel_conv.cu.
+bool tc_supported_dim(int D);
+int64_t tc_scratch_bytes(int64_t N, int64_t M, int D);
+int softmin_partial_tc(const float* x, const float* y, const float* h_a, const float* h_b, float h_scale_b,
+                       const float* center, int64_t N, int64_t M, int D, float eps, void* scratch,
+                       float** part_out, int* n_part_out, cudaStream_t st);
+
 #define B200OT_STR2(x) #x
 #define B200OT_STR(x) B200OT_STR2(x)
 #define B200OT_CUDA_TRY(expr)                                                         \

@@ -51,9 +51,15 @@ __device__ __forceinline__ uint4 pack8_bf16(const __nv_bfloat16* src) {
   return v;
 }
 
+// Column images carry, besides the split coordinates, the per-column additive exponent term
+//   c_j = h_scale * (h_a[j] + h_scale_b * h_b[j]) - |Y_j|^2 / 2      (h_a null: just the fold)
+// in the rank-one chunk, and the fp32 weight w_j (kernel conv) behind the bf16 data.  Padding columns get
+// c = -1e38 when h_a is given (softmin: they must vanish from the log-sum-exp) and w = 0 otherwise.
 static __global__ void tc_pack_kernel(const float* __restrict__ pts, const float* __restrict__ w,
-                                      const float* __restrict__ center, float scale, int64_t n, int D, int kp,
-                                      int tile, int is_cols, unsigned char* __restrict__ out) {
+                                      const float* __restrict__ h_a, const float* __restrict__ h_b,
+                                      float h_scale_b, float h_scale, const float* __restrict__ center,
+                                      float scale, int64_t n, int D, int kp, int tile, int is_cols,
+                                      unsigned char* __restrict__ out) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t npad = ((n + tile - 1) / tile) * tile;
   if (p >= npad) return;
@@ -85,7 +91,16 @@ static __global__ void tc_pack_kernel(const float* __restrict__ pts, const float
   }
   // rank-one chunk (16 wide): rows [1,1,1, r_h,r_m,r_l, 0..]   columns [c_h,c_m,c_l, 1,1,1, 0..]
   {
-    const float r = live ? -0.5f * sq : 0.f;
+    float r = live ? -0.5f * sq : 0.f;
+    if (is_cols && h_a != nullptr) {
+      if (live) {
+        float h = h_a[p];
+        if (h_b != nullptr) h = fmaf(h_scale_b, h_b[p], h);
+        r = fmaf(h_scale, h, r);
+      } else {
+        r = -1.0e38f;
+      }
+    }
     const __nv_bfloat16 rh = __float2bfloat16_rn(r);
     const float q1 = r - __bfloat162float(rh);
     const __nv_bfloat16 rm = __float2bfloat16_rn(q1);
@@ -128,10 +143,13 @@ struct TcCfg {
   static_assert(BN % 64 == 0 && BN <= 256, "unsupported column tile");
 };
 
-template <class C>
+// MODE 0: gaussian kernel conv  part[(split*NH + half)*N + row]   = sum_j w_j 2^S_ij
+// MODE 1: softmin               part2[(split*NH + half)*N + row]  = (m, s) with sum_j 2^S_ij = s 2^m  (lazy max,
+//         sum-guarded exactly like softmin.cuh; same partial format as softmin_partial_kernel)
+template <class C, int MODE>
 __global__ void __launch_bounds__(C::THREADS, 1)
-    gauss_tc_kernel(const unsigned char* __restrict__ a_imgs, const unsigned char* __restrict__ b_imgs,
-                    float* __restrict__ part, int64_t N, int kp, int ntiles_b, int tiles_per_split, int NSTAGE) {
+    tc_reduce_kernel(const unsigned char* __restrict__ a_imgs, const unsigned char* __restrict__ b_imgs,
+                     float* __restrict__ part, int64_t N, int kp, int ntiles_b, int tiles_per_split, int NSTAGE) {
   constexpr int BN = C::BN, NEPI = C::NEPI, NACC = C::NACC;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int a_bytes = kTcM * kp * 2;
@@ -234,7 +252,8 @@ __global__ void __launch_bounds__(C::THREADS, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_a);
     }
-    float acc0 = 0.f, acc1 = 0.f;
+    float acc0 = 0.f, acc1 = 0.f;      // MODE 0: weighted sums
+    float m = kNegBig, srun = 0.f;     // MODE 1: running (m, s)
     for (int k = 0; k < nt; ++k) {
       const int st = k % NSTAGE, acc = k % NACC;
       mbar_wait(&tmem_full[acc], (k / NACC) & 1);
@@ -245,18 +264,51 @@ __global__ void __launch_bounds__(C::THREADS, 1)
       for (int c0 = 0; c0 < CW; c0 += 32) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * CW + c0, v);
-        const float4* w4 = reinterpret_cast<const float4*>(wts + half * CW + c0);
+        if constexpr (MODE == 0) {
+          const float4* w4 = reinterpret_cast<const float4*>(wts + half * CW + c0);
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          const float4 w = w4[c / 4];
-          ts0 = fmaf(ex2_approx(v[c + 0]), w.x, ts0);
-          ts1 = fmaf(ex2_approx(v[c + 1]), w.y, ts1);
-          ts0 = fmaf(ex2_approx(v[c + 2]), w.z, ts0);
-          ts1 = fmaf(ex2_approx(v[c + 3]), w.w, ts1);
+          for (int c = 0; c < 32; c += 4) {
+            const float4 w = w4[c / 4];
+            ts0 = fmaf(ex2_approx(v[c + 0]), w.x, ts0);
+            ts1 = fmaf(ex2_approx(v[c + 1]), w.y, ts1);
+            ts0 = fmaf(ex2_approx(v[c + 2]), w.z, ts0);
+            ts1 = fmaf(ex2_approx(v[c + 3]), w.w, ts1);
+          }
+        } else {
+          float cs0 = 0.f, cs1 = 0.f;
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            cs0 += ex2_approx(v[c] - m);
+            cs1 += ex2_approx(v[c + 1] - m);
+          }
+          if (!(cs0 + cs1 <= 1.8446744e19f)) {
+            // outdated max (a term above 2^64 or an overflow): rebase on this chunk's max and redo it
+            float cm = v[0];
+#pragma unroll
+            for (int c = 1; c < 32; ++c) cm = fmaxf(cm, v[c]);
+            const float sc = ex2_approx(m - cm);
+            srun *= sc;
+            ts0 *= sc;
+            ts1 *= sc;
+            m = cm;
+            cs0 = 0.f;
+            cs1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+              cs0 += ex2_approx(v[c] - m);
+              cs1 += ex2_approx(v[c + 1] - m);
+            }
+          }
+          ts0 += cs0;
+          ts1 += cs1;
         }
       }
-      acc0 += ts0;
-      acc1 += ts1;
+      if constexpr (MODE == 0) {
+        acc0 += ts0;
+        acc1 += ts1;
+      } else {
+        srun += ts0 + ts1;
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -264,8 +316,13 @@ __global__ void __launch_bounds__(C::THREADS, 1)
         mbar_arrive(&empty_b[st]);
       }
     }
-    // two warps may share a row (NEPI = 8): combine through global atomics-free layout [split][half][N]
-    if (row < N) part[((int64_t)split * NH + half) * N + row] = acc0 + acc1;
+    if (row < N) {
+      if constexpr (MODE == 0) {
+        part[((int64_t)split * NH + half) * N + row] = acc0 + acc1;
+      } else {
+        reinterpret_cast<float2*>(part)[((int64_t)split * NH + half) * N + row] = make_float2(m, srun);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();

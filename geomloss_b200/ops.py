@@ -48,7 +48,7 @@ def _f32c(t, name):
     return t.contiguous()
 
 
-MAX_D_TC = 64  # gaussian kernel convolution, forward: tensor-core path for 8 < D <= 64
+MAX_D_TC = 64  # forward softmin (p = 2) and gaussian kernel convolution: tensor-core path for 8 < D <= 64
 
 
 def _check_clouds(x, y, max_d=None):
@@ -99,7 +99,7 @@ def softmin_raw(eps, x, y, h_a, h_b=None, h_scale_b=0.0, *, p=2, center=None, ou
     """
     x, y, h_a, h_b = _f32c(x, "x"), _f32c(y, "y"), _f32c(h_a, "h_a"), _f32c(h_b, "h_b")
     center, out_old = _f32c(center, "center"), _f32c(out_old, "out_old")
-    _check_clouds(x, y)
+    _check_clouds(x, y, MAX_D_TC if p == 2 else MAX_D)
     N, D = x.shape
     M = y.shape[0]
     if h_a.numel() != M or (h_b is not None and h_b.numel() != M):
@@ -124,6 +124,7 @@ def softmin_grad_rows(eps, x, y, h_a, h_b, h_scale_b, lse2, grad_out, *, p=2, ce
     """grad_x of <grad_out, softmin(eps, (x, y), h)> with y, h constant (b200ot_softmin_bwd_x)."""
     x, y, h_a, h_b = _f32c(x, "x"), _f32c(y, "y"), _f32c(h_a, "h_a"), _f32c(h_b, "h_b")
     center, lse2, grad_out = _f32c(center, "center"), _f32c(lse2, "lse2"), _f32c(grad_out, "grad_out")
+    _check_clouds(x, y)  # row gradients: CUDA-core kernels only (D <= MAX_D)
     N, D = x.shape
     M = y.shape[0]
     dev = x.device

@@ -147,6 +147,18 @@ B200OT_API int b200ot_kernel_conv_bwd_x(const float* x, const float* y, const fl
                              float blur, void* scratch, int64_t scratch_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Grid softmin  —  the separable soft-C-transform on (batch, N, N[, N]) images / volumes
+ * replaces softmin_grid (src/geomloss/_legacy/utils.py:190-279), the operator of the image Sinkhorn loop
+ * (src/geomloss/_legacy/sinkhorn_images.py:26-202):
+ *   out <- alpha_old * out_old + beta * ( -eps * LSE over the whole grid of  h - |x - y|^p / (p eps) ),
+ *   h = h_a + h_scale_b * h_b (h_b nullable), pixel coordinates arange(N)/N, p in {1, 2}, dim in {1, 2, 3}.
+ * `out` must not alias an input (the per-axis passes run in place on it).  N <= 1024.
+ * ------------------------------------------------------------------------------------------- */
+B200OT_API int b200ot_softmin_grid(const float* h_a, const float* h_b, float h_scale_b, const float* out_old,
+                                   float alpha_old, float beta, float* out, int64_t batch, int32_t N, int32_t dim,
+                                   int32_t p, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Pipe-ceiling micro-benchmarks (used by bench.py to measure the MUFU / FP32 roofline of the
  * device it runs on; each launches one kernel doing `iters` dependent steps per thread and
  * returns the number of operations executed per thread-step through *ops_per_thread_iter).

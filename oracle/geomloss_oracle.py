@@ -4,9 +4,10 @@ TEST INFRASTRUCTURE ONLY.  This file is a from-scratch restatement, in plain tor
 algorithm the reference's ``backend="tensorized"`` path runs.  It exists so that the CUDA engine in
 ``geomloss_b200`` can be checked on the GPU box, where ``/root/reference`` does not exist.  Only
 ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference`` legs may
-import it; the product package never does (``tests/test_no_oracle_in_product.py`` enforces this).
+import it; the product package never does (``tests/test_host_logic.py`` enforces this).
 
-Parity status: PINNED.  ``tests/golden/make_golden.py`` imports the real reference from
+Parity status: PINNED for the point-cloud path (everything above the "grids" block at the end of this
+file, which is UNPINNED — see the note there).  ``tests/golden/make_golden.py`` imports the real reference from
 ``/root/reference/src`` in the build container, runs it on seeded inputs and stores its outputs in
 ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks every function below against those
 fixtures (the reference itself ships no test for this path — SURVEY.md section 4).
@@ -301,3 +302,102 @@ def pair_interactions(n_eps: int, N: int, M: int, debias: bool = True) -> float:
     """pair-interactions evaluated by one loss call."""
     per_iter = 2.0 * N * M + (float(N) * N + float(M) * M if debias else 0.0)
     return (n_eps + 2) * per_iter
+
+
+# ------------------------------------------------------------------------------------------------
+# grids (images / volumes)                  utils.py:69-108, :190-279 ; sinkhorn_images.py:26-202
+#
+# PARITY UNPINNED for this block: the reference's softmin_grid needs pykeops (absent, un-vendored), so no
+# golden output of the reference exists for it.  The restatement below follows the reference line by
+# line with dense torch broadcasting in place of the KeOps LazyTensor reduction, and
+# tests/test_oracle_golden.py::test_grid_softmin_is_the_full_grid_softmin checks it against the PINNED
+# point-cloud softmin evaluated on the explicit pixel coordinates (the separable form must equal the
+# full N^D x N^D soft-C-transform).
+# ------------------------------------------------------------------------------------------------
+
+
+def grid_pyramid(t):
+    from torch.nn.functional import avg_pool2d, avg_pool3d
+
+    d = t.dim() - 2
+    levels = [t]
+    for _ in range(int(np.log2(t.shape[2]))):
+        t = 4 * avg_pool2d(t, 2) if d == 2 else 8 * avg_pool3d(t, 2)
+        levels.append(t)
+    levels.reverse()
+    return levels
+
+
+def grid_upsample(t):
+    from torch.nn.functional import interpolate
+
+    return interpolate(t, scale_factor=2, mode="bilinear" if t.dim() == 4 else "trilinear", align_corners=False)
+
+
+def grid_log_dens(a):
+    out = a.log()
+    out[a <= 0] = -10000.0
+    return out
+
+
+def softmin_grid_dense(eps, p, h):
+    """-eps * (separable log-sum-exp along every grid axis) for h:(B,K,N,N) or (B,K,N,N,N).   utils.py:190-279"""
+    d = h.dim() - 2
+    n = h.shape[-1]
+    x = torch.arange(n).type_as(h) / n
+    x = x / eps if p == 1 else x / np.sqrt(2 * eps)
+    diff = x[:, None] - x[None, :]
+    kmat = -(diff.abs() if p == 1 else diff**2)  # (N_i, N_j)
+
+    def along_last(t):  # out[..., i] = LSE_j(t[..., j] + kmat[i, j])
+        return torch.logsumexp(t.unsqueeze(-2) + kmat, dim=-1)
+
+    for axis in range(d):
+        h = along_last(h.transpose(-1, -1 - axis)).transpose(-1, -1 - axis)
+    return -eps * h
+
+
+def sinkhorn_images(a, b, p=2, blur=None, reach=None, scaling=0.5, debias=True, potentials=False):
+    """Multiscale Sinkhorn divergence on grids.                               sinkhorn_images.py:26-202"""
+    if blur is None:
+        blur = 1 / a.shape[-1]
+    a_s, b_s = grid_pyramid(a)[1:], grid_pyramid(b)[1:]
+    a_logs, b_logs = [grid_log_dens(t) for t in a_s], [grid_log_dens(t) for t in b_s]
+    eps_final, rho = blur**p, (None if reach is None else reach**p)
+    eps_list = epsilon_schedule(p, 1, blur, scaling)
+    scales = [1 / t.shape[-1] for t in a_s]
+    cur = scales.pop(0)
+    jumps = []
+    for i, eps in enumerate(eps_list[1:]):
+        if cur**p > eps:
+            jumps.append(i + 1)
+            cur = scales.pop(0)
+    assert len(jumps) == len(a_s) - 1
+    sm = softmin_grid_dense
+    last = True
+    with torch.no_grad():
+        k, eps = 0, eps_list[0]
+        lam = damping(eps, rho)
+        a_log, b_log = a_logs[0], b_logs[0]
+        g_ab, f_ba = lam * sm(eps, p, a_log), lam * sm(eps, p, b_log)
+        f_aa, g_bb = lam * sm(eps, p, a_log), lam * sm(eps, p, b_log)
+        for i, eps in enumerate(eps_list):
+            lam = damping(eps, rho)
+            ft_ba = lam * sm(eps, p, b_log + g_ab / eps)
+            gt_ab = lam * sm(eps, p, a_log + f_ba / eps)
+            ft_aa = lam * sm(eps, p, a_log + f_aa / eps)
+            gt_bb = lam * sm(eps, p, b_log + g_bb / eps)
+            f_ba, g_ab = 0.5 * (f_ba + ft_ba), 0.5 * (g_ab + gt_ab)
+            f_aa, g_bb = 0.5 * (f_aa + ft_aa), 0.5 * (g_bb + gt_bb)
+            if i in jumps:
+                if i == len(eps_list) - 1:
+                    last = False
+                f_ba, g_ab = grid_upsample(f_ba), grid_upsample(g_ab)
+                f_aa, g_bb = grid_upsample(f_aa), grid_upsample(g_bb)
+                k += 1
+                a_log, b_log = a_logs[k], b_logs[k]
+        if last:
+            f_ba, g_ab = (lam * sm(eps, p, b_log + g_ab / eps), lam * sm(eps, p, a_log + f_ba / eps))
+            f_aa = lam * sm(eps, p, a_log + f_aa / eps)
+            g_bb = lam * sm(eps, p, b_log + g_bb / eps)
+    return sinkhorn_value(eps_final, rho, a, b, f_aa, g_bb, g_ab, f_ba, debias=debias, potentials=potentials)

@@ -131,3 +131,29 @@ def test_counting_helpers():
     # 40 softmins (debias) / 20 at 8 eps values; BASELINE.md: 2.12e14 pairs at cfg 2
     assert O.n_softmins(8, True) == 40 and O.n_softmins(8, False) == 20
     assert abs(O.pair_interactions(51, 10**6, 10**6) - 2.12e14) < 1e12
+
+
+@pytest.mark.parametrize("d,n", [(2, 8), (3, 4)])
+def test_grid_softmin_is_the_full_grid_softmin(d, n):
+    """The (unpinned) grid restatement must equal the pinned dense softmin on the explicit pixel coordinates:
+    p=2: cost |x-y|^2/2; p=1: the per-axis (L1) cost the separable reference formula implies."""
+    g = torch.Generator().manual_seed(d)
+    h = torch.randn(1, 1, *([n] * d), generator=g, dtype=torch.float64)
+    coords = torch.stack(torch.meshgrid(*[torch.arange(n, dtype=torch.float64) / n] * d, indexing="ij"), -1).reshape(-1, d)
+    for p in (1, 2):
+        C = O.cost_matrix(coords, coords, 2) if p == 2 else (coords[:, None, :] - coords[None, :, :]).abs().sum(-1)
+        for eps in (0.5, 0.02):
+            ref = O.softmin_dense(eps, C[None], h.reshape(1, -1))[0]
+            got = O.softmin_grid_dense(eps, p, h).reshape(-1)
+            assert (got - ref).abs().max().item() < 1e-12
+
+
+def test_grid_pyramid_and_schedule():
+    a = torch.rand(2, 1, 16, 16)
+    lv = O.grid_pyramid(a)
+    assert [t.shape[-1] for t in lv] == [1, 2, 4, 8, 16]
+    for t in lv:  # sum-pooling preserves mass
+        np.testing.assert_allclose(t.sum((1, 2, 3)).numpy(), a.sum((1, 2, 3)).numpy(), rtol=1e-5)
+    v = O.sinkhorn_images(a.double(), a.double().flip(-1), blur=1 / 16)
+    assert v.shape == (2,) and (v > 0).all()
+    assert torch.allclose(O.sinkhorn_images(a.double(), a.double()), torch.zeros(2, dtype=torch.float64), atol=1e-12)
