@@ -87,13 +87,13 @@ static int launch_rowsum(const ReducePlan& pl, cudaStream_t st, const float* x, 
   if (pl.small) {
     using C = RowSumCfg<MODE, D, kSmallR, kSmallNT, kSmallTJ, 3, 4>;
     return launch_reduce<C>(rowsum_partial_kernel<C>, pl, st, x, center, scale, clampq, cols,
-                            (const float*)nullptr, part, N, pl.ntiles, pl.tiles_per_split);
+                            (const float*)nullptr, part, N, pl.ntiles, pl.tiles_per_split, (const int*)nullptr, (const int*)nullptr);
   }
   // D >= 5: one row per thread (same 512 rows per CTA) keeps the 2 x (D+1) accumulator pairs in registers
   using C = std::conditional_t<(D <= 4), RowSumCfg<MODE, D, kBigR, kBigNT, kBigTJ, 3, 2>,
                                RowSumCfg<MODE, D, 1, kBigR * kBigNT, kBigTJ, 3, 1>>;
   return launch_reduce<C>(rowsum_partial_kernel<C>, pl, st, x, center, scale, clampq, cols, (const float*)nullptr,
-                          part, N, pl.ntiles, pl.tiles_per_split);
+                          part, N, pl.ntiles, pl.tiles_per_split, (const int*)nullptr, (const int*)nullptr);
 }
 
 template <int MODE>

@@ -79,7 +79,8 @@ template <class C>
 static int launch_partial(const float* x, const float* center, float scale, float clampq, const float* cols,
                           float* part, const ReducePlan& pl, int64_t N, cudaStream_t st) {
   return launch_reduce<C>(softmin_partial_kernel<C>, pl, st, x, center, scale, clampq, cols,
-                          reinterpret_cast<float2*>(part), N, pl.ntiles, pl.tiles_per_split);
+                          reinterpret_cast<float2*>(part), N, pl.ntiles, pl.tiles_per_split, (const int*)nullptr,
+                          (const int*)nullptr);
 }
 
 template <int D>
@@ -170,6 +171,50 @@ B200OT_API int b200ot_softmin_partial(const float* x, const float* center, const
   const ReducePlan pl = make_plan(N, M);
   if (n_split != pl.n_split) return B200OT_EINVAL;
   return softmin_partial_impl(x, center, cols, part, pl, N, D, p, eps, (cudaStream_t)stream);
+}
+
+B200OT_API void b200ot_sparse_tile_shape(int32_t* rows_per_tile, int32_t* cols_per_tile) {
+  if (rows_per_tile) *rows_per_tile = kBigNT * kBigR;
+  if (cols_per_tile) *cols_per_tile = kBigTJ;
+}
+
+B200OT_API int b200ot_softmin_partial_sparse(const float* x, const float* center, const float* cols,
+                                             const int32_t* tile_ptr, const int32_t* tile_list, float* part,
+                                             int64_t N, int64_t M, int32_t D, int32_t p, float eps, void* stream) {
+  if (!x || !cols || !tile_ptr || !tile_list || !part || N <= 0 || M <= 0 || !supported_simt_dim(D) ||
+      (p != 1 && p != 2) || !(eps > 0.f))
+    return B200OT_EINVAL;
+  if ((((uintptr_t)cols) & 15) || (((uintptr_t)part) & 7)) return B200OT_EALIGN;
+  ReducePlan pl;
+  pl.small = false;
+  pl.tj = kBigTJ;
+  pl.rows_cta = kBigNT * kBigR;
+  pl.ntiles = (int)(round_up64(M, kBigTJ) / kBigTJ);
+  pl.tiles_per_split = pl.ntiles;
+  pl.n_split = 1;
+  pl.row_tiles = ceil_div64(N, pl.rows_cta);
+  const float scale = softmin_coord_scale(p, eps);
+  const float clampq = scale * scale * 1e-8f;
+  cudaStream_t st = (cudaStream_t)stream;
+  auto go = [&](auto cfg) -> int {
+    using C = decltype(cfg);
+    return launch_reduce<C>(softmin_partial_kernel<C>, pl, st, x, center, scale, clampq, cols,
+                            reinterpret_cast<float2*>(part), N, pl.ntiles, pl.tiles_per_split,
+                            reinterpret_cast<const int*>(tile_ptr), reinterpret_cast<const int*>(tile_list));
+  };
+  if (D > 3) return B200OT_EINVAL;  // multiscale clustering is a low-dimensional device (reference: D <= 3)
+  if (p == 2) {
+    switch (D) {
+      case 1: return go(typename Variants<1, 2, false>::Big{});
+      case 2: return go(typename Variants<2, 2, false>::Big{});
+      default: return go(typename Variants<3, 2, false>::Big{});
+    }
+  }
+  switch (D) {
+    case 1: return go(typename Variants<1, 1, true>::Big{});
+    case 2: return go(typename Variants<2, 1, true>::Big{});
+    default: return go(typename Variants<3, 1, true>::Big{});
+  }
 }
 
 B200OT_API int b200ot_softmin_merge(const float* part, int32_t n_part, float* merged, int64_t N, void* stream) {

@@ -51,17 +51,18 @@ __global__ void rowsum_merge_kernel(const float* __restrict__ part, int n_part, 
 
 template <int MODE, int D>
 static int launch_rowsum(const ReducePlan& pl, cudaStream_t st, const float* x, const float* center, float scale,
-                         float clampq, const float* cols, const float* lse2, float* part, int64_t N) {
+                         float clampq, const float* cols, const float* lse2, float* part, int64_t N,
+                         const int* tile_ptr = nullptr, const int* tile_list = nullptr) {
   if (pl.small) {
     using C = RowSumCfg<MODE, D, kSmallR, kSmallNT, kSmallTJ, 3, 4>;
     return launch_reduce<C>(rowsum_partial_kernel<C>, pl, st, x, center, scale, clampq, cols, lse2, part, N,
-                            pl.ntiles, pl.tiles_per_split);
+                            pl.ntiles, pl.tiles_per_split, tile_ptr, tile_list);
   }
   // D >= 5: one row per thread (same 512 rows per CTA) keeps the 2 x (D+1) accumulator pairs in registers
   using C = std::conditional_t<(D <= 4), RowSumCfg<MODE, D, kBigR, kBigNT, kBigTJ, 3, 2>,
                                RowSumCfg<MODE, D, 1, kBigR * kBigNT, kBigTJ, 3, 1>>;
   return launch_reduce<C>(rowsum_partial_kernel<C>, pl, st, x, center, scale, clampq, cols, lse2, part, N, pl.ntiles,
-                          pl.tiles_per_split);
+                          pl.tiles_per_split, tile_ptr, tile_list);
 }
 
 template <int MODE>
@@ -111,6 +112,41 @@ B200OT_API int b200ot_softmin_bwd_partial(const float* x, const float* center, c
   cudaStream_t st = (cudaStream_t)stream;
   return (p == 2) ? launch_rowsum_d<kSoftminBwdP2>(D, pl, st, x, center, scale, clampq, cols, lse2, part, N)
                   : launch_rowsum_d<kSoftminBwdP1>(D, pl, st, x, center, scale, clampq, cols, lse2, part, N);
+}
+
+B200OT_API int b200ot_softmin_bwd_partial_sparse(const float* x, const float* center, const float* cols,
+                                                 const float* lse2, const int32_t* tile_ptr,
+                                                 const int32_t* tile_list, float* part, int64_t N, int64_t M,
+                                                 int32_t D, int32_t p, float eps, void* stream) {
+  if (!x || !cols || !lse2 || !tile_ptr || !tile_list || !part || N <= 0 || M <= 0 || D < 1 || D > 3 ||
+      (p != 1 && p != 2) || !(eps > 0.f))
+    return B200OT_EINVAL;
+  if (((uintptr_t)cols) & 15) return B200OT_EALIGN;
+  ReducePlan pl;
+  pl.small = false;
+  pl.tj = kBigTJ;
+  pl.rows_cta = kBigNT * kBigR;
+  pl.ntiles = (int)(round_up64(M, kBigTJ) / kBigTJ);
+  pl.tiles_per_split = pl.ntiles;
+  pl.n_split = 1;
+  pl.row_tiles = ceil_div64(N, pl.rows_cta);
+  const float scale = softmin_coord_scale(p, eps);
+  const float clampq = scale * scale * 1e-8f;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int* tp = reinterpret_cast<const int*>(tile_ptr);
+  const int* tl = reinterpret_cast<const int*>(tile_list);
+  if (p == 2) {
+    switch (D) {
+      case 1: return launch_rowsum<kSoftminBwdP2, 1>(pl, st, x, center, scale, clampq, cols, lse2, part, N, tp, tl);
+      case 2: return launch_rowsum<kSoftminBwdP2, 2>(pl, st, x, center, scale, clampq, cols, lse2, part, N, tp, tl);
+      default: return launch_rowsum<kSoftminBwdP2, 3>(pl, st, x, center, scale, clampq, cols, lse2, part, N, tp, tl);
+    }
+  }
+  switch (D) {
+    case 1: return launch_rowsum<kSoftminBwdP1, 1>(pl, st, x, center, scale, clampq, cols, lse2, part, N, tp, tl);
+    case 2: return launch_rowsum<kSoftminBwdP1, 2>(pl, st, x, center, scale, clampq, cols, lse2, part, N, tp, tl);
+    default: return launch_rowsum<kSoftminBwdP1, 3>(pl, st, x, center, scale, clampq, cols, lse2, part, N, tp, tl);
+  }
 }
 
 B200OT_API int b200ot_softmin_bwd_finalize(const float* part, int32_t n_part, const float* x, const float* center,

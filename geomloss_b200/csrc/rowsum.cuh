@@ -55,7 +55,8 @@ template <class C>
 __global__ void __launch_bounds__(C::NT + 32, C::MINB)
     rowsum_partial_kernel(const float* __restrict__ x, const float* __restrict__ center, float scale, float clampq,
                           const float* __restrict__ cols, const float* __restrict__ lse2, float* __restrict__ part,
-                          int64_t N, int ntiles, int tiles_per_split) {
+                          int64_t N, int ntiles, int tiles_per_split, const int* __restrict__ tile_ptr,
+                          const int* __restrict__ tile_list) {
   constexpr int D = C::D, R = C::R, NT = C::NT, NF2 = C::NF2, STAGES = C::STAGES, NACC = C::NACC, MODE = C::MODE;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* tiles = reinterpret_cast<float*>(smem_raw);
@@ -65,8 +66,9 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int split = blockIdx.y;
-  const int t0 = split * tiles_per_split;
-  const int t1 = min(ntiles, t0 + tiles_per_split);
+  const bool sparse = (tile_ptr != nullptr);  // block-sparse mode: see softmin.cuh
+  const int t0 = sparse ? tile_ptr[blockIdx.x] : split * tiles_per_split;
+  const int t1 = sparse ? tile_ptr[blockIdx.x + 1] : min(ntiles, t0 + tiles_per_split);
   const int nt = t1 - t0;
 
   if (threadIdx.x == 0) {
@@ -83,9 +85,9 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
       for (int k = 0; k < nt; ++k) {
         const int st = k % STAGES;
         if (k >= STAGES) mbar_wait(&empty[st], ((k / STAGES) + 1) & 1);
+        const int64_t t = sparse ? tile_list[t0 + k] : (t0 + k);
         mbar_arrive_expect_tx(&full[st], C::TILE_BYTES);
-        tma_load_1d(tiles + st * C::TILE_FLOATS, cols + (int64_t)(t0 + k) * C::TILE_FLOATS, C::TILE_BYTES,
-                    &full[st]);
+        tma_load_1d(tiles + st * C::TILE_FLOATS, cols + t * C::TILE_FLOATS, C::TILE_BYTES, &full[st]);
       }
     }
     return;

@@ -124,7 +124,8 @@ template <class C>
 __global__ void __launch_bounds__(C::NT + 32, C::MINB)
     softmin_partial_kernel(const float* __restrict__ x, const float* __restrict__ center, float scale,
                            float clampq, const float* __restrict__ cols, float2* __restrict__ part, int64_t N,
-                           int ntiles, int tiles_per_split) {
+                           int ntiles, int tiles_per_split, const int* __restrict__ tile_ptr,
+                           const int* __restrict__ tile_list) {
   constexpr int D = C::D, R = C::R, NT = C::NT, NF2 = C::NF2, CH = C::CH, STAGES = C::STAGES;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* tiles = reinterpret_cast<float*>(smem_raw);
@@ -134,8 +135,11 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int split = blockIdx.y;
-  const int t0 = split * tiles_per_split;
-  const int t1 = min(ntiles, t0 + tiles_per_split);
+  // dense mode: this CTA reduces the contiguous tile range of its split;
+  // block-sparse mode (tile_ptr != null; multiscale kernel truncation): the tiles listed for its row tile
+  const bool sparse = (tile_ptr != nullptr);
+  const int t0 = sparse ? tile_ptr[blockIdx.x] : split * tiles_per_split;
+  const int t1 = sparse ? tile_ptr[blockIdx.x + 1] : min(ntiles, t0 + tiles_per_split);
   const int nt = t1 - t0;
 
   if (threadIdx.x == 0) {
@@ -148,14 +152,14 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
   __syncthreads();
 
   if (warp == 0) {
-    // ===== producer: one elected lane streams the column tiles of this split =====
+    // ===== producer: one elected lane streams the column tiles of this CTA =====
     if (lane == 0) {
       for (int k = 0; k < nt; ++k) {
         const int st = k % STAGES;
         if (k >= STAGES) mbar_wait(&empty[st], ((k / STAGES) + 1) & 1);
+        const int64_t t = sparse ? tile_list[t0 + k] : (t0 + k);
         mbar_arrive_expect_tx(&full[st], C::TILE_BYTES);
-        tma_load_1d(tiles + st * C::TILE_FLOATS, cols + (int64_t)(t0 + k) * C::TILE_FLOATS, C::TILE_BYTES,
-                    &full[st]);
+        tma_load_1d(tiles + st * C::TILE_FLOATS, cols + t * C::TILE_FLOATS, C::TILE_BYTES, &full[st]);
       }
     }
     return;

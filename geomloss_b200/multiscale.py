@@ -1,0 +1,302 @@
+"""Two-scale (coarse clusters -> fine points) Sinkhorn with kernel truncation on point clouds.
+
+Host side of the reference's ``backend="multiscale"`` (src/geomloss/_legacy/sinkhorn_samples.py:453-681 and the
+jump branch of sinkhorn_loop, src/geomloss/_legacy/sinkhorn_divergence.py:519-606), restated in torch on the
+device; the pykeops cluster utilities it relies on (grid_cluster, cluster_ranges_centroids, from_matrix —
+SURVEY.md appendix B) are replaced by:
+
+  clusterize            voxel-grid labels -> compact sorted labels (torch.unique), weighted centroids
+                        (index_add), points sorted by label so that clusters are contiguous;
+  coarse phase          the ordinary dense softmin kernels on the ~2000 centroids per cloud;
+  kernel truncation     the coarse mask  f_i + g_j > C_ij - truncate*eps  (sinkhorn_samples.py:512-515) is
+                        turned into a per-row-tile LIST OF COLUMN TILES for the block-sparse mode of the
+                        softmin kernel (b200ot_softmin_partial_sparse): a (512-row, 1024-column) tile pair
+                        is kept as soon as it contains one kept cluster pair (2-D prefix sum over the mask),
+                        i.e. a SUPERSET of the reference's kept blocks — closer to the exact, dense result;
+  extrapolation         dense fine-rows x coarse-columns softmin (sinkhorn_samples.py:533-544);
+  fine phase            block-sparse softmins, fused prologue/epilogue as in the single-scale loop.
+
+``truncate=None`` keeps every tile and is exact (the reference's "exact mode", :504-505).
+NB the two-scale scheme is NOT the single-scale loop with fewer flops: its early iterations run on the
+centroids and the jump inserts a non-averaged update, so with the reference's fixed iteration counts its
+value differs from the dense backends by a few percent (6 % at configs[0]) — in the reference too.
+Parity: unpinned against the reference (pykeops is not installable here); tests compare with a dense CPU
+restatement of the same two-scale algorithm (oracle.sinkhorn_multiscale_dense).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .sinkhorn import damping, log_weights, scaling_parameters, sinkhorn_cost
+
+
+# ------------------------------------------------------------------------------------------------------
+# clustering                                                        sinkhorn_samples.py:453-490
+# ------------------------------------------------------------------------------------------------------
+def grid_labels(x, scale):
+    """Voxel-grid labels, compacted to 0..C-1 in sorted order (pykeops grid_cluster + relabelling)."""
+    ij = torch.floor((x - x.min(0).values) / scale).long()
+    key = ij[:, 0]
+    for k in range(1, x.shape[1]):
+        key = key * (int(ij[:, k].max().item()) + 1) + ij[:, k]
+    _, lab = torch.unique(key, sorted=True, return_inverse=True)
+    return lab
+
+
+def clusterize(a, x, scale=None, labels=None):
+    """Returns (a_c, x_c), (a_sorted, x_sorted), sorted labels, perm.  Clusters are contiguous after the sort."""
+    lab = grid_labels(x.detach(), scale) if labels is None else torch.unique(labels.view(-1), return_inverse=True)[1]
+    C = int(lab.max().item()) + 1
+    a_c = torch.zeros(C, dtype=a.dtype, device=a.device).index_add_(0, lab, a.detach())
+    x_c = torch.zeros(C, x.shape[1], dtype=x.dtype, device=x.device).index_add_(0, lab, a.detach()[:, None] * x.detach())
+    x_c = x_c / a_c[:, None]
+    lab_sorted, perm = torch.sort(lab, stable=True)
+    return (a_c, x_c), (a[perm], x[perm]), lab_sorted, perm
+
+
+# ------------------------------------------------------------------------------------------------------
+# block-sparse softmin (staged C-ABI calls)
+# ------------------------------------------------------------------------------------------------------
+def tile_shape():
+    r, c = ctypes.c_int32(0), ctypes.c_int32(0)
+    _lib.lib().b200ot_sparse_tile_shape(ctypes.byref(r), ctypes.byref(c))
+    return r.value, c.value
+
+
+def tiles_from_cluster_mask(keep, lab_rows, lab_cols):
+    """Cluster-level mask (Cr, Cc) + sorted labels of the fine rows / columns -> CSR list of column tiles per
+    row tile (int32 tile_ptr, tile_list) for b200ot_softmin_partial_sparse."""
+    tr, tc = tile_shape()
+    n, m = lab_rows.numel(), lab_cols.numel()
+    dev = lab_rows.device
+    r0 = lab_rows[torch.arange(0, n, tr, device=dev)]
+    r1 = lab_rows[torch.clamp(torch.arange(tr - 1, n + tr - 1, tr, device=dev), max=n - 1)]
+    c0 = lab_cols[torch.arange(0, m, tc, device=dev)]
+    c1 = lab_cols[torch.clamp(torch.arange(tc - 1, m + tc - 1, tc, device=dev), max=m - 1)]
+    if keep is None:
+        keep_t = torch.ones(r0.numel(), c0.numel(), dtype=torch.bool, device=dev)
+    else:
+        K = torch.zeros(keep.shape[0] + 1, keep.shape[1] + 1, dtype=torch.int32, device=dev)
+        K[1:, 1:] = keep.to(torch.int32).cumsum(0).cumsum(1)
+        box = (K[(r1 + 1)[:, None], (c1 + 1)[None, :]] - K[r0[:, None], (c1 + 1)[None, :]]
+               - K[(r1 + 1)[:, None], c0[None, :]] + K[r0[:, None], c0[None, :]])
+        keep_t = box > 0
+    nz = keep_t.nonzero()  # sorted by row tile, then column tile (one host sync, as in the reference)
+    counts = torch.bincount(nz[:, 0], minlength=keep_t.shape[0])
+    tile_ptr = torch.zeros(keep_t.shape[0] + 1, dtype=torch.int32, device=dev)
+    tile_ptr[1:] = counts.cumsum(0).to(torch.int32)
+    return tile_ptr.contiguous(), nz[:, 1].to(torch.int32).contiguous(), float(keep_t.float().mean().item())
+
+
+class SparseProblem:
+    """rows x, columns y (both sorted by cluster) + the tile lists of one of the four Sinkhorn problems."""
+
+    def __init__(self, tile_ptr, tile_list, density):
+        self.tile_ptr, self.tile_list, self.density = tile_ptr, tile_list, density
+
+
+def softmin_sparse_raw(eps, x, y, h_a, h_b, h_scale_b, prob, *, p=2, center=None, out_old=None, alpha_old=0.0,
+                       beta=1.0, want_lse2=False):
+    x, y, h_a, h_b = ops._f32c(x, "x"), ops._f32c(y, "y"), ops._f32c(h_a, "h_a"), ops._f32c(h_b, "h_b")
+    center, out_old = ops._f32c(center, "center"), ops._f32c(out_old, "out_old")
+    N, D = x.shape
+    M = y.shape[0]
+    dev = x.device
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        out = torch.empty(N, dtype=torch.float32, device=dev)
+        lse2 = torch.empty(N, dtype=torch.float32, device=dev) if want_lse2 else None
+        cols = ops._scratch(L.b200ot_packed_cols_floats(M, D, 1) * 4, dev, "sparse_cols")
+        part = ops._scratch(N * 8, dev, "sparse_part")
+        st = ops._stream(dev)
+        _lib.check(L.b200ot_softmin_pack(ops._ptr(y), ops._ptr(h_a), ops._ptr(h_b), float(h_scale_b), ops._ptr(center), M,
+                                         D, int(p), float(eps), ops._ptr(cols), st), "b200ot_softmin_pack")
+        _lib.check(L.b200ot_softmin_partial_sparse(ops._ptr(x), ops._ptr(center), ops._ptr(cols), ops._ptr(prob.tile_ptr),
+                                                   ops._ptr(prob.tile_list), ops._ptr(part), N, M, D, int(p), float(eps),
+                                                   st), "b200ot_softmin_partial_sparse")
+        _lib.check(L.b200ot_softmin_finalize(ops._ptr(part), 1, ops._ptr(out_old), float(alpha_old), float(beta),
+                                             ops._ptr(out), ops._ptr(lse2), N, float(eps), st), "b200ot_softmin_finalize")
+    ops.count_launches(3)
+    return out, lse2
+
+
+class _SparseSoftmin(torch.autograd.Function):
+    """Block-sparse softmin with the reference's autograd contract (gradient to the row cloud only)."""
+
+    @staticmethod
+    def forward(ctx, x, y, h_a, h_b, h_scale_b, eps, p, center, scale_out, prob):
+        need = ctx.needs_input_grad[0]
+        out, lse2 = softmin_sparse_raw(eps, x, y, h_a, h_b, h_scale_b, prob, p=p, center=center, beta=scale_out,
+                                       want_lse2=need)
+        if need:
+            ctx.save_for_backward(x, y, h_a, h_b, center, lse2)
+            ctx.meta = (float(h_scale_b), float(eps), int(p), float(scale_out), prob)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, y, h_a, h_b, center, lse2 = ctx.saved_tensors
+        h_scale_b, eps, p, scale_out, prob = ctx.meta
+        N, D = x.shape
+        M = y.shape[0]
+        dev = x.device
+        L = _lib.lib()
+        go = (grad_out * scale_out).contiguous()
+        with torch.cuda.device(dev):
+            gx = torch.empty_like(x)
+            cols = ops._scratch(L.b200ot_packed_cols_floats(M, D, 1) * 4, dev, "sparse_cols")
+            part = ops._scratch(N * 4 * (D + 1), dev, "sparse_part")
+            st = ops._stream(dev)
+            _lib.check(L.b200ot_softmin_pack(ops._ptr(y), ops._ptr(h_a), ops._ptr(h_b), h_scale_b, ops._ptr(center), M, D, p,
+                                             eps, ops._ptr(cols), st), "b200ot_softmin_pack")
+            _lib.check(L.b200ot_softmin_bwd_partial_sparse(ops._ptr(x), ops._ptr(center), ops._ptr(cols), ops._ptr(lse2),
+                                                           ops._ptr(prob.tile_ptr), ops._ptr(prob.tile_list),
+                                                           ops._ptr(part), N, M, D, p, eps, st),
+                       "b200ot_softmin_bwd_partial_sparse")
+            _lib.check(L.b200ot_softmin_bwd_finalize(ops._ptr(part), 1, ops._ptr(x), ops._ptr(center), ops._ptr(go),
+                                                     ops._ptr(gx), N, D, p, eps, st), "b200ot_softmin_bwd_finalize")
+        ops.count_launches(3)
+        return gx, None, None, None, None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------------
+# driver                                                            sinkhorn_samples.py:547-681
+# ------------------------------------------------------------------------------------------------------
+def sinkhorn_multiscale(a, x, b, y, p=2, blur=0.05, reach=None, diameter=None, scaling=0.5, truncate=5,
+                        cluster_scale=None, debias=True, potentials=False, labels_x=None, labels_y=None,
+                        verbose=False, **_ignored):
+    """Two-scale Sinkhorn divergence between a:(N,) x:(N,D) and b:(M,) y:(M,D), D <= 3."""
+    if p not in (1, 2):
+        raise KeyError(p)
+    N, D = x.shape
+    if D > 3:
+        raise NotImplementedError("the multiscale clustering is a D <= 3 device (reference: samples_loss.py:237-243)")
+    diameter, eps_final, eps_list, rho = scaling_parameters(x, y, p, blur, reach, diameter, scaling)
+    if cluster_scale is None:
+        cluster_scale = diameter / (np.sqrt(D) * 2000 ** (1 / D))
+    (a_c, x_c), (a_s, x_s), lab_x, perm_x = clusterize(a, x, scale=cluster_scale, labels=labels_x)
+    (b_c, y_c), (b_s, y_s), lab_y, perm_y = clusterize(b, y, scale=cluster_scale, labels=labels_y)
+
+    jump = len(eps_list) - 1
+    for i, eps in enumerate(eps_list[2:]):
+        if cluster_scale**p > eps:
+            jump = i + 1
+            break
+    if verbose:
+        print("{}x{} clusters, computed at scale = {:2.3f}".format(len(x_c), len(y_c), cluster_scale))
+        print("Successive scales : ", ", ".join(["{:.3f}".format(e ** (1 / p)) for e in eps_list]))
+        if jump >= len(eps_list) - 1:
+            print("Extrapolate from coarse to fine after the last iteration.")
+        else:
+            print("Jump from coarse to fine between indices {} (σ={:2.3f}) and {} (σ={:2.3f}).".format(
+                jump, eps_list[jump] ** (1 / p), jump + 1, eps_list[jump + 1] ** (1 / p)))
+
+    center = ops.default_center(x.detach(), y.detach())
+    sm = ops.softmin_raw
+    ac_log, bc_log = log_weights(a_c), log_weights(b_c)
+    a_log, b_log = log_weights(a_s.detach()), log_weights(b_s.detach())
+    xs_d, ys_d = x_s.detach(), y_s.detach()
+    kw = dict(p=p, center=center)
+
+    with torch.no_grad():
+        # ---- coarse phase on the centroids ----
+        eps = eps_list[0]
+        lam = damping(eps, rho)
+        g_ab = sm(eps, y_c, x_c, ac_log, beta=lam, **kw)[0]
+        f_ba = sm(eps, x_c, y_c, bc_log, beta=lam, **kw)[0]
+        if debias:
+            f_aa = sm(eps, x_c, x_c, ac_log, beta=lam, **kw)[0]
+            g_bb = sm(eps, y_c, y_c, bc_log, beta=lam, **kw)[0]
+        for i in range(jump + 1):
+            eps = eps_list[i]
+            lam = damping(eps, rho)
+            inv = 1.0 / eps
+            ft_ba = sm(eps, x_c, y_c, bc_log, g_ab, inv, out_old=f_ba, alpha_old=0.5, beta=0.5 * lam, **kw)[0]
+            gt_ab = sm(eps, y_c, x_c, ac_log, f_ba, inv, out_old=g_ab, alpha_old=0.5, beta=0.5 * lam, **kw)[0]
+            if debias:
+                ft_aa = sm(eps, x_c, x_c, ac_log, f_aa, inv, out_old=f_aa, alpha_old=0.5, beta=0.5 * lam, **kw)[0]
+                gt_bb = sm(eps, y_c, y_c, bc_log, g_bb, inv, out_old=g_bb, alpha_old=0.5, beta=0.5 * lam, **kw)[0]
+                f_aa, g_bb = ft_aa, gt_bb
+            f_ba, g_ab = ft_ba, gt_ab
+
+    # ---- jump: extrapolate the coarse potentials to the fine points (dense fine-rows x coarse-columns) ----
+    last_is_jump = jump >= len(eps_list) - 1
+    inv = 1.0 / eps
+    if last_is_jump:
+        # the extrapolation is the last, gradient-carrying step (sinkhorn_divergence.py:520-526, appendix A-21)
+        smg = ops.softmin
+        f_ba_f = smg(eps, x_s, y_c, bc_log, g_ab, inv, scale_out=lam, **kw)
+        g_ab_f = smg(eps, y_s, x_c, ac_log, f_ba, inv, scale_out=lam, **kw)
+        f_aa_f = smg(eps, x_s, x_c, ac_log, f_aa, inv, scale_out=lam, **kw) if debias else None
+        g_bb_f = smg(eps, y_s, y_c, bc_log, g_bb, inv, scale_out=lam, **kw) if debias else None
+    else:
+        with torch.no_grad():
+            # kernel truncation on the coarse potentials (sinkhorn_samples.py:493-530)
+            def coarse_cost(u, v):
+                d2 = ((u[:, None, :] - v[None, :, :]) ** 2).sum(-1)
+                return d2 / 2 if p == 2 else d2.clamp_min(1e-8).sqrt()
+
+            def mask(fu, gv, u, v):
+                if truncate is None:
+                    return None
+                return fu[:, None] + gv[None, :] > coarse_cost(u, v) - truncate * eps
+
+            k_xy = mask(f_ba, g_ab, x_c, y_c)
+            probs = {
+                "xy": SparseProblem(*tiles_from_cluster_mask(k_xy, lab_x, lab_y)),
+                "yx": SparseProblem(*tiles_from_cluster_mask(None if k_xy is None else k_xy.t(), lab_y, lab_x)),
+            }
+            if debias:
+                probs["xx"] = SparseProblem(*tiles_from_cluster_mask(mask(f_aa, f_aa, x_c, x_c), lab_x, lab_x))
+                probs["yy"] = SparseProblem(*tiles_from_cluster_mask(mask(g_bb, g_bb, y_c, y_c), lab_y, lab_y))
+            if verbose:
+                for name, pr in probs.items():
+                    print("Keep {:2.1f}% of the {} tile pairs.".format(100 * pr.density, name))
+
+            f_ba_f = sm(eps, xs_d, y_c, bc_log, g_ab, inv, beta=lam, **kw)[0]
+            g_ab_f = sm(eps, ys_d, x_c, ac_log, f_ba, inv, beta=lam, **kw)[0]
+            f_aa_f = g_bb_f = None
+            if debias:
+                f_aa_f = sm(eps, xs_d, x_c, ac_log, f_aa, inv, beta=lam, **kw)[0]
+                g_bb_f = sm(eps, ys_d, y_c, bc_log, g_bb, inv, beta=lam, **kw)[0]
+
+            # ---- fine phase: block-sparse softmins ----
+            sp = softmin_sparse_raw
+            for i in range(jump + 1, len(eps_list)):
+                eps = eps_list[i]
+                lam = damping(eps, rho)
+                inv = 1.0 / eps
+                ft_ba = sp(eps, xs_d, ys_d, b_log, g_ab_f, inv, probs["xy"], out_old=f_ba_f, alpha_old=0.5,
+                           beta=0.5 * lam, **kw)[0]
+                gt_ab = sp(eps, ys_d, xs_d, a_log, f_ba_f, inv, probs["yx"], out_old=g_ab_f, alpha_old=0.5,
+                           beta=0.5 * lam, **kw)[0]
+                if debias:
+                    ft_aa = sp(eps, xs_d, xs_d, a_log, f_aa_f, inv, probs["xx"], out_old=f_aa_f, alpha_old=0.5,
+                               beta=0.5 * lam, **kw)[0]
+                    gt_bb = sp(eps, ys_d, ys_d, b_log, g_bb_f, inv, probs["yy"], out_old=g_bb_f, alpha_old=0.5,
+                               beta=0.5 * lam, **kw)[0]
+                    f_aa_f, g_bb_f = ft_aa, gt_bb
+                f_ba_f, g_ab_f = ft_ba, gt_ab
+        # final, non-averaged, gradient-carrying step on the fine clouds (sinkhorn_divergence.py:612-623)
+        inv = 1.0 / eps
+        spg = _SparseSoftmin.apply
+        new_f_ba = spg(x_s, ys_d, b_log, g_ab_f, inv, eps, p, center, lam, probs["xy"])
+        new_g_ab = spg(y_s, xs_d, a_log, f_ba_f, inv, eps, p, center, lam, probs["yx"])
+        if debias:
+            f_aa_f = spg(x_s, xs_d, a_log, f_aa_f, inv, eps, p, center, lam, probs["xx"])
+            g_bb_f = spg(y_s, ys_d, b_log, g_bb_f, inv, eps, p, center, lam, probs["yy"])
+        f_ba_f, g_ab_f = new_f_ba, new_g_ab
+    if not debias:
+        f_aa_f = g_bb_f = None
+
+    out = sinkhorn_cost(eps_final, rho, a_s, b_s, f_aa_f, g_bb_f, g_ab_f, f_ba_f, debias=debias, potentials=potentials)
+    if potentials:  # undo the cluster sort (sinkhorn_samples.py:675-679)
+        F, G = out
+        f_x, g_y = torch.empty_like(F), torch.empty_like(G)
+        f_x[perm_x], g_y[perm_y] = F, G
+        return f_x, g_y
+    return out

@@ -8,19 +8,22 @@ its quirks that user code may rely on:
     time, exactly like the reference at this commit (SURVEY.md A-13);
   * unknown ``p`` raises ``KeyError`` (the reference's cost table only has p = 1, 2).
 
-What differs by design: there is ONE engine.  ``backend`` is still validated and still drives the
-reference's routing rules (labels need "auto"/"multiscale", batches are looped over), but
-"tensorized", "online", "multiscale" and "auto" all run the same never-materialised sm_100a kernels,
-evaluated exactly (the multiscale truncation of the reference is an approximation of this exact
-computation; ``truncate`` / ``cluster_scale`` / labels are accepted and currently unused).
-Inputs must be float32 CUDA tensors: there is no CPU path.
+What differs by design: ``backend`` keeps the reference's routing rules (samples_loss.py:220-257: labels need
+"auto"/"multiscale"; "auto" picks "multiscale" for Sinkhorn, p = 2, D <= 3 above 1e8 pairs; a batched
+multiscale call warns and falls back to the dense path), but "tensorized" and "online" are ONE engine: the
+never-materialised sm_100a reductions, evaluated exactly.  "multiscale" is the two-scale scheme with kernel
+truncation on the block-sparse mode of the same kernels (multiscale.py) for ``loss="sinkhorn"``; the kernel
+MMDs are always evaluated exactly.  Inputs must be float32 CUDA tensors: there is no CPU path.
 """
 from __future__ import annotations
 
 import torch
 from torch.nn import Module
 
+import warnings
+
 from .kernel_loss import kernel_points
+from .multiscale import sinkhorn_multiscale
 from .sinkhorn import sinkhorn_points
 
 _LOSSES = ("sinkhorn", "hausdorff", "energy", "gaussian", "laplacian")
@@ -78,6 +81,18 @@ class SamplesLoss(Module):
             if backend not in ("auto", "multiscale"):
                 raise ValueError(
                     'Explicit cluster labels are only supported with the "auto" and "multiscale" backends.')
+            backend = "multiscale"
+        elif backend == "auto":
+            if M * N <= 5000**2:
+                backend = "tensorized"
+            elif D <= 3 and self.loss == "sinkhorn" and M * N > 10000**2 and self.p == 2:
+                backend = "multiscale"
+            else:
+                backend = "online"
+        if backend == "multiscale" and B > 1:
+            warnings.warn("The 'multiscale' backend do not support batchsize > 1. Using 'tensorized' instead: "
+                          "beware of memory overflows!")
+            backend = "tensorized"
         if self.cost is not None:
             raise NotImplementedError(
                 "custom cost functions need a dense (B,N,M) cost matrix or a KeOps formula; the CUDA engine "
@@ -85,6 +100,18 @@ class SamplesLoss(Module):
         routine = _route(self.loss)
         kw = dict(p=self.p, blur=self.blur, reach=self.reach, diameter=self.diameter, scaling=self.scaling,
                   debias=self.debias, potentials=self.potentials, kernel=self.kernel, **self._engine)
+        if backend == "multiscale" and self.loss == "sinkhorn" and not self._engine and D <= 3:
+            # single problem (B == 0, or B == 1 squeezed like the reference does, samples_loss.py:249-251)
+            sq = (lambda t: t[0]) if B == 1 else (lambda t: t)
+            values = sinkhorn_multiscale(sq(a), sq(x), sq(b), sq(y), p=self.p, blur=self.blur, reach=self.reach,
+                                         diameter=self.diameter, scaling=self.scaling, truncate=self.truncate,
+                                         cluster_scale=self.cluster_scale, debias=self.debias,
+                                         potentials=self.potentials, labels_x=l_x, labels_y=l_y,
+                                         verbose=self.verbose)
+            if self.potentials:
+                F, G = values
+                return F.view_as(a), G.view_as(b)
+            return values if B == 0 else values.view(-1)
 
         if B == 0:
             values = routine(a, x, b, y, **kw)

@@ -108,6 +108,15 @@ B200OT_API int32_t b200ot_softmin_num_splits(int64_t N, int64_t M, int32_t D);
 B200OT_API int b200ot_softmin_partial(const float* x, const float* center, const float* cols, float* part, int32_t n_split,
                            int64_t N, int64_t M, int32_t D, int32_t p, float eps, void* stream);
 
+/* Block-sparse partial reduction (the reference's softmin_multiscale with `ranges`, sinkhorn_samples.py:445-450,
+ * built by kernel_truncation :493-530): row tile r (b200ot_sparse_tile_shape rows of x, in order) reduces only over
+ * the packed column tiles tile_list[tile_ptr[r] .. tile_ptr[r+1]) (each b200ot_sparse_tile_shape columns).
+ * part: (N, 2) pairs (one split).  D <= 3. */
+B200OT_API void b200ot_sparse_tile_shape(int32_t* rows_per_tile, int32_t* cols_per_tile);
+B200OT_API int b200ot_softmin_partial_sparse(const float* x, const float* center, const float* cols,
+                                             const int32_t* tile_ptr, const int32_t* tile_list, float* part,
+                                             int64_t N, int64_t M, int32_t D, int32_t p, float eps, void* stream);
+
 /* Collapse n_part partial (m, s) sets into one per row: merged[i*2 + {0,1}].  A rank calls this on its own
  * splits before exchanging partials with the other column shards (N*8 bytes per rank). */
 B200OT_API int b200ot_softmin_merge(const float* part, int32_t n_part, float* merged, int64_t N, void* stream);
@@ -123,6 +132,11 @@ B200OT_API int b200ot_softmin_finalize(const float* part, int32_t n_part, const 
 B200OT_API int b200ot_softmin_bwd_partial(const float* x, const float* center, const float* cols, const float* lse2,
                                           float* part, int32_t n_split, int64_t N, int64_t M, int32_t D, int32_t p,
                                           float eps, void* stream);
+/* block-sparse variant (see b200ot_softmin_partial_sparse): part is (N, D+1), one split */
+B200OT_API int b200ot_softmin_bwd_partial_sparse(const float* x, const float* center, const float* cols,
+                                                 const float* lse2, const int32_t* tile_ptr,
+                                                 const int32_t* tile_list, float* part, int64_t N, int64_t M,
+                                                 int32_t D, int32_t p, float eps, void* stream);
 /* merged[i*width + a] = sum_s part[(s*N + i)*width + a] */
 B200OT_API int b200ot_rowsum_merge(const float* part, int32_t n_part, int32_t width, float* merged, int64_t N,
                                    void* stream);

@@ -401,3 +401,93 @@ def sinkhorn_images(a, b, p=2, blur=None, reach=None, scaling=0.5, debias=True, 
             f_aa = lam * sm(eps, p, a_log + f_aa / eps)
             g_bb = lam * sm(eps, p, b_log + g_bb / eps)
     return sinkhorn_value(eps_final, rho, a, b, f_aa, g_bb, g_ab, f_ba, debias=debias, potentials=potentials)
+
+
+# ------------------------------------------------------------------------------------------------
+# multiscale (two-scale Sinkhorn with kernel truncation)     sinkhorn_samples.py:453-681,
+#                                                            sinkhorn_divergence.py:519-606
+# PARITY UNPINNED (pykeops: grid_cluster, cluster_ranges_centroids, from_matrix are not installable here;
+# their semantics are restated from SURVEY.md appendix B).  Dense torch: the block-sparse reduction of the
+# reference is emulated with a point-level -inf mask built from the cluster-level `keep` matrix.
+# ------------------------------------------------------------------------------------------------
+
+
+def ms_grid_labels(x, scale):
+    ij = torch.floor((x - x.min(0).values) / scale).long()
+    key = ij[:, 0]
+    for k in range(1, x.shape[1]):
+        key = key * (int(ij[:, k].max()) + 1) + ij[:, k]
+    return torch.unique(key, sorted=True, return_inverse=True)[1]
+
+
+def ms_clusterize(a, x, scale):
+    lab = ms_grid_labels(x, scale)
+    C = int(lab.max()) + 1
+    a_c = torch.zeros(C, dtype=a.dtype).index_add_(0, lab, a)
+    x_c = torch.zeros(C, x.shape[1], dtype=x.dtype).index_add_(0, lab, a[:, None] * x) / a_c[:, None]
+    return a_c, x_c, lab
+
+
+def sinkhorn_multiscale_dense(a, x, b, y, p=2, blur=0.05, reach=None, diameter=None, scaling=0.5, truncate=5,
+                              cluster_scale=None, debias=True, potentials=False):
+    """The reference's two-scale scheme on unbatched clouds, evaluated densely (no sort needed: the sort of
+    the reference only makes clusters contiguous for KeOps)."""
+    diameter, eps_final, eps_list, rho = scaling_parameters(x, y, p, blur, reach, diameter, scaling)
+    D = x.shape[1]
+    if cluster_scale is None:
+        cluster_scale = diameter / (np.sqrt(D) * 2000 ** (1 / D))
+    a_c, x_c, lab_x = ms_clusterize(a, x, cluster_scale)
+    b_c, y_c, lab_y = ms_clusterize(b, y, cluster_scale)
+    jump = len(eps_list) - 1
+    for i, eps in enumerate(eps_list[2:]):
+        if cluster_scale**p > eps:
+            jump = i + 1
+            break
+
+    def sm(eps, u, v, h, mask=None):
+        t = h[None, :] - cost_matrix(u, v, p) / eps
+        if mask is not None:
+            t = t.masked_fill(~mask, -float("inf"))
+        return -eps * torch.logsumexp(t, dim=1)
+
+    ac_log, bc_log, a_log, b_log = log_weights(a_c), log_weights(b_c), log_weights(a), log_weights(b)
+    eps = eps_list[0]
+    lam = damping(eps, rho)
+    g_ab, f_ba = lam * sm(eps, y_c, x_c, ac_log), lam * sm(eps, x_c, y_c, bc_log)
+    f_aa, g_bb = lam * sm(eps, x_c, x_c, ac_log), lam * sm(eps, y_c, y_c, bc_log)
+    for i in range(jump + 1):
+        eps = eps_list[i]
+        lam = damping(eps, rho)
+        ft_ba = lam * sm(eps, x_c, y_c, bc_log + g_ab / eps)
+        gt_ab = lam * sm(eps, y_c, x_c, ac_log + f_ba / eps)
+        ft_aa = lam * sm(eps, x_c, x_c, ac_log + f_aa / eps)
+        gt_bb = lam * sm(eps, y_c, y_c, bc_log + g_bb / eps)
+        f_ba, g_ab = 0.5 * (f_ba + ft_ba), 0.5 * (g_ab + gt_ab)
+        f_aa, g_bb = 0.5 * (f_aa + ft_aa), 0.5 * (g_bb + gt_bb)
+    masks = {}
+    if jump < len(eps_list) - 1 and truncate is not None:
+        k_xy = f_ba[:, None] + g_ab[None, :] > cost_matrix(x_c, y_c, p) - truncate * eps
+        k_xx = f_aa[:, None] + f_aa[None, :] > cost_matrix(x_c, x_c, p) - truncate * eps
+        k_yy = g_bb[:, None] + g_bb[None, :] > cost_matrix(y_c, y_c, p) - truncate * eps
+        masks = {"xy": k_xy[lab_x][:, lab_y], "yx": k_xy.t()[lab_y][:, lab_x], "xx": k_xx[lab_x][:, lab_x],
+                 "yy": k_yy[lab_y][:, lab_y]}
+    # extrapolation: fine rows x coarse columns, all four from the OLD coarse potentials
+    f_ba, g_ab, f_aa, g_bb = (lam * sm(eps, x, y_c, bc_log + g_ab / eps), lam * sm(eps, y, x_c, ac_log + f_ba / eps),
+                              lam * sm(eps, x, x_c, ac_log + f_aa / eps), lam * sm(eps, y, y_c, bc_log + g_bb / eps))
+    if jump < len(eps_list) - 1:
+        for i in range(jump + 1, len(eps_list)):
+            eps = eps_list[i]
+            lam = damping(eps, rho)
+            ft_ba = lam * sm(eps, x, y, b_log + g_ab / eps, masks.get("xy"))
+            gt_ab = lam * sm(eps, y, x, a_log + f_ba / eps, masks.get("yx"))
+            ft_aa = lam * sm(eps, x, x, a_log + f_aa / eps, masks.get("xx"))
+            gt_bb = lam * sm(eps, y, y, b_log + g_bb / eps, masks.get("yy"))
+            f_ba, g_ab = 0.5 * (f_ba + ft_ba), 0.5 * (g_ab + gt_ab)
+            f_aa, g_bb = 0.5 * (f_aa + ft_aa), 0.5 * (g_bb + gt_bb)
+        f_ba, g_ab = (lam * sm(eps, x, y, b_log + g_ab / eps, masks.get("xy")),
+                      lam * sm(eps, y, x, a_log + f_ba / eps, masks.get("yx")))
+        f_aa = lam * sm(eps, x, x, a_log + f_aa / eps, masks.get("xx"))
+        g_bb = lam * sm(eps, y, y, b_log + g_bb / eps, masks.get("yy"))
+    out = sinkhorn_value(eps_final, rho, a[None], b[None], f_aa[None], g_bb[None], g_ab[None], f_ba[None],
+                         debias=debias, potentials=potentials)
+    return (out[0][0], out[1][0]) if potentials else out[0]

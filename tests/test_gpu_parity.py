@@ -246,10 +246,13 @@ def test_cfg1_sinkhorn_n1000():
     assert F.shape == (1, 1000) and G.shape == (1, 1000)
     np.testing.assert_allclose(F.cpu().numpy(), g["pot_f_f64"], atol=1e-6)  # bar: 1e-5
     np.testing.assert_allclose(G.cpu().numpy(), g["pot_g_f64"], atol=1e-6)
-    # 2-argument form = uniform weights; every backend string runs the same engine
-    for backend in ("auto", "tensorized", "online", "multiscale"):
+    # 2-argument form = uniform weights; "auto" / "tensorized" / "online" are one exact engine
+    for backend in ("auto", "tensorized", "online"):
         v2 = SamplesLoss("sinkhorn", p=2, blur=0.05, backend=backend)(x, y)
         assert abs(v2.item() - ref64) <= 5e-6 * abs(ref64)
+    # "multiscale" is a different (two-scale) iteration scheme: same ballpark, not the same number
+    v3 = SamplesLoss("sinkhorn", p=2, blur=0.05, backend="multiscale")(x, y)
+    assert abs(v3.item() - ref64) <= 0.15 * abs(ref64)
 
 
 @pytest.mark.parametrize("name", golden_names("sinkhorn_case"))
@@ -415,6 +418,61 @@ def test_full_size_sinkhorn_iteration_identities(million):
 
 
 # ------------------------------------------------------------------------------------------------
+# multiscale (two-scale, block-sparse) vs the dense engine
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kw", [dict(p=2, blur=0.02), dict(p=2, blur=0.03, reach=0.4, debias=False), dict(p=1, blur=0.02),
+                                dict(p=2, blur=0.4)])
+def test_multiscale_vs_two_scale_oracle(kw):
+    """The two-scale scheme (coarse centroids -> jump with kernel truncation -> block-sparse fine phase) against a
+    dense CPU restatement of the same algorithm.  NB it is not comparable to the single-scale backends at
+    tight tolerance: its iterates differ by design (see multiscale.py).  blur=.4 exercises the 'jump on the last
+    iteration' branch.  Our tile-level mask keeps a superset of the reference's cluster-level blocks, so the
+    truncated results agree to the (tiny) weight of the pruned terms."""
+    from geomloss_b200 import SamplesLoss
+    from oracle import geomloss_oracle as O
+
+    g = torch.Generator().manual_seed(31)
+    n, m = 5200, 4700
+    x = torch.rand(n, 3, generator=g)
+    y = torch.rand(m, 3, generator=g) * 0.8 + 0.15
+    a = torch.rand(n, generator=g) + 0.5
+    b = torch.rand(m, generator=g) + 0.5
+    a, b = a / a.sum(), b / b.sum()
+    cs = 0.12  # ~600 clusters per cloud: several clusters per 512 x 1024 tile, real sparsity at blur = .02
+    xd, yd, ad, bd = x.to(DEV), y.to(DEV), a.to(DEV), b.to(DEV)
+    for truncate in (None, 5):
+        ref = O.sinkhorn_multiscale_dense(a.double(), x.double(), b.double(), y.double(), truncate=truncate,
+                                          cluster_scale=cs, **kw).item()
+        L = SamplesLoss("sinkhorn", backend="multiscale", truncate=truncate, cluster_scale=cs, **kw)
+        val = L(ad, xd, bd, yd).item()
+        assert abs(val - ref) <= 5e-5 * abs(ref), (truncate, val, ref)
+    Fr, Gr = O.sinkhorn_multiscale_dense(a.double(), x.double(), b.double(), y.double(), truncate=None, cluster_scale=cs,
+                                         potentials=True, **kw)
+    F, G = SamplesLoss("sinkhorn", backend="multiscale", truncate=None, cluster_scale=cs, potentials=True, **kw)(ad, xd,
+                                                                                                              bd, yd)
+    assert F.shape == (n,) and G.shape == (m,)  # multiscale returns un-batched potentials (SURVEY A-12), de-permuted
+    assert (F.cpu().double() - Fr).abs().max().item() < 2e-5 and (G.cpu().double() - Gr).abs().max().item() < 2e-5
+    # autograd contract: d/da = potential (balanced, debiased); d/dx close to the dense engine's gradient
+    if kw.get("reach") is None:
+        ag, xg = ad.clone().requires_grad_(True), xd.clone().requires_grad_(True)
+        val = SamplesLoss("sinkhorn", backend="multiscale", truncate=None, cluster_scale=cs, **kw)(ag, xg, bd, yd)
+        ga, gx = torch.autograd.grad(val, [ag, xg])
+        assert (ga - F).abs().max().item() < 1e-6
+        xg2 = xd.clone().requires_grad_(True)
+        (gd,) = torch.autograd.grad(SamplesLoss("sinkhorn", backend="online", **kw)(ad, xg2, bd, yd), xg2)
+        cos = torch.nn.functional.cosine_similarity(gx.flatten(), gd.flatten(), dim=0).item()
+        assert cos > 0.98, cos
+    # user-supplied cluster labels (6-argument form) route to the multiscale backend
+    from geomloss_b200.multiscale import grid_labels
+
+    lab = SamplesLoss("sinkhorn", truncate=None, cluster_scale=cs, **kw)(grid_labels(xd, cs), ad, xd, grid_labels(yd, cs),
+                                                                            bd, yd)
+    plain = SamplesLoss("sinkhorn", backend="multiscale", truncate=None, cluster_scale=cs, **kw)(ad, xd, bd, yd)
+    # (centroids are accumulated with float atomics: run-to-run differences of a few ulps are expected)
+    assert abs(lab.item() - plain.item()) <= 2e-5 * abs(plain.item())
+
+
+# ------------------------------------------------------------------------------------------------
 # grids (images / volumes): parity against the (unpinned, cross-checked) dense grid oracle
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape", [(2, 1, 8, 8), (1, 2, 32, 32), (1, 1, 64, 64), (1, 1, 16, 16, 16), (2, 1, 32, 32, 32)])
@@ -448,7 +506,9 @@ def test_image_sinkhorn_vs_oracle(shape):
     b = torch.rand(*shape, generator=g) ** 3
     a[..., :3] = 0.0  # empty pixels
     a, b = a / a.sum(), b / b.sum() * 1.0
-    for kw in (dict(p=2), dict(p=2, reach=0.3, scaling=0.7), dict(p=1, blur=2.0 / shape[-1])):
+    # (blur must resolve the finest pixels, else the reference's own "bug in the multiscale pre-processing"
+    #  assertion fires — kept verbatim in both restatements)
+    for kw in (dict(p=2), dict(p=2, reach=0.3, scaling=0.7), dict(p=1)):
         ref = O.sinkhorn_images(a.double(), b.double(), **kw)
         ag = a.to(DEV).requires_grad_(True)
         val = sinkhorn_divergence(ag, b.to(DEV), **kw)
@@ -475,7 +535,9 @@ def test_errors_on_gpu():
     with pytest.raises(TypeError):
         SamplesLoss("sinkhorn")(x.double(), y.double())
     with pytest.raises(NotImplementedError):
-        ops.softmin_raw(0.1, torch.rand(4, 40, device=DEV), torch.rand(5, 40, device=DEV), torch.zeros(5, device=DEV))
+        ops.softmin_raw(0.1, torch.rand(4, 100, device=DEV), torch.rand(5, 100, device=DEV), torch.zeros(5, device=DEV))
+    with pytest.raises(NotImplementedError):  # p = 1 has no tensor-core path
+        ops.softmin_raw(0.1, torch.rand(4, 40, device=DEV), torch.rand(5, 40, device=DEV), torch.zeros(5, device=DEV), p=1)
     with pytest.raises(ValueError):
         ops.softmin_raw(0.1, x, y, torch.zeros(11, device=DEV))
     with pytest.raises(_lib.B200OTError):

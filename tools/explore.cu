@@ -246,7 +246,7 @@ static void run_variant(const char* name, Problem& P, int reps) {
   dim3 grid((unsigned)row_tiles, (unsigned)nsplit);
   auto launch = [&]() {
     kern<<<grid, C::NT + 32, C::SMEM_BYTES>>>(P.x, P.center, scale, clampq, P.cols, (float2*)P.part, P.N, ntiles,
-                                              tps);
+                                              tps, (const int*)nullptr, (const int*)nullptr);
   };
   const double ms = time_kernel(launch, reps);
   CK(b200ot_softmin_finalize(P.part, nsplit, nullptr, 0.f, 1.f, P.out, P.lse2, P.N, P.eps, nullptr) == 0
