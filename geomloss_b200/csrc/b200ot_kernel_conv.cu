@@ -138,13 +138,13 @@ struct TcPlan {
 
 bool tc_supported_dim(int D) { return D > B200OT_MAX_D && D <= 64; }
 
-static TcPlan make_tc_plan(int64_t N, int64_t M, int D) {
+static TcPlan make_tc_plan(int64_t N, int64_t M, int D, bool bwd = false) {
   TcPlan p;
   p.kp = tc_kp(D);
   p.a_tiles = ceil_div64(N, kTcM);
   p.b_tiles = ceil_div64(M, kTcBN);
   p.a_bytes = tc_a_img_bytes(p.kp);
-  p.b_bytes = tc_b_img_bytes(p.kp, kTcBN);
+  p.b_bytes = tc_b_img_bytes(p.kp, kTcBN, bwd ? tc_dk(D) : 0);
   const int64_t bar_bytes = 8 * (1 + 2 * kTcMaxStage + 2 * 2) + 16;
   const int64_t avail = 227 * 1024 - bar_bytes - 1024;  // the row operand lives in TMEM, not in shared memory
   int64_t ns = avail / p.b_bytes;
@@ -158,11 +158,48 @@ static TcPlan make_tc_plan(int64_t N, int64_t M, int D) {
   p.n_split = (int)ceil_div64(p.b_tiles, p.tiles_per_split);
   p.off_b = round_up64(p.a_tiles * p.a_bytes, 256);
   p.off_part = p.off_b + round_up64(p.b_tiles * p.b_bytes, 256);
-  p.total = p.off_part + round_up64((int64_t)p.n_split * (kTcEpi / 4) * N * 8, 256);  // (m, s) pairs at most
+  // partials: (m, s) pairs forward, D+1 sums per row backward
+  p.total = p.off_part + round_up64((int64_t)p.n_split * (kTcEpi / 4) * N * 4 * (bwd ? D + 1 : 2), 256);
   return p;
 }
 
-int64_t tc_scratch_bytes(int64_t N, int64_t M, int D) { return make_tc_plan(N, M, D).total; }
+int64_t tc_scratch_bytes(int64_t N, int64_t M, int D) { return make_tc_plan(N, M, D, true).total; }
+
+// Row gradients on the tensor-core path (gaussian conv: kind 0 / softmin p=2: kind 1).  Leaves n_part sets of
+// (N, D+1) partial sums in *part_out.
+int bwd_partial_tc(int kind, const float* x, const float* y, const float* w, const float* h_a, const float* h_b,
+                   float h_scale_b, const float* lse2, const float* center, float scale, int64_t N, int64_t M, int D,
+                   void* scratch, float** part_out, int* n_part_out, cudaStream_t st) {
+  const TcPlan p = make_tc_plan(N, M, D, true);
+  if (p.nstage < 1) return B200OT_EINVAL;
+  unsigned char* base = reinterpret_cast<unsigned char*>(scratch);
+  unsigned char* a_imgs = base;
+  unsigned char* b_imgs = base + p.off_b;
+  float* part = reinterpret_cast<float*>(base + p.off_part);
+  const int threads = 128;
+  tc_pack_kernel<<<(unsigned)ceil_div64(p.a_tiles * kTcM, threads), threads, 0, st>>>(
+      x, nullptr, nullptr, nullptr, 0.f, 0.f, center, scale, N, D, p.kp, kTcM, 0, a_imgs, 0, lse2);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  tc_pack_kernel<<<(unsigned)ceil_div64(p.b_tiles * kTcBN, threads), threads, 0, st>>>(
+      y, w, h_a, h_b, h_scale_b, kLog2e, center, scale, M, D, p.kp, kTcBN, 1, b_imgs, 1, nullptr);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  dim3 grid((unsigned)p.a_tiles, (unsigned)p.n_split);
+  if (kind == 0) {
+    auto kern = tc_reduce_kernel<TcConvCfg, 2>;
+    B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    kern<<<grid, TcConvCfg::THREADS, (size_t)p.smem, st>>>(a_imgs, b_imgs, part, N, p.kp, (int)p.b_tiles,
+                                                          p.tiles_per_split, p.nstage, D);
+  } else {
+    auto kern = tc_reduce_kernel<TcConvCfg, 3>;
+    B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    kern<<<grid, TcConvCfg::THREADS, (size_t)p.smem, st>>>(a_imgs, b_imgs, part, N, p.kp, (int)p.b_tiles,
+                                                          p.tiles_per_split, p.nstage, D);
+  }
+  B200OT_CUDA_TRY(cudaGetLastError());
+  *part_out = part;
+  *n_part_out = p.n_split * (kTcEpi / 4);
+  return B200OT_OK;
+}
 
 // Tensor-core softmin partials (p = 2): packs both clouds, runs the reduction, leaves n_part (m, s) sets in
 // `*part_out` (inside scratch) for b200ot_softmin_finalize.
@@ -187,7 +224,7 @@ int softmin_partial_tc(const float* x, const float* y, const float* h_a, const f
   B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   dim3 grid((unsigned)p.a_tiles, (unsigned)p.n_split);
   kern<<<grid, TcConvCfg::THREADS, (size_t)p.smem, st>>>(a_imgs, b_imgs, part, N, p.kp, (int)p.b_tiles,
-                                                        p.tiles_per_split, p.nstage);
+                                                        p.tiles_per_split, p.nstage, D);
   B200OT_CUDA_TRY(cudaGetLastError());
   *part_out = part;
   *n_part_out = p.n_split * (kTcEpi / 4);
@@ -214,7 +251,7 @@ static int conv_fwd_tc(const float* x, const float* y, const float* w, const flo
   B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   dim3 grid((unsigned)p.a_tiles, (unsigned)p.n_split);
   kern<<<grid, TcConvCfg::THREADS, (size_t)p.smem, st>>>(a_imgs, b_imgs, part, N, p.kp, (int)p.b_tiles,
-                                                        p.tiles_per_split, p.nstage);
+                                                        p.tiles_per_split, p.nstage, D);
   B200OT_CUDA_TRY(cudaGetLastError());
   conv_fwd_finalize_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, st>>>(part, p.n_split * (kTcEpi / 4), 1.f, out,
                                                                        N);
@@ -230,7 +267,7 @@ extern "C" {
 
 B200OT_API int64_t b200ot_kernel_conv_scratch_bytes(int64_t N, int64_t M, int32_t D) {
   if (N <= 0 || M <= 0 || D <= 0) return 0;
-  if (tc_supported_dim(D)) return make_tc_plan(N, M, D).total;
+  if (tc_supported_dim(D)) return make_tc_plan(N, M, D, true).total;
   const ReducePlan pl = make_plan(N, M);
   const int64_t cols = b200ot_packed_cols_floats(M, D, 2) * 4;
   const int64_t part = (int64_t)pl.n_split * N * 4 * (D + 1);
@@ -274,12 +311,25 @@ B200OT_API int b200ot_kernel_conv_bwd_x(const float* x, const float* y, const fl
                                         const float* grad_out, float* grad_x, int64_t N, int64_t M, int32_t D,
                                         int32_t kind, float blur, void* scratch, int64_t scratch_bytes,
                                         void* stream) {
-  if (!x || !y || !w || !grad_out || !grad_x || !scratch || N <= 0 || M <= 0 || !supported_simt_dim(D) ||
+  const bool tc = (kind == B200OT_KERNEL_GAUSSIAN) && tc_supported_dim(D);
+  if (!x || !y || !w || !grad_out || !grad_x || !scratch || N <= 0 || M <= 0 || (!supported_simt_dim(D) && !tc) ||
       kind < 0 || kind > 2)
     return B200OT_EINVAL;
   if (kind != B200OT_KERNEL_ENERGY && !(blur > 0.f)) return B200OT_EINVAL;
   if (((uintptr_t)scratch) & 15) return B200OT_EALIGN;
   if (scratch_bytes < b200ot_kernel_conv_scratch_bytes(N, M, D)) return B200OT_ESCRATCH;
+  if (tc) {
+    float* tc_part = nullptr;
+    int n_part = 0;
+    const float scale = sqrtf(kLog2e) / blur;
+    const int rc = bwd_partial_tc(0, x, y, w, nullptr, nullptr, 0.f, nullptr, center, scale, N, M, D, scratch,
+                                  &tc_part, &n_part, (cudaStream_t)stream);
+    if (rc) return rc;
+    conv_bwd_finalize_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, (cudaStream_t)stream>>>(
+        tc_part, n_part, x, center, grad_out, grad_x, N, D, kind, scale, 1.0f / (scale * blur * blur));
+    B200OT_CUDA_TRY(cudaGetLastError());
+    return B200OT_OK;
+  }
   const ReducePlan pl = make_plan(N, M);
   const ConvScales cs = conv_scales(kind, blur);
   float* cols = reinterpret_cast<float*>(scratch);

@@ -152,8 +152,8 @@ B200OT_API int b200ot_softmin_bwd_partial_sparse(const float* x, const float* ce
 B200OT_API int b200ot_softmin_bwd_finalize(const float* part, int32_t n_part, const float* x, const float* center,
                                            const float* grad_out, float* grad_x, int64_t N, int32_t D, int32_t p,
                                            float eps, void* stream) {
-  if (!part || n_part <= 0 || !x || !grad_out || !grad_x || N <= 0 || !supported_simt_dim(D) ||
-      (p != 1 && p != 2) || !(eps > 0.f))
+  if (!part || n_part <= 0 || !x || !grad_out || !grad_x || N <= 0 ||
+      (!supported_simt_dim(D) && !(tc_supported_dim(D) && p == 2)) || (p != 1 && p != 2) || !(eps > 0.f))
     return B200OT_EINVAL;
   const int threads = 256;
   softmin_bwd_finalize_kernel<<<(unsigned)ceil_div64(N, threads), threads, 0, (cudaStream_t)stream>>>(
@@ -166,11 +166,20 @@ B200OT_API int b200ot_softmin_bwd_x(const float* x, const float* y, const float*
                                     float h_scale_b, const float* center, const float* lse2, const float* grad_out,
                                     float* grad_x, int64_t N, int64_t M, int32_t D, int32_t p, float eps,
                                     void* scratch, int64_t scratch_bytes, void* stream) {
-  if (!x || !y || !h_a || !lse2 || !grad_out || !grad_x || !scratch || N <= 0 || M <= 0 || !supported_simt_dim(D) ||
-      (p != 1 && p != 2) || !(eps > 0.f))
+  const bool tc = tc_supported_dim(D) && p == 2;
+  if (!x || !y || !h_a || !lse2 || !grad_out || !grad_x || !scratch || N <= 0 || M <= 0 ||
+      (!supported_simt_dim(D) && !tc) || (p != 1 && p != 2) || !(eps > 0.f))
     return B200OT_EINVAL;
   if (((uintptr_t)scratch) & 15) return B200OT_EALIGN;
   if (scratch_bytes < b200ot_softmin_scratch_bytes(N, M, D)) return B200OT_ESCRATCH;
+  if (tc) {
+    float* tc_part = nullptr;
+    int n_part = 0;
+    const int rc = bwd_partial_tc(1, x, y, nullptr, h_a, h_b, h_scale_b, lse2, center, softmin_coord_scale(2, eps), N, M,
+                                  D, scratch, &tc_part, &n_part, (cudaStream_t)stream);
+    if (rc) return rc;
+    return b200ot_softmin_bwd_finalize(tc_part, n_part, x, center, grad_out, grad_x, N, D, p, eps, stream);
+  }
   const ReducePlan pl = make_plan(N, M);
   float* cols = reinterpret_cast<float*>(scratch);
   float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) +

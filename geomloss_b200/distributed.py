@@ -121,6 +121,14 @@ class CudaStages:
         return gx
 
 
+    # -- kernel convolutions (plain sums: partial results simply add across shards) --
+    def conv_shard(self, kind, x, y, w, blur, center):
+        return ops.kernel_conv_raw(kind, x, y, w, blur, center=center)
+
+    def conv_grad_shard(self, kind, x, y, w, blur, grad_out, center):
+        return ops.kernel_conv_grad_rows(kind, x, y, w, blur, grad_out, center=center)
+
+
 class ColumnShardedEngine:
     """Drop-in replacements for ``ops.softmin_raw`` / ``ops.softmin`` whose column reduction is spread over
     the ranks of ``group``.  Every rank must pass identical (replicated) tensors."""
@@ -155,9 +163,14 @@ class ColumnShardedEngine:
         return _ShardedSoftmin.apply(self, x, y.detach(), h_a.detach(), None if h_b is None else h_b.detach(),
                                      h_scale_b, eps, p, center, scale_out)
 
+    # -- kernel MMD matvec: out = K(x, y) @ w with the columns sharded, one all_reduce(SUM) --------
+    def kernel_conv(self, kind, x, y, w, blur, *, center=None):
+        return _ShardedConv.apply(self, x, y, w, kind, blur, center)
+
     def attach(self, loss_module):
-        """Make a ``SamplesLoss`` module run its Sinkhorn softmins through this engine."""
-        loss_module._engine = dict(softmin_raw=self.softmin_raw, softmin_grad=self.softmin)
+        """Make a ``SamplesLoss`` module run its reductions (Sinkhorn softmins, kernel matvecs) through this
+        engine."""
+        loss_module._engine = dict(softmin_raw=self.softmin_raw, softmin_grad=self.softmin, conv=self.kernel_conv)
         return loss_module
 
 
@@ -192,3 +205,61 @@ class _ShardedSoftmin(torch.autograd.Function):
         eng.collectives += 1
         gx = eng.stages.softmin_bwd_finalize(sums, eps, x, center, (grad_out * scale_out).contiguous(), p)
         return None, gx, None, None, None, None, None, None, None, None
+
+
+class _ShardedConv(torch.autograd.Function):
+    """out = K(x, y) @ w, columns sharded.  Gradients: rows by a sharded reduction + all_reduce; columns and
+    weights are computed for the local shard (full row reduction, kernels are symmetric) and all_gathered."""
+
+    @staticmethod
+    def forward(ctx, eng, x, y, w, kind, blur, center):
+        lo, hi = shard_bounds(y.shape[0], eng.rank, eng.world)
+        if hi > lo:
+            out = eng.stages.conv_shard(kind, x, y[lo:hi], w[lo:hi], blur, center)
+        else:
+            out = torch.zeros(x.shape[0], dtype=x.dtype, device=x.device)
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=eng.group)
+        eng.collectives += 1
+        ctx.eng = eng
+        ctx.save_for_backward(x, y, w, center if center is not None else w)
+        ctx.meta = (kind, float(blur), center is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        eng = ctx.eng
+        x, y, w, center = ctx.saved_tensors
+        kind, blur, has_center = ctx.meta
+        center = center if has_center else None
+        go = go.contiguous()
+        M = y.shape[0]
+        lo, hi = shard_bounds(M, eng.rank, eng.world)
+        gx = gy = gw = None
+        if ctx.needs_input_grad[1]:
+            if hi > lo:
+                gx = eng.stages.conv_grad_shard(kind, x, y[lo:hi], w[lo:hi], blur, go, center)
+            else:
+                gx = torch.zeros_like(x)
+            dist.all_reduce(gx, op=dist.ReduceOp.SUM, group=eng.group)
+            eng.collectives += 1
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            # shard-local rows y[lo:hi] against ALL of x; ragged shards -> pad to the largest, gather, trim
+            size = -(-M // eng.world)
+            sizes = [shard_bounds(M, r, eng.world) for r in range(eng.world)]
+            if ctx.needs_input_grad[2]:
+                loc = torch.zeros(size, y.shape[1], dtype=y.dtype, device=y.device)
+                if hi > lo:
+                    loc[: hi - lo] = eng.stages.conv_grad_shard(kind, y[lo:hi], x, go, blur, w[lo:hi], center)
+                buf = torch.empty(eng.world * size, y.shape[1], dtype=y.dtype, device=y.device)
+                dist.all_gather_into_tensor(buf, loc, group=eng.group)
+                gy = torch.cat([buf[r * size: r * size + (b - a)] for r, (a, b) in enumerate(sizes)])
+                eng.collectives += 1
+            if ctx.needs_input_grad[3]:
+                loc = torch.zeros(size, dtype=w.dtype, device=w.device)
+                if hi > lo:
+                    loc[: hi - lo] = eng.stages.conv_shard(kind, y[lo:hi], x, go, blur, center)
+                buf = torch.empty(eng.world * size, dtype=w.dtype, device=w.device)
+                dist.all_gather_into_tensor(buf, loc, group=eng.group)
+                gw = torch.cat([buf[r * size: r * size + (b - a)] for r, (a, b) in enumerate(sizes)])
+                eng.collectives += 1
+        return None, gx, gy, gw, None, None, None

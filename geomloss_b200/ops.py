@@ -48,7 +48,7 @@ def _f32c(t, name):
     return t.contiguous()
 
 
-MAX_D_TC = 64  # forward softmin (p = 2) and gaussian kernel convolution: tensor-core path for 8 < D <= 64
+MAX_D_TC = 64  # softmin (p = 2) and gaussian kernel convolution, forward + row gradients: tensor-core path, 8 < D <= 64
 
 
 def _check_clouds(x, y, max_d=None):
@@ -124,7 +124,7 @@ def softmin_grad_rows(eps, x, y, h_a, h_b, h_scale_b, lse2, grad_out, *, p=2, ce
     """grad_x of <grad_out, softmin(eps, (x, y), h)> with y, h constant (b200ot_softmin_bwd_x)."""
     x, y, h_a, h_b = _f32c(x, "x"), _f32c(y, "y"), _f32c(h_a, "h_a"), _f32c(h_b, "h_b")
     center, lse2, grad_out = _f32c(center, "center"), _f32c(lse2, "lse2"), _f32c(grad_out, "grad_out")
-    _check_clouds(x, y)  # row gradients: CUDA-core kernels only (D <= MAX_D)
+    _check_clouds(x, y, MAX_D_TC if p == 2 else MAX_D)
     N, D = x.shape
     M = y.shape[0]
     dev = x.device
@@ -202,7 +202,7 @@ def kernel_conv_raw(kind, x, y, w, blur, *, center=None):
 def kernel_conv_grad_rows(kind, x, y, w, blur, grad_out, *, center=None):
     x, y, w, center = _f32c(x, "x"), _f32c(y, "y"), _f32c(w, "w"), _f32c(center, "center")
     grad_out = _f32c(grad_out, "grad_out")
-    _check_clouds(x, y)  # row gradients: CUDA-core kernels only (D <= MAX_D)
+    _check_clouds(x, y, MAX_D_TC if kind == "gaussian" else MAX_D)
     N, D = x.shape
     M = y.shape[0]
     dev = x.device

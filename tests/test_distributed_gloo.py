@@ -72,6 +72,21 @@ class OracleStages:
         return (grad_out.double()[:, None] * g).float()
 
 
+    def conv_shard(self, kind, x, y, w, blur, center):
+        from oracle import geomloss_oracle as O
+
+        return (O.kernel_matrix(kind, x.double(), y.double(), blur) @ w.double()).float()
+
+    def conv_grad_shard(self, kind, x, y, w, blur, grad_out, center):
+        from oracle import geomloss_oracle as O
+
+        with torch.enable_grad():  # called from inside an autograd backward (grad mode is off there)
+            xr = x.detach().double().requires_grad_(True)
+            out = O.kernel_matrix(kind, xr, y.detach().double(), blur) @ w.detach().double()
+            (g,) = torch.autograd.grad(out, xr, grad_out.detach().double())
+        return g.float()
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -114,6 +129,20 @@ def _worker(rank, world, port, results):
                             gy=(gy - ry).abs().max().item(), gscale=rx.abs().max().item(),
                             F=(F - Fr).abs().max().item(), G=(G - Gr).abs().max().item(),
                             collectives=eng.collectives)
+        # kernel MMDs: sharded matvecs (all_reduce) and their three gradients (all_reduce / all_gather)
+        for kind in ("gaussian", "energy"):
+            eng = ColumnShardedEngine(stages=OracleStages())
+            ag, xg = a.clone().requires_grad_(True), x.clone().requires_grad_(True)
+            bg, yg = b.clone().requires_grad_(True), y.clone().requires_grad_(True)
+            val = eng.attach(SamplesLoss(kind, blur=0.3))(ag, xg, bg, yg)
+            grads = torch.autograd.grad(val, [ag, xg, bg, yg])
+            ar, xr = a.double().requires_grad_(True), x.double().requires_grad_(True)
+            br, yr = b.double().requires_grad_(True), y.double().requires_grad_(True)
+            ref = O.samples_loss(ar, xr, br, yr, loss=kind, blur=0.3)
+            rgrads = torch.autograd.grad(ref, [ar, xr, br, yr])
+            out["mmd_" + kind] = dict(val=val.item(), ref=ref.item(),
+                                      gerr=max((g.double() - r).abs().max().item() / max(r.abs().max().item(), 1e-12)
+                                               for g, r in zip(grads, rgrads)), collectives=eng.collectives)
         # every rank must end with the same numbers (replicated state)
         vals = [None] * world
         dist.all_gather_object(vals, out["bal"]["val"])
@@ -143,6 +172,10 @@ def test_column_sharded_engine_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert out["replicated"]
+    for kind in ("gaussian", "energy"):
+        r = out["mmd_" + kind]
+        assert abs(r["val"] - r["ref"]) <= 1e-5 * abs(r["ref"]) + 1e-9, r
+        assert r["gerr"] < 1e-4 and r["collectives"] > 0, r
     for tag in ("bal", "unb_p1"):
         r = out[tag]
         assert abs(r["val"] - r["ref"]) <= 2e-5 * abs(r["ref"]), r

@@ -149,7 +149,7 @@ def test_kernel_conv_vs_oracle(kind):
 @pytest.mark.parametrize("shape", [(300, 500, 16), (129, 65, 33), (1000, 2100, 64), (4000, 3000, 64)])
 def test_gaussian_conv_tensor_core_path(shape):
     """8 < D <= 64: the exponent comes from tcgen05.mma (bf16x3 split operands, fp32 accumulate in TMEM)."""
-    from geomloss_b200 import ops
+    from geomloss_b200 import SamplesLoss, ops
     from oracle import geomloss_oracle as O
 
     n, m, d = shape
@@ -161,6 +161,16 @@ def test_gaussian_conv_tensor_core_path(shape):
         out = ops.kernel_conv_raw("gaussian", x.to(DEV), y.to(DEV), w.to(DEV), blur,
                                   center=ops.default_center(x.to(DEV), y.to(DEV))).cpu().numpy()
         np.testing.assert_allclose(out, ref, rtol=2e-5, atol=1e-30, err_msg=f"blur={blur}")
+    # gradients of the gaussian MMD at D > 8 (rows, columns, weights) against fp64 autograd of the oracle
+    xg, yg = x.to(DEV).requires_grad_(True), y.to(DEV).requires_grad_(True)
+    val = SamplesLoss("gaussian", blur=2.0)(xg, yg)
+    gx, gy = torch.autograd.grad(val, [xg, yg])
+    xr, yr = x.double().requires_grad_(True), y.double().requires_grad_(True)
+    ref = O.samples_loss(xr, yr, loss="gaussian", blur=2.0)
+    rx, ry = torch.autograd.grad(ref, [xr, yr])
+    assert abs(val.item() - ref.item()) <= 1e-4 * abs(ref.item()) + 1e-9
+    assert (gx.cpu().double() - rx).abs().max() <= 2e-4 * rx.abs().max()
+    assert (gy.cpu().double() - ry).abs().max() <= 2e-4 * ry.abs().max()
     # BASELINE configs[2] regime (blur = .05 at D = 64): |x/blur|^2 ~ 1e4, every off-diagonal term underflows and
     # the diagonal exponent is a cancellation of three O(6000) numbers; fp32 accumulation (the reference's own
     # fp32 expansion has ~1e-3 error here) bounds the accuracy, the result must stay ~1
@@ -190,11 +200,21 @@ def test_softmin_tensor_core_path(shape):
     Fr, Gr = O.samples_loss(x.double(), y.double(), loss="sinkhorn", p=2, blur=0.5, scaling=0.6, potentials=True)
     assert (F.cpu().double() - Fr).abs().max() < 2e-5 * max(1.0, Fr.abs().max().item())
     assert (G.cpu().double() - Gr).abs().max() < 2e-5 * max(1.0, Gr.abs().max().item())
-    # gradients w.r.t. positions are not built for D > 8 yet: loud, typed failure — never a silent fallback
-    xg = x.to(DEV).requires_grad_(True)
-    val = SamplesLoss("sinkhorn", p=2, blur=0.5, scaling=0.6)(xg, y.to(DEV))
-    with pytest.raises(NotImplementedError):
-        val.backward()
+    # row gradients: exponent from the tensor cores, D-wide weighted sums on the CUDA cores
+    go = torch.randn(n, generator=g)
+    for eps in (2.0, 0.3):
+        ref = O.softmin_grad_rows(eps, x.double(), y.double(), h.double(), go.double(), p=2).numpy()
+        xg = x.to(DEV).requires_grad_(True)
+        out = ops.softmin(eps, xg, y.to(DEV), h.to(DEV), p=2, center=ops.default_center(x.to(DEV), y.to(DEV)))
+        (gx,) = torch.autograd.grad(out, xg, go.to(DEV))
+        np.testing.assert_allclose(gx.cpu().numpy(), ref, atol=5e-5 * max(1.0, np.abs(ref).max()))
+    xg, yg = x.to(DEV).requires_grad_(True), y.to(DEV).requires_grad_(True)
+    val = SamplesLoss("sinkhorn", p=2, blur=0.5, scaling=0.6)(xg, yg)
+    gx, gy = torch.autograd.grad(val, [xg, yg])
+    xr, yr = x.double().requires_grad_(True), y.double().requires_grad_(True)
+    rx, ry = torch.autograd.grad(O.samples_loss(xr, yr, loss="sinkhorn", p=2, blur=0.5, scaling=0.6), [xr, yr])
+    assert (gx.cpu().double() - rx).abs().max() <= 1e-4 * rx.abs().max()
+    assert (gy.cpu().double() - ry).abs().max() <= 1e-4 * ry.abs().max()
 
 
 @pytest.mark.parametrize("kind", ["gaussian", "laplacian", "energy"])
