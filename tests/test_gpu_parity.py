@@ -168,7 +168,8 @@ def test_gaussian_conv_tensor_core_path(shape):
     xr, yr = x.double().requires_grad_(True), y.double().requires_grad_(True)
     ref = O.samples_loss(xr, yr, loss="gaussian", blur=2.0)
     rx, ry = torch.autograd.grad(ref, [xr, yr])
-    assert abs(val.item() - ref.item()) <= 1e-4 * abs(ref.item()) + 1e-9
+    # (the MMD value is a difference of three O(1) sums: fp32 matvec rounding is ~1e-7 absolute)
+    assert abs(val.item() - ref.item()) <= 1e-4 * abs(ref.item()) + 3e-7
     assert (gx.cpu().double() - rx).abs().max() <= 2e-4 * rx.abs().max()
     assert (gy.cpu().double() - ry).abs().max() <= 2e-4 * ry.abs().max()
     # BASELINE configs[2] regime (blur = .05 at D = 64): |x/blur|^2 ~ 1e4, every off-diagonal term underflows and

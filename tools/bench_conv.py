@@ -35,3 +35,28 @@ for D in dims:
         ms = min(ts)
         print(json.dumps({"conv": kind, "N": N, "M": N, "D": D, "ms": round(ms, 3),
                           "Tpairs_s": round(N * N / (ms * 1e-3) / 1e12, 3), "sum": float(out.sum())}))
+
+# forward + backward of the gaussian MMD at D = 64 (BASELINE configs[2] protocol: L = Loss(x, y); L.backward())
+if 64 in dims:
+    import time
+
+    from geomloss_b200 import SamplesLoss
+
+    n = min(N, 400_000)
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(n, 64, generator=g).to(dev).requires_grad_(True)
+    y = torch.rand(n, 64, generator=g).to(dev)
+    L = SamplesLoss("gaussian", blur=2.0)
+    for phase in ("fwd", "fwd+bwd"):
+        for rep in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            val = L(x, y)
+            if phase == "fwd+bwd":
+                (gx,) = torch.autograd.grad(val, x)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        # forward: 3 matvecs (xx, yy, xy); backward adds d/dx of the xx and xy terms (2 row-gradient reductions)
+        print(json.dumps({"loss": "gaussian MMD", "N": n, "D": 64, "phase": phase, "s": round(dt, 4),
+                          "pairs": (3 if phase == "fwd" else 5) * n * n,
+                          "Tpairs_s": round((3 if phase == "fwd" else 5) * n * n / dt / 1e12, 3)}))
