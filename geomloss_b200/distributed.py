@@ -120,6 +120,54 @@ class CudaStages:
         ops.count_launches(1)
         return gx
 
+    # -- block-sparse (multiscale fine phase): ALL columns are packed, the tile lists select this rank's --
+    def tile_shape(self):
+        r, c = ctypes.c_int32(0), ctypes.c_int32(0)
+        _lib.lib().b200ot_sparse_tile_shape(ctypes.byref(r), ctypes.byref(c))
+        return r.value, c.value
+
+    def softmin_sparse_shard(self, eps, x, y, h_a, h_b, h_scale_b, p, center, tile_ptr, tile_list):
+        """(N, 2) partial (m, s) over the column tiles listed for this rank."""
+        x, y, h_a, h_b, center = (ops._f32c(t, n) for t, n in ((x, "x"), (y, "y"), (h_a, "h_a"), (h_b, "h_b"),
+                                                               (center, "center")))
+        N, D = x.shape
+        M = y.shape[0]
+        dev = x.device
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            part = torch.empty(N, 2, dtype=torch.float32, device=dev)
+            cols = ops._scratch(L.b200ot_packed_cols_floats(M, D, 1) * 4, dev, "sparse_cols")
+            st = ops._stream(dev)
+            _lib.check(L.b200ot_softmin_pack(ops._ptr(y), ops._ptr(h_a), ops._ptr(h_b), float(h_scale_b),
+                                             ops._ptr(center), M, D, int(p), float(eps), ops._ptr(cols), st),
+                       "b200ot_softmin_pack")
+            _lib.check(L.b200ot_softmin_partial_sparse(ops._ptr(x), ops._ptr(center), ops._ptr(cols),
+                                                       ops._ptr(tile_ptr), ops._ptr(tile_list), ops._ptr(part), N, M,
+                                                       D, int(p), float(eps), st), "b200ot_softmin_partial_sparse")
+        ops.count_launches(2)
+        return part
+
+    def softmin_bwd_sparse_shard(self, eps, x, y, h_a, h_b, h_scale_b, p, center, lse2, tile_ptr, tile_list):
+        """(N, D+1) partial backward sums over the column tiles listed for this rank."""
+        x, y, h_a, h_b, center, lse2 = (ops._f32c(t, n) for t, n in ((x, "x"), (y, "y"), (h_a, "h_a"), (h_b, "h_b"),
+                                                                     (center, "center"), (lse2, "lse2")))
+        N, D = x.shape
+        M = y.shape[0]
+        dev = x.device
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            sums = torch.empty(N, D + 1, dtype=torch.float32, device=dev)
+            cols = ops._scratch(L.b200ot_packed_cols_floats(M, D, 1) * 4, dev, "sparse_cols")
+            st = ops._stream(dev)
+            _lib.check(L.b200ot_softmin_pack(ops._ptr(y), ops._ptr(h_a), ops._ptr(h_b), float(h_scale_b),
+                                             ops._ptr(center), M, D, int(p), float(eps), ops._ptr(cols), st),
+                       "b200ot_softmin_pack")
+            _lib.check(L.b200ot_softmin_bwd_partial_sparse(ops._ptr(x), ops._ptr(center), ops._ptr(cols),
+                                                           ops._ptr(lse2), ops._ptr(tile_ptr), ops._ptr(tile_list),
+                                                           ops._ptr(sums), N, M, D, int(p), float(eps), st),
+                       "b200ot_softmin_bwd_partial_sparse")
+        ops.count_launches(2)
+        return sums
 
     # -- kernel convolutions (plain sums: partial results simply add across shards) --
     def conv_shard(self, kind, x, y, w, blur, center):
@@ -144,9 +192,12 @@ class ColumnShardedEngine:
 
     # -- forward -------------------------------------------------------------------------------
     def softmin_raw(self, eps, x, y, h_a, h_b=None, h_scale_b=0.0, *, p=2, center=None, out_old=None,
-                    alpha_old=0.0, beta=1.0, out=None, want_lse2=False):
+                    alpha_old=0.0, beta=1.0, out=None, want_lse2=False, local=False):
         M = y.shape[0]
         N = x.shape[0]
+        if local:  # replicated (un-sharded) reduction: every rank computes the whole thing, no collective
+            mine = self.stages.softmin_shard(eps, x, y, h_a, h_b, h_scale_b, p, center)
+            return self.stages.softmin_finalize(mine[None], eps, out_old, alpha_old, beta, want_lse2)
         lo, hi = shard_bounds(M, self.rank, self.world)
         if hi > lo:
             mine = self.stages.softmin_shard(eps, x, y[lo:hi], h_a[lo:hi], None if h_b is None else h_b[lo:hi],
@@ -159,9 +210,40 @@ class ColumnShardedEngine:
         return self.stages.softmin_finalize(parts, eps, out_old, alpha_old, beta, want_lse2)
 
     # -- forward + backward (the final, gradient-carrying Sinkhorn step) --------------------------
-    def softmin(self, eps, x, y, h_a, h_b=None, h_scale_b=0.0, *, p=2, center=None, scale_out=1.0):
+    def softmin(self, eps, x, y, h_a, h_b=None, h_scale_b=0.0, *, p=2, center=None, scale_out=1.0, local=False):
         return _ShardedSoftmin.apply(self, x, y.detach(), h_a.detach(), None if h_b is None else h_b.detach(),
-                                     h_scale_b, eps, p, center, scale_out)
+                                     h_scale_b, eps, p, center, scale_out, local, None)
+
+    # -- the operator set of multiscale.sinkhorn_multiscale (same names as multiscale.LocalEngine) ----
+    def tile_shape(self):
+        return self.stages.tile_shape()
+
+    def broadcast(self, t):
+        t = t.contiguous()
+        dist.broadcast(t, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        self.collectives += 1
+        return t
+
+    def dense_raw(self, *args, **kw):
+        return self.softmin_raw(*args, local=True, **kw)
+
+    def dense(self, *args, **kw):
+        return self.softmin(*args, local=True, **kw)
+
+    def sparse_raw(self, eps, x, y, h_a, h_b, h_scale_b, prob, *, p=2, center=None, out_old=None, alpha_old=0.0,
+                   beta=1.0, want_lse2=False):
+        """Block-sparse softmin; ``prob`` holds THIS rank's column tiles (multiscale.tiles_from_cluster_mask)."""
+        mine = self.stages.softmin_sparse_shard(eps, x, y, h_a, h_b, h_scale_b, p, center, prob.tile_ptr,
+                                                prob.tile_list)
+        N = x.shape[0]
+        parts = torch.empty(self.world, N, 2, dtype=mine.dtype, device=mine.device)
+        dist.all_gather_into_tensor(parts.view(self.world * N, 2), mine, group=self.group)
+        self.collectives += 1
+        return self.stages.softmin_finalize(parts, eps, out_old, alpha_old, beta, want_lse2)
+
+    def sparse(self, eps, x, y, h_a, h_b, h_scale_b, prob, *, p=2, center=None, scale_out=1.0):
+        return _ShardedSoftmin.apply(self, x, y.detach(), h_a.detach(), None if h_b is None else h_b.detach(),
+                                     h_scale_b, eps, p, center, scale_out, False, prob)
 
     # -- kernel MMD matvec: out = K(x, y) @ w with the columns sharded, one all_reduce(SUM) --------
     def kernel_conv(self, kind, x, y, w, blur, *, center=None):
@@ -171,17 +253,22 @@ class ColumnShardedEngine:
         """Make a ``SamplesLoss`` module run its reductions (Sinkhorn softmins, kernel matvecs) through this
         engine."""
         loss_module._engine = dict(softmin_raw=self.softmin_raw, softmin_grad=self.softmin, conv=self.kernel_conv)
+        loss_module._multiscale_engine = self
         return loss_module
 
 
 class _ShardedSoftmin(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, eng, x, y, h_a, h_b, h_scale_b, eps, p, center, scale_out):
+    def forward(ctx, eng, x, y, h_a, h_b, h_scale_b, eps, p, center, scale_out, local, prob):
         need = ctx.needs_input_grad[1]
-        out, lse2 = eng.softmin_raw(eps, x, y, h_a, h_b, h_scale_b, p=p, center=center, beta=scale_out,
-                                    want_lse2=need)
+        if prob is not None:
+            out, lse2 = eng.sparse_raw(eps, x, y, h_a, h_b, h_scale_b, prob, p=p, center=center, beta=scale_out,
+                                       want_lse2=need)
+        else:
+            out, lse2 = eng.softmin_raw(eps, x, y, h_a, h_b, h_scale_b, p=p, center=center, beta=scale_out,
+                                        want_lse2=need, local=local)
         if need:
-            ctx.eng = eng
+            ctx.eng, ctx.local, ctx.prob = eng, local, prob
             ctx.save_for_backward(x, y, h_a, h_b if h_b is not None else h_a, center if center is not None else h_a,
                                   lse2)
             ctx.meta = (float(h_scale_b), float(eps), int(p), float(scale_out), h_b is not None, center is not None)
@@ -195,16 +282,20 @@ class _ShardedSoftmin(torch.autograd.Function):
         h_b = h_b if has_hb else None
         center = center if has_center else None
         M = y.shape[0]
-        lo, hi = shard_bounds(M, eng.rank, eng.world)
-        if hi > lo:
+        lo, hi = (0, M) if ctx.local else shard_bounds(M, eng.rank, eng.world)
+        if ctx.prob is not None:
+            sums = eng.stages.softmin_bwd_sparse_shard(eps, x, y, h_a, h_b, h_scale_b, p, center, lse2,
+                                                       ctx.prob.tile_ptr, ctx.prob.tile_list)
+        elif hi > lo:
             sums = eng.stages.softmin_bwd_shard(eps, x, y[lo:hi], h_a[lo:hi], None if h_b is None else h_b[lo:hi],
                                                 h_scale_b, p, center, lse2)
         else:
             sums = torch.zeros(x.shape[0], x.shape[1] + 1, dtype=x.dtype, device=x.device)
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=eng.group)
-        eng.collectives += 1
+        if not ctx.local:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=eng.group)
+            eng.collectives += 1
         gx = eng.stages.softmin_bwd_finalize(sums, eps, x, center, (grad_out * scale_out).contiguous(), p)
-        return None, gx, None, None, None, None, None, None, None, None
+        return None, gx, None, None, None, None, None, None, None, None, None, None
 
 
 class _ShardedConv(torch.autograd.Function):

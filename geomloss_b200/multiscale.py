@@ -67,10 +67,14 @@ def tile_shape():
     return r.value, c.value
 
 
-def tiles_from_cluster_mask(keep, lab_rows, lab_cols):
+def tiles_from_cluster_mask(keep, lab_rows, lab_cols, rank=0, world=1, tile=None):
     """Cluster-level mask (Cr, Cc) + sorted labels of the fine rows / columns -> CSR list of column tiles per
-    row tile (int32 tile_ptr, tile_list) for b200ot_softmin_partial_sparse."""
-    tr, tc = tile_shape()
+    row tile (int32 tile_ptr, tile_list) for b200ot_softmin_partial_sparse.
+
+    ``world > 1`` (column-sharded multi-GPU run): rank ``rank`` keeps only the column
+    tiles of ITS contiguous column range; the ranges are cut so that every rank gets the same number of kept
+    tile pairs (clusters are contiguous after the sort, so a range is a slab of column clusters)."""
+    tr, tc = tile if tile is not None else tile_shape()
     n, m = lab_rows.numel(), lab_cols.numel()
     dev = lab_rows.device
     r0 = lab_rows[torch.arange(0, n, tr, device=dev)]
@@ -85,11 +89,21 @@ def tiles_from_cluster_mask(keep, lab_rows, lab_cols):
         box = (K[(r1 + 1)[:, None], (c1 + 1)[None, :]] - K[r0[:, None], (c1 + 1)[None, :]]
                - K[(r1 + 1)[:, None], c0[None, :]] + K[r0[:, None], c0[None, :]])
         keep_t = box > 0
+    density = float(keep_t.float().mean().item())
+    if world > 1:
+        load = keep_t.sum(0).double().cumsum(0)  # kept tile pairs up to (and including) each column tile
+        cuts = torch.searchsorted(load, load[-1] * torch.arange(1, world, device=dev, dtype=torch.float64) / world)
+        cuts = [0] + [int(c) + 1 for c in cuts.tolist()] + [keep_t.shape[1]]
+        cuts = [min(max(c, 0), keep_t.shape[1]) for c in cuts]
+        lo, hi = cuts[rank], max(cuts[rank], cuts[rank + 1])
+        keep_t = keep_t.clone()
+        keep_t[:, :lo] = False
+        keep_t[:, hi:] = False
     nz = keep_t.nonzero()  # sorted by row tile, then column tile (one host sync, as in the reference)
     counts = torch.bincount(nz[:, 0], minlength=keep_t.shape[0])
     tile_ptr = torch.zeros(keep_t.shape[0] + 1, dtype=torch.int32, device=dev)
     tile_ptr[1:] = counts.cumsum(0).to(torch.int32)
-    return tile_ptr.contiguous(), nz[:, 1].to(torch.int32).contiguous(), float(keep_t.float().mean().item())
+    return tile_ptr.contiguous(), nz[:, 1].to(torch.int32).contiguous(), density
 
 
 class SparseProblem:
@@ -163,13 +177,37 @@ class _SparseSoftmin(torch.autograd.Function):
         return gx, None, None, None, None, None, None, None, None, None
 
 
+class LocalEngine:
+    """The reductions of the two-scale driver on ONE GPU.  ``distributed.ColumnShardedEngine`` offers the same
+    five operators with the column tiles of the fine phase spread over the ranks."""
+
+    rank, world = 0, 1
+    tile_shape = staticmethod(tile_shape)
+    dense_raw = staticmethod(ops.softmin_raw)
+    dense = staticmethod(ops.softmin)
+    sparse_raw = staticmethod(softmin_sparse_raw)
+
+    @staticmethod
+    def broadcast(t):
+        return t
+
+    @staticmethod
+    def sparse(eps, x, y, h_a, h_b, h_scale_b, prob, *, p=2, center=None, scale_out=1.0):
+        return _SparseSoftmin.apply(x, y, h_a, h_b, h_scale_b, eps, p, center, scale_out, prob)
+
+
 # ------------------------------------------------------------------------------------------------------
 # driver                                                            sinkhorn_samples.py:547-681
 # ------------------------------------------------------------------------------------------------------
 def sinkhorn_multiscale(a, x, b, y, p=2, blur=0.05, reach=None, diameter=None, scaling=0.5, truncate=5,
                         cluster_scale=None, debias=True, potentials=False, labels_x=None, labels_y=None,
-                        verbose=False, **_ignored):
-    """Two-scale Sinkhorn divergence between a:(N,) x:(N,D) and b:(M,) y:(M,D), D <= 3."""
+                        verbose=False, engine=None, **_ignored):
+    """Two-scale Sinkhorn divergence between a:(N,) x:(N,D) and b:(M,) y:(M,D), D <= 3.
+
+    ``engine``: ``LocalEngine`` (default) or a ``distributed.ColumnShardedEngine`` — BASELINE configs[3]: the
+    coarse problem (~2000 centroids per cloud) and the fine-rows x coarse-columns extrapolation are replicated,
+    the block-sparse fine phase is column-sharded with one all_gather of (N, 2) partials per softmin."""
+    eng = engine if engine is not None else LocalEngine()
     if p not in (1, 2):
         raise KeyError(p)
     N, D = x.shape
@@ -180,6 +218,8 @@ def sinkhorn_multiscale(a, x, b, y, p=2, blur=0.05, reach=None, diameter=None, s
         cluster_scale = diameter / (np.sqrt(D) * 2000 ** (1 / D))
     (a_c, x_c), (a_s, x_s), lab_x, perm_x = clusterize(a, x, scale=cluster_scale, labels=labels_x)
     (b_c, y_c), (b_s, y_s), lab_y, perm_y = clusterize(b, y, scale=cluster_scale, labels=labels_y)
+    # centroids come from atomics (index_add): every rank must continue from the SAME bits
+    a_c, x_c, b_c, y_c = (eng.broadcast(t) for t in (a_c, x_c, b_c, y_c))
 
     jump = len(eps_list) - 1
     for i, eps in enumerate(eps_list[2:]):
@@ -196,7 +236,7 @@ def sinkhorn_multiscale(a, x, b, y, p=2, blur=0.05, reach=None, diameter=None, s
                 jump, eps_list[jump] ** (1 / p), jump + 1, eps_list[jump + 1] ** (1 / p)))
 
     center = ops.default_center(x.detach(), y.detach())
-    sm = ops.softmin_raw
+    sm = eng.dense_raw
     ac_log, bc_log = log_weights(a_c), log_weights(b_c)
     a_log, b_log = log_weights(a_s.detach()), log_weights(b_s.detach())
     xs_d, ys_d = x_s.detach(), y_s.detach()
@@ -228,7 +268,7 @@ def sinkhorn_multiscale(a, x, b, y, p=2, blur=0.05, reach=None, diameter=None, s
     inv = 1.0 / eps
     if last_is_jump:
         # the extrapolation is the last, gradient-carrying step (sinkhorn_divergence.py:520-526, appendix A-21)
-        smg = ops.softmin
+        smg = eng.dense
         f_ba_f = smg(eps, x_s, y_c, bc_log, g_ab, inv, scale_out=lam, **kw)
         g_ab_f = smg(eps, y_s, x_c, ac_log, f_ba, inv, scale_out=lam, **kw)
         f_aa_f = smg(eps, x_s, x_c, ac_log, f_aa, inv, scale_out=lam, **kw) if debias else None
@@ -246,13 +286,14 @@ def sinkhorn_multiscale(a, x, b, y, p=2, blur=0.05, reach=None, diameter=None, s
                 return fu[:, None] + gv[None, :] > coarse_cost(u, v) - truncate * eps
 
             k_xy = mask(f_ba, g_ab, x_c, y_c)
+            tkw = dict(rank=eng.rank, world=eng.world, tile=eng.tile_shape())
             probs = {
-                "xy": SparseProblem(*tiles_from_cluster_mask(k_xy, lab_x, lab_y)),
-                "yx": SparseProblem(*tiles_from_cluster_mask(None if k_xy is None else k_xy.t(), lab_y, lab_x)),
+                "xy": SparseProblem(*tiles_from_cluster_mask(k_xy, lab_x, lab_y, **tkw)),
+                "yx": SparseProblem(*tiles_from_cluster_mask(None if k_xy is None else k_xy.t(), lab_y, lab_x, **tkw)),
             }
             if debias:
-                probs["xx"] = SparseProblem(*tiles_from_cluster_mask(mask(f_aa, f_aa, x_c, x_c), lab_x, lab_x))
-                probs["yy"] = SparseProblem(*tiles_from_cluster_mask(mask(g_bb, g_bb, y_c, y_c), lab_y, lab_y))
+                probs["xx"] = SparseProblem(*tiles_from_cluster_mask(mask(f_aa, f_aa, x_c, x_c), lab_x, lab_x, **tkw))
+                probs["yy"] = SparseProblem(*tiles_from_cluster_mask(mask(g_bb, g_bb, y_c, y_c), lab_y, lab_y, **tkw))
             if verbose:
                 for name, pr in probs.items():
                     print("Keep {:2.1f}% of the {} tile pairs.".format(100 * pr.density, name))
@@ -265,7 +306,7 @@ def sinkhorn_multiscale(a, x, b, y, p=2, blur=0.05, reach=None, diameter=None, s
                 g_bb_f = sm(eps, ys_d, y_c, bc_log, g_bb, inv, beta=lam, **kw)[0]
 
             # ---- fine phase: block-sparse softmins ----
-            sp = softmin_sparse_raw
+            sp = eng.sparse_raw
             for i in range(jump + 1, len(eps_list)):
                 eps = eps_list[i]
                 lam = damping(eps, rho)
@@ -283,12 +324,13 @@ def sinkhorn_multiscale(a, x, b, y, p=2, blur=0.05, reach=None, diameter=None, s
                 f_ba_f, g_ab_f = ft_ba, gt_ab
         # final, non-averaged, gradient-carrying step on the fine clouds (sinkhorn_divergence.py:612-623)
         inv = 1.0 / eps
-        spg = _SparseSoftmin.apply
-        new_f_ba = spg(x_s, ys_d, b_log, g_ab_f, inv, eps, p, center, lam, probs["xy"])
-        new_g_ab = spg(y_s, xs_d, a_log, f_ba_f, inv, eps, p, center, lam, probs["yx"])
+        spg = eng.sparse
+        gkw = dict(p=p, center=center, scale_out=lam)
+        new_f_ba = spg(eps, x_s, ys_d, b_log, g_ab_f, inv, probs["xy"], **gkw)
+        new_g_ab = spg(eps, y_s, xs_d, a_log, f_ba_f, inv, probs["yx"], **gkw)
         if debias:
-            f_aa_f = spg(x_s, xs_d, a_log, f_aa_f, inv, eps, p, center, lam, probs["xx"])
-            g_bb_f = spg(y_s, ys_d, b_log, g_bb_f, inv, eps, p, center, lam, probs["yy"])
+            f_aa_f = spg(eps, x_s, xs_d, a_log, f_aa_f, inv, probs["xx"], **gkw)
+            g_bb_f = spg(eps, y_s, ys_d, b_log, g_bb_f, inv, probs["yy"], **gkw)
         f_ba_f, g_ab_f = new_f_ba, new_g_ab
     if not debias:
         f_aa_f = g_bb_f = None

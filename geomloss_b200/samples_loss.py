@@ -68,6 +68,7 @@ class SamplesLoss(Module):
         self.verbose = verbose
         # injected by geomloss_b200.distributed.shard_columns(): column-sharded reduction operators
         self._engine = {}
+        self._multiscale_engine = None
 
     # ------------------------------------------------------------------------------------------
     def forward(self, *args):
@@ -100,14 +101,14 @@ class SamplesLoss(Module):
         routine = _route(self.loss)
         kw = dict(p=self.p, blur=self.blur, reach=self.reach, diameter=self.diameter, scaling=self.scaling,
                   debias=self.debias, potentials=self.potentials, kernel=self.kernel, **self._engine)
-        if backend == "multiscale" and self.loss == "sinkhorn" and not self._engine and D <= 3:
+        if backend == "multiscale" and self.loss == "sinkhorn" and D <= 3:
             # single problem (B == 0, or B == 1 squeezed like the reference does, samples_loss.py:249-251)
             sq = (lambda t: t[0]) if B == 1 else (lambda t: t)
             values = sinkhorn_multiscale(sq(a), sq(x), sq(b), sq(y), p=self.p, blur=self.blur, reach=self.reach,
                                          diameter=self.diameter, scaling=self.scaling, truncate=self.truncate,
                                          cluster_scale=self.cluster_scale, debias=self.debias,
                                          potentials=self.potentials, labels_x=l_x, labels_y=l_y,
-                                         verbose=self.verbose)
+                                         verbose=self.verbose, engine=self._multiscale_engine)
             if self.potentials:
                 F, G = values
                 return F.view_as(a), G.view_as(b)

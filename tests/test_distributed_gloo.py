@@ -71,6 +71,41 @@ class OracleStages:
         g = (x.double() - sums[:, 1:] / sw) if p == 2 else sums[:, 1:] / sw
         return (grad_out.double()[:, None] * g).float()
 
+    # -- block-sparse stand-ins: dense evaluation, masked at the granularity of the (small, test-only) tiles --
+    TILE = (16, 32)
+
+    def tile_shape(self):
+        return self.TILE
+
+    def _tile_mask(self, N, M, tile_ptr, tile_list):
+        tr, tc = self.TILE
+        mask = torch.zeros(N, M, dtype=torch.bool)
+        ptr, lst = tile_ptr.tolist(), tile_list.tolist()
+        for rt in range(len(ptr) - 1):
+            for ct in lst[ptr[rt]:ptr[rt + 1]]:
+                mask[rt * tr:(rt + 1) * tr, ct * tc:(ct + 1) * tc] = True
+        return mask
+
+    def softmin_sparse_shard(self, eps, x, y, h_a, h_b, h_scale_b, p, center, tile_ptr, tile_list):
+        t = self._t(eps, x.double(), y.double(), h_a.double(), None if h_b is None else h_b.double(), h_scale_b, p)
+        t = t.masked_fill(~self._tile_mask(x.shape[0], y.shape[0], tile_ptr, tile_list), -1.0e30)
+        m = t.max(1).values
+        s = torch.exp2(t - m[:, None]).sum(1)
+        s = torch.where(m <= -1.0e29, torch.zeros_like(s), s)  # a row with no listed tile: neutral partial
+        return torch.stack([m, s], 1).float()
+
+    def softmin_bwd_sparse_shard(self, eps, x, y, h_a, h_b, h_scale_b, p, center, lse2, tile_ptr, tile_list):
+        xd, yd = x.double(), y.double()
+        t = self._t(eps, xd, yd, h_a.double(), None if h_b is None else h_b.double(), h_scale_b, p)
+        w = torch.exp2(t - lse2.double()[:, None]) * self._tile_mask(x.shape[0], y.shape[0], tile_ptr, tile_list)
+        if p == 2:
+            vec = w @ yd
+        else:
+            diff = xd[:, None, :] - yd[None, :, :]
+            q = (diff**2).sum(-1)
+            unit = torch.where(q[..., None] < 1e-8, torch.zeros_like(diff), diff / q.clamp_min(1e-8).sqrt()[..., None])
+            vec = (w[..., None] * unit).sum(1)
+        return torch.cat([w.sum(1, keepdim=True), vec], 1).float()
 
     def conv_shard(self, kind, x, y, w, blur, center):
         from oracle import geomloss_oracle as O
@@ -143,6 +178,33 @@ def _worker(rank, world, port, results):
             out["mmd_" + kind] = dict(val=val.item(), ref=ref.item(),
                                       gerr=max((g.double() - r).abs().max().item() / max(r.abs().max().item(), 1e-12)
                                                for g, r in zip(grads, rgrads)), collectives=eng.collectives)
+        # two-scale (multiscale) Sinkhorn: coarse phase replicated, block-sparse fine phase column-sharded by tiles
+        gm = torch.Generator().manual_seed(5)
+        xm, ym = torch.rand(700, 3, generator=gm), torch.rand(610, 3, generator=gm) * 0.8 + 0.1
+        am, bm = torch.rand(700, generator=gm) + 0.5, torch.rand(610, generator=gm) + 0.5
+        am, bm = am / am.sum(), bm / bm.sum()
+        solo_groups = [dist.new_group([r]) for r in range(world)]  # every rank alone: the un-sharded run
+        for tag, kw, truncate in (("ms_exact", dict(p=2, blur=0.05), None), ("ms_trunc", dict(p=2, blur=0.05), 5),
+                                  ("ms_lastjump", dict(p=2, blur=0.4, reach=0.5), 5)):
+            eng = ColumnShardedEngine(stages=OracleStages())
+            L = eng.attach(SamplesLoss("sinkhorn", backend="multiscale", cluster_scale=0.2, truncate=truncate, **kw))
+            xg = xm.clone().requires_grad_(True)
+            val = L(am, xg, bm, ym)
+            (gx,) = torch.autograd.grad(val, xg)
+            ref = O.sinkhorn_multiscale_dense(am.double(), xm.double(), bm.double(), ym.double(), cluster_scale=0.2,
+                                              truncate=truncate, **kw)
+            # gradient contract (last step only, detached columns) is pinned on the GPU; here: sharded == un-sharded
+            solo = ColumnShardedEngine(group=solo_groups[rank], stages=OracleStages())
+            xs = xm.clone().requires_grad_(True)
+            (rx,) = torch.autograd.grad(solo.attach(SamplesLoss("sinkhorn", backend="multiscale", cluster_scale=0.2,
+                                                                truncate=truncate, **kw))(am, xs, bm, ym), xs)
+            F, G = eng.attach(SamplesLoss("sinkhorn", backend="multiscale", cluster_scale=0.2, truncate=truncate,
+                                          potentials=True, **kw))(am, xm, bm, ym)
+            Fr, Gr = O.sinkhorn_multiscale_dense(am.double(), xm.double(), bm.double(), ym.double(),
+                                                 cluster_scale=0.2, truncate=truncate, potentials=True, **kw)
+            out[tag] = dict(val=val.item(), ref=ref.item(), gx=(gx - rx).abs().max().item(),
+                            gscale=rx.abs().max().item(), F=(F - Fr).abs().max().item(),
+                            G=(G - Gr).abs().max().item(), collectives=eng.collectives)
         # every rank must end with the same numbers (replicated state)
         vals = [None] * world
         dist.all_gather_object(vals, out["bal"]["val"])
@@ -176,6 +238,12 @@ def test_column_sharded_engine_world2():
         r = out["mmd_" + kind]
         assert abs(r["val"] - r["ref"]) <= 1e-5 * abs(r["ref"]) + 1e-9, r
         assert r["gerr"] < 1e-4 and r["collectives"] > 0, r
+    for tag in ("ms_exact", "ms_trunc", "ms_lastjump"):
+        r = out[tag]
+        assert abs(r["val"] - r["ref"]) <= 5e-5 * abs(r["ref"]), (tag, r)
+        assert r["gx"] <= 1e-5 * r["gscale"] and r["gscale"] > 0, (tag, r)
+        assert r["F"] < 2e-5 and r["G"] < 2e-5, (tag, r)
+        assert r["collectives"] > 0
     for tag in ("bal", "unb_p1"):
         r = out[tag]
         assert abs(r["val"] - r["ref"]) <= 2e-5 * abs(r["ref"]), r
