@@ -9,6 +9,7 @@
 #include "pack.cuh"
 #include "plan.cuh"
 #include "rowsum.cuh"
+#include "tcbwd.cuh"
 #include "tcconv.cuh"
 
 #include <type_traits>
@@ -144,8 +145,8 @@ static TcPlan make_tc_plan(int64_t N, int64_t M, int D, bool bwd = false) {
   p.a_tiles = ceil_div64(N, kTcM);
   p.b_tiles = ceil_div64(M, kTcBN);
   p.a_bytes = tc_a_img_bytes(p.kp);
-  p.b_bytes = tc_b_img_bytes(p.kp, kTcBN, bwd ? tc_dk(D) : 0);
-  const int64_t bar_bytes = 8 * (1 + 2 * kTcMaxStage + 2 * 2) + 16;
+  p.b_bytes = tc_b_img_bytes(p.kp, kTcBN);
+  const int64_t bar_bytes = 1024;  // mbarriers, the TMEM slot, (backward) 128 floats of row-sum exchange
   const int64_t avail = 227 * 1024 - bar_bytes - 1024;  // the row operand lives in TMEM, not in shared memory
   int64_t ns = avail / p.b_bytes;
   p.nstage = (int)(ns > kTcMaxStage ? kTcMaxStage : ns);
@@ -178,26 +179,26 @@ int bwd_partial_tc(int kind, const float* x, const float* y, const float* w, con
   float* part = reinterpret_cast<float*>(base + p.off_part);
   const int threads = 128;
   tc_pack_kernel<<<(unsigned)ceil_div64(p.a_tiles * kTcM, threads), threads, 0, st>>>(
-      x, nullptr, nullptr, nullptr, 0.f, 0.f, center, scale, N, D, p.kp, kTcM, 0, a_imgs, 0, lse2);
+      x, nullptr, nullptr, nullptr, 0.f, 0.f, center, scale, N, D, p.kp, kTcM, 0, a_imgs, lse2);
   B200OT_CUDA_TRY(cudaGetLastError());
   tc_pack_kernel<<<(unsigned)ceil_div64(p.b_tiles * kTcBN, threads), threads, 0, st>>>(
-      y, w, h_a, h_b, h_scale_b, kLog2e, center, scale, M, D, p.kp, kTcBN, 1, b_imgs, 1, nullptr);
+      y, w, h_a, h_b, h_scale_b, kLog2e, center, scale, M, D, p.kp, kTcBN, 1, b_imgs, nullptr);
   B200OT_CUDA_TRY(cudaGetLastError());
   dim3 grid((unsigned)p.a_tiles, (unsigned)p.n_split);
   if (kind == 0) {
-    auto kern = tc_reduce_kernel<TcConvCfg, 2>;
+    auto kern = tc_bwd_kernel<TcConvCfg, 2>;
     B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     kern<<<grid, TcConvCfg::THREADS, (size_t)p.smem, st>>>(a_imgs, b_imgs, part, N, p.kp, (int)p.b_tiles,
                                                           p.tiles_per_split, p.nstage, D);
   } else {
-    auto kern = tc_reduce_kernel<TcConvCfg, 3>;
+    auto kern = tc_bwd_kernel<TcConvCfg, 3>;
     B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     kern<<<grid, TcConvCfg::THREADS, (size_t)p.smem, st>>>(a_imgs, b_imgs, part, N, p.kp, (int)p.b_tiles,
                                                           p.tiles_per_split, p.nstage, D);
   }
   B200OT_CUDA_TRY(cudaGetLastError());
   *part_out = part;
-  *n_part_out = p.n_split * (kTcEpi / 4);
+  *n_part_out = p.n_split;  // G of a CTA is complete over its column split (both column halves feed one GEMM)
   return B200OT_OK;
 }
 

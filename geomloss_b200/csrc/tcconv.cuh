@@ -37,10 +37,8 @@ __host__ __device__ inline int tc_dk(int D) { return ((D + 15) / 16) * 16; }
 // K extent of an operand image: three split terms + one 16-wide chunk of rank-one terms
 __host__ __device__ inline int tc_kp(int D) { return 3 * tc_dk(D) + 16; }
 __host__ __device__ inline int64_t tc_a_img_bytes(int kp) { return (int64_t)kTcM * kp * 2; }
-// column image: bf16 operand data | fp32 weights | (backward only) fp32 scaled coordinates [bn][dk]
-__host__ __device__ inline int64_t tc_b_img_bytes(int kp, int bn, int dk_f32 = 0) {
-  return (int64_t)bn * kp * 2 + (int64_t)bn * 4 + (int64_t)bn * dk_f32 * 4;
-}
+// column image: bf16 operand data | fp32 weights
+__host__ __device__ inline int64_t tc_b_img_bytes(int kp, int bn) { return (int64_t)bn * kp * 2 + (int64_t)bn * 4; }
 
 // ---------------------------------------------------------------------------------------------------
 // pack: one thread per (padded) point; writes its 16-byte piece of every K chunk of its tile image
@@ -62,7 +60,7 @@ static __global__ void tc_pack_kernel(const float* __restrict__ pts, const float
                                       const float* __restrict__ h_a, const float* __restrict__ h_b,
                                       float h_scale_b, float h_scale, const float* __restrict__ center,
                                       float scale, int64_t n, int D, int kp, int tile, int is_cols,
-                                      unsigned char* __restrict__ out, int with_f32 = 0,
+                                      unsigned char* __restrict__ out,
                                       const float* __restrict__ row_extra = nullptr) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t npad = ((n + tile - 1) / tile) * tile;
@@ -70,11 +68,8 @@ static __global__ void tc_pack_kernel(const float* __restrict__ pts, const float
   const int64_t t = p / tile;
   const int pt = (int)(p % tile);
   const int dk = tc_dk(D);
-  const int64_t img_bytes =
-      (int64_t)tile * kp * 2 + (is_cols ? (int64_t)tile * 4 : 0) + ((is_cols && with_f32) ? (int64_t)tile * dk * 4 : 0);
+  const int64_t img_bytes = (int64_t)tile * kp * 2 + (is_cols ? (int64_t)tile * 4 : 0);
   unsigned char* img = out + t * img_bytes;
-  float* f32blk = (is_cols && with_f32) ? reinterpret_cast<float*>(img + (int64_t)tile * kp * 2 + (int64_t)tile * 4)
-                                        : nullptr;
   const bool live = p < n;
   float sq = 0.f;
   for (int kc = 0; kc < dk / 8; ++kc) {
@@ -85,7 +80,6 @@ static __global__ void tc_pack_kernel(const float* __restrict__ pts, const float
       float X = 0.f;
       if (live && d < D) X = scale * (pts[p * D + d] - (center ? center[d] : 0.f));
       sq = fmaf(X, X, sq);
-      if (f32blk) f32blk[(int64_t)pt * dk + d] = X;
       const __nv_bfloat16 h = __float2bfloat16_rn(X);
       const float r1 = X - __bfloat162float(h);
       const __nv_bfloat16 m = __float2bfloat16_rn(r1);
@@ -155,22 +149,17 @@ struct TcCfg {
 // MODE 0: gaussian kernel conv  part[(split*NH + half)*N + row]   = sum_j w_j 2^S_ij
 // MODE 1: softmin               part2[(split*NH + half)*N + row]  = (m, s) with sum_j 2^S_ij = s 2^m  (lazy max,
 //         sum-guarded exactly like softmin.cuh; same partial format as softmin_partial_kernel)
-// MODE 2: gaussian row gradient part[((split*NH+half)*N + row)*(D+1) + {0, 1+k}] = sum_j w_j e_ij {1, Y_jk}
-// MODE 3: softmin row gradient  same layout with the softmax weights 2^(S_ij - lse2_i) (lse2 rides in the row
-//         operand's rank-one chunk).  In modes 2/3 the exponent still comes from the tensor cores; the
-//         D-wide weighted sums run on the CUDA cores (64 FFMA per pair at D = 64: FMA-pipe bound).
+// (row gradients — modes 2 and 3 — are a two-GEMM kernel of their own: tcbwd.cuh)
 template <class C, int MODE>
 __global__ void __launch_bounds__(C::THREADS, 1)
     tc_reduce_kernel(const unsigned char* __restrict__ a_imgs, const unsigned char* __restrict__ b_imgs,
                      float* __restrict__ part, int64_t N, int kp, int ntiles_b, int tiles_per_split, int NSTAGE,
                      int D) {
   constexpr int BN = C::BN, NEPI = C::NEPI, NACC = C::NACC;
-  constexpr bool BWD = (MODE >= 2);  // modes 2/3 also accumulate sum_j w_ij Y_j on the CUDA cores
-  constexpr int DKMAX = 64;
+  static_assert(MODE == 0 || MODE == 1, "row gradients live in tcbwd.cuh");
   extern __shared__ __align__(1024) unsigned char smem[];
   const int a_bytes = kTcM * kp * 2;
-  const int dk = (kp - 16) / 3;
-  const int b_bytes = BN * kp * 2 + BN * 4 + (BWD ? BN * dk * 4 : 0);
+  const int b_bytes = BN * kp * 2 + BN * 4;
   unsigned char* sb = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * b_bytes);
   uint64_t* bar_a = bars;
@@ -271,11 +260,6 @@ __global__ void __launch_bounds__(C::THREADS, 1)
     }
     float acc0 = 0.f, acc1 = 0.f;      // MODE 0: weighted sums
     float m = kNegBig, srun = 0.f;     // MODE 1: running (m, s)
-    float gacc[BWD ? DKMAX : 1];       // MODE 2/3: sum_j w_ij Y_jk
-    if constexpr (BWD) {
-#pragma unroll
-      for (int k2 = 0; k2 < DKMAX; ++k2) gacc[k2] = 0.f;
-    }
     for (int k = 0; k < nt; ++k) {
       const int st = k % NSTAGE, acc = k % NACC;
       mbar_wait(&tmem_full[acc], (k / NACC) & 1);
@@ -286,26 +270,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
       for (int c0 = 0; c0 < CW; c0 += 32) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * CW + c0, v);
-        if constexpr (BWD) {
-          const float* yf = wts + BN + (half * CW + c0) * dk;  // fp32 coordinates of these 32 columns
-#pragma unroll 4
-          for (int c = 0; c < 32; ++c) {
-            float w = ex2_approx(v[c]);
-            if constexpr (MODE == 2) w *= wts[half * CW + c0 + c];
-            ts0 += w;
-            const float4* y4 = reinterpret_cast<const float4*>(yf + c * dk);
-#pragma unroll
-            for (int k4 = 0; k4 < DKMAX / 4; ++k4) {
-              if (k4 * 4 < dk) {
-                const float4 yv = y4[k4];
-                gacc[4 * k4 + 0] = fmaf(w, yv.x, gacc[4 * k4 + 0]);
-                gacc[4 * k4 + 1] = fmaf(w, yv.y, gacc[4 * k4 + 1]);
-                gacc[4 * k4 + 2] = fmaf(w, yv.z, gacc[4 * k4 + 2]);
-                gacc[4 * k4 + 3] = fmaf(w, yv.w, gacc[4 * k4 + 3]);
-              }
-            }
-          }
-        } else if constexpr (MODE == 0) {
+        if constexpr (MODE == 0) {
           const float4* w4 = reinterpret_cast<const float4*>(wts + half * CW + c0);
 #pragma unroll
           for (int c = 0; c < 32; c += 4) {
@@ -344,7 +309,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
           ts1 += cs1;
         }
       }
-      if constexpr (MODE == 0 || BWD) {
+      if constexpr (MODE == 0) {
         acc0 += ts0;
         acc1 += ts1;
       } else {
@@ -358,13 +323,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
       }
     }
     if (row < N) {
-      if constexpr (BWD) {
-        float* dst = part + (((int64_t)split * NH + half) * N + row) * (D + 1);
-        dst[0] = acc0 + acc1;
-#pragma unroll
-        for (int k2 = 0; k2 < DKMAX; ++k2)
-          if (k2 < D) dst[1 + k2] = gacc[k2];
-      } else if constexpr (MODE == 0) {
+      if constexpr (MODE == 0) {
         part[((int64_t)split * NH + half) * N + row] = acc0 + acc1;
       } else {
         reinterpret_cast<float2*>(part)[((int64_t)split * NH + half) * N + row] = make_float2(m, srun);

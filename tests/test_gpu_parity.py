@@ -201,7 +201,7 @@ def test_softmin_tensor_core_path(shape):
     Fr, Gr = O.samples_loss(x.double(), y.double(), loss="sinkhorn", p=2, blur=0.5, scaling=0.6, potentials=True)
     assert (F.cpu().double() - Fr).abs().max() < 2e-5 * max(1.0, Fr.abs().max().item())
     assert (G.cpu().double() - Gr).abs().max() < 2e-5 * max(1.0, Gr.abs().max().item())
-    # row gradients: exponent from the tensor cores, D-wide weighted sums on the CUDA cores
+    # row gradients: two chained tcgen05 GEMMs (S = X.Y^T -> P = 2^S in TMEM -> G = P.Y), csrc/tcbwd.cuh
     go = torch.randn(n, generator=g)
     for eps in (2.0, 0.3):
         ref = O.softmin_grad_rows(eps, x.double(), y.double(), h.double(), go.double(), p=2).numpy()
