@@ -10,6 +10,8 @@ C ABI: ``include/b200ot.h`` (``geomloss_b200/libb200ot.so``, built by ``__graft_
 """
 from .samples_loss import SamplesLoss  # noqa: F401
 from .sinkhorn_images import sinkhorn_divergence  # noqa: F401  (the reference exports the IMAGE routine here)
+from . import ot  # noqa: F401  (geomloss.ot.solve_sample facade)
+from .barycenter_images import ImagesBarycenter  # noqa: F401
 
 __version__ = "0.1.0"
-__all__ = ["SamplesLoss", "sinkhorn_divergence"]
+__all__ = ["SamplesLoss", "ImagesBarycenter", "sinkhorn_divergence", "ot"]

@@ -491,3 +491,137 @@ def sinkhorn_multiscale_dense(a, x, b, y, p=2, blur=0.05, reach=None, diameter=N
     out = sinkhorn_value(eps_final, rho, a[None], b[None], f_aa[None], g_bb[None], g_ab[None], f_ba[None],
                          debias=debias, potentials=potentials)
     return (out[0][0], out[1][0]) if potentials else out[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# geomloss.ot.solve_sample (new API)           ot/_implementations/sample.py:190-395 (driver),
+#     :91-182 (softmin_sample), ot/_abstract_solvers/sinkhorn_ot.py:17-29 (eps = inf initialisation),
+#     :240-447 (loop), annealing.py:46-226 (eps ladder), unbalanced_ot.py:12-185 (dampening, value),
+#     ot/_ot_result.py:275-410 + sample.py:511-620 (result attributes)
+# PARITY PINNED: tests/golden/ot_sample_case*.npz (fp32 and fp64 runs of the reference).
+# Conventions differ from the legacy API: C = |x-y|^2 WITHOUT the 1/2, reg = eps and unbalanced = rho are
+# used as given (blur/reach map to p*blur^p, p*reach^p), the first iterate is the eps = +inf softmin (cost
+# averages) shifted by half its mean, the eps ladder is geomspace(diameter^p, reg, max_iter).
+# ------------------------------------------------------------------------------------------------
+def ot_annealing_eps(maxmin_cost, eps, n_iter):
+    """annealing.py:131-170 with scaling=None (the only form solve_sample uses)."""
+    maxmin_cost = max(float(maxmin_cost), eps)
+    if n_iter == 1:
+        return [eps]
+    return list(np.geomspace(maxmin_cost, eps, n_iter))
+
+
+def ot_softmin(eps, log_w, C, pot):
+    """sample.py:91-182 — finite eps and eps = +inf."""
+    if eps == float("inf"):
+        w = log_w.exp()
+        return ((C - pot[None, :]) * w[None, :]).sum(1) / w.sum()
+    return -eps * torch.logsumexp(log_w[None, :] + (pot[None, :] - C) / eps, dim=1)
+
+
+def ot_sinkhorn_cost(a, b, f_aa, g_bb, g_ab, f_ba, eps, rho, debias):
+    """unbalanced_ot.py:25-185 (forward values only)."""
+    if rho is None:
+        F, G = (f_ba - f_aa, g_ab - g_bb) if debias else (f_ba, g_ab)
+    elif not debias:
+        F = (rho + eps / 2 * b.sum()) - (rho + eps / 2) * torch.exp(-f_ba / rho)
+        G = (rho + eps / 2 * a.sum()) - (rho + eps / 2) * torch.exp(-g_ab / rho)
+    else:
+        F = (rho + eps / 2) * (torch.exp(-f_aa / rho) - torch.exp(-f_ba / rho))
+        G = (rho + eps / 2) * (torch.exp(-g_bb / rho) - torch.exp(-g_ab / rho))
+    return (a * F).sum() + (b * G).sum()
+
+
+def ot_solve_sample(X_a, X_b, a=None, b=None, debias=False, reg=None, unbalanced=None, max_iter=None, blur=None,
+                    reach=None):
+    """Dense CPU restatement of geomloss.ot.solve_sample(cost="sqeuclidean"); returns the result attributes."""
+    p = 2
+    if blur is not None:
+        reg = p * blur**p
+    if reach is not None:
+        unbalanced = p * reach**p
+    N, M = X_a.shape[0], X_b.shape[0]
+    a = torch.full((N,), 1.0 / N, dtype=X_a.dtype) if a is None else a
+    b = torch.full((M,), 1.0 / M, dtype=X_a.dtype) if b is None else b
+    eps_list = ot_annealing_eps(max_diameter(X_a, X_b) ** p, reg, max_iter)
+    rho = unbalanced
+
+    def cost(u, v):  # sample.py:38-66: expansion, no 1/2
+        return (u * u).sum(-1)[:, None] - 2 * u @ v.t() + (v * v).sum(-1)[None, :]
+
+    C_xy, C_yx = cost(X_a, X_b), cost(X_b, X_a)
+    C_xx, C_yy = (cost(X_a, X_a), cost(X_b, X_b)) if debias else (None, None)
+    log_a, log_b = log_weights(a), log_weights(b)
+
+    def damp(eps):
+        return 1.0 if rho is None else 1.0 / (1.0 + eps / rho)
+
+    def init(lw_self, lw_other, C):  # sinkhorn_ot.py:17-29
+        f = ot_softmin(float("inf"), lw_other, C, 0 * lw_other)
+        # quirk kept: on un-batched (N,) vectors bk.dot_products treats N as the batch axis, so the "constant
+        # offset" is the per-point 0.5 * a_i * f_i, not half the mean of f (torch.py:28-32, sinkhorn_ot.py:24-27)
+        return lam * (f - 0.5 * lw_self.exp() * f)
+
+    lam = damp(eps_list[0])
+    f_ba, g_ab = init(log_a, log_b, C_xy), init(log_b, log_a, C_yx)
+    if debias:
+        f_aa, g_bb = init(log_a, log_a, C_xx), init(log_b, log_b, C_yy)
+    for eps in eps_list:
+        lam = damp(eps)
+        ft_ba, gt_ab = lam * ot_softmin(eps, log_b, C_xy, g_ab), lam * ot_softmin(eps, log_a, C_yx, f_ba)
+        if debias:
+            ft_aa, gt_bb = lam * ot_softmin(eps, log_a, C_xx, f_aa), lam * ot_softmin(eps, log_b, C_yy, g_bb)
+            f_aa, g_bb = 0.5 * (f_aa + ft_aa), 0.5 * (g_bb + gt_bb)
+        f_ba, g_ab = 0.5 * (f_ba + ft_ba), 0.5 * (g_ab + gt_ab)
+    f_ba, g_ab = lam * ot_softmin(eps, log_b, C_xy, g_ab), lam * ot_softmin(eps, log_a, C_yx, f_ba)
+    if debias:
+        f_aa, g_bb = lam * ot_softmin(eps, log_a, C_xx, f_aa), lam * ot_softmin(eps, log_b, C_yy, g_bb)
+    else:
+        f_aa = g_bb = None
+    density = torch.exp((f_ba[:, None] + g_ab[None, :] - C_xy) / reg)  # sample.py:511-561
+    out = dict(value=ot_sinkhorn_cost(a, b, f_aa, g_bb, g_ab, f_ba, reg, rho, debias), potential_a=f_ba,
+               potential_b=g_ab, marginal_a=a * (density @ b), marginal_b=b * (density.t() @ a),
+               plan=density * a[:, None] * b[None, :])
+    if debias:
+        out.update(potential_aa=f_aa, potential_bb=g_bb)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# ImagesBarycenter                          _legacy/wasserstein_barycenter_images.py:6-93
+# PARITY UNPINNED (the reference's softmin_grid needs pykeops); dense torch, differentiable end to end, so the
+# tests can check the CUDA path's closed-form softmin_grid backward against plain autograd.
+# ------------------------------------------------------------------------------------------------
+def images_barycenter(measures, weights, blur=0, p=2, scaling_N=10, backward_iterations=5):
+    sm = softmin_grid_dense
+    if blur == 0:
+        blur = 1 / measures.shape[-1]
+    w = weights[:, :, None, None]
+
+    def step(f, g, d, eps, a_log):
+        bar = d - (sm(eps, p, a_log + g / eps) / eps * w).sum(1, keepdim=True)
+        f_new = 0.5 * (f + sm(eps, p, a_log + g / eps))
+        g_new = 0.5 * (g + sm(eps, p, bar + f / eps))
+        bar = d - (sm(eps, p, a_log + g_new / eps) / eps * w).sum(1, keepdim=True)
+        d_new = 0.5 * (d + bar + sm(eps, p, d) / eps)
+        return f_new, g_new, d_new, bar
+
+    with torch.set_grad_enabled(torch.is_grad_enabled() and backward_iterations == 0):
+        levels = [grid_log_dens(t) for t in grid_pyramid(measures)[1:]]
+        sigma = 1.0
+        eps = sigma**p
+        f = sm(eps, p, levels[0])
+        g = sm(eps, p, levels[0])
+        d = torch.ones_like(levels[0]).sum(dim=1, keepdim=True)
+        d = d - d.logsumexp([2, 3], keepdim=True)
+        for n, a_log in enumerate(levels):
+            for _ in range(scaling_N):
+                eps = sigma**p
+                f, g, d, bar = step(f, g, d, eps, a_log)
+                sigma = max(sigma * 2 ** (-1 / scaling_N), blur)
+            if n + 1 < len(levels):
+                f, g, d = grid_upsample(f), grid_upsample(g), grid_upsample(d)
+    if (measures.requires_grad or weights.requires_grad) and backward_iterations > 0:
+        for _ in range(backward_iterations):
+            f, g, d, bar = step(f, g, d, eps, a_log)
+    return bar.exp()

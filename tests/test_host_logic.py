@@ -115,3 +115,57 @@ def test_product_never_touches_the_oracle_or_a_cpu_fallback():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), f
                 assert "geomloss_oracle" not in text, f
+
+
+# ------------------------------------------------------------------------------------------------
+# geomloss.ot.solve_sample facade: argument handling (reference: sample.py:283-345, _arguments.py:14-154)
+# ------------------------------------------------------------------------------------------------
+def test_ot_solve_sample_argument_errors():
+    from geomloss_b200 import ot
+
+    x, y = torch.rand(5, 3), torch.rand(7, 3)
+    with pytest.raises(ValueError, match="redundant"):
+        ot.solve_sample(x, y, reg=0.1, blur=0.1, max_iter=3)
+    with pytest.raises(ValueError, match="redundant"):
+        ot.solve_sample(x, y, reg=0.1, unbalanced=1.0, reach=0.1, max_iter=3)
+    with pytest.raises(ValueError, match="max_iter"):
+        ot.solve_sample(x, y, reg=0.1)
+    with pytest.raises(NotImplementedError):
+        ot.solve_sample(x, y, reg=0.0, max_iter=3)
+    with pytest.raises(ValueError):
+        ot.solve_sample(x, y, reg=-1.0, max_iter=3)
+    with pytest.raises(ValueError):
+        ot.solve_sample(x, y, reg=0.1, unbalanced=-2.0, max_iter=3)
+    with pytest.raises(NotImplementedError):
+        ot.solve_sample(x, y, reg=0.1, max_iter=3, tol=1e-3)
+    with pytest.raises(NotImplementedError):
+        ot.solve_sample(x, y, reg=0.1, max_iter=3, method="symmetric")
+    with pytest.raises(NotImplementedError):
+        ot.solve_sample(x, y, reg=0.1, max_iter=3, unbalanced=1.0, unbalanced_type="TV")
+    with pytest.raises(ValueError, match="same number of coordinates"):
+        ot.solve_sample(x, torch.rand(7, 2), reg=0.1, max_iter=3)
+    with pytest.raises(ValueError, match="X_a"):
+        ot.solve_sample(torch.rand(2, 5, 3), y, reg=0.1, max_iter=3)
+    with pytest.raises(ValueError, match="negative"):
+        ot.solve_sample(x, y, a=-torch.ones(5), reg=0.1, max_iter=3)
+    with pytest.raises(ValueError, match="shape"):
+        ot.solve_sample(x, y, a=torch.ones(6), reg=0.1, max_iter=3)
+    with pytest.raises(ValueError, match="do not sum up"):
+        ot.solve_sample(x, y, a=torch.ones(5), b=torch.ones(7), reg=0.1, max_iter=3)
+    with pytest.raises(NotImplementedError):
+        ot.solve_sample_batch(x[None], y[None], reg=0.1, max_iter=3)
+    # the product has no CPU path: valid arguments on CPU tensors must fail loudly, not fall back
+    with pytest.raises(Exception):
+        ot.solve_sample(x, y, reg=0.1, max_iter=3)
+
+
+def test_ot_annealing_ladder():
+    from geomloss_b200.ot import annealing_eps
+
+    assert annealing_eps(3.0, 0.01, 1) == [0.01]
+    lad = annealing_eps(3.0, 0.01, 5)
+    assert len(lad) == 5 and abs(lad[0] - 3.0) < 1e-12 and abs(lad[-1] - 0.01) < 1e-12
+    assert all(abs(lad[i + 1] / lad[i] - lad[1] / lad[0]) < 1e-9 for i in range(3))
+    assert annealing_eps(0.5, 2.0, 3) == [2.0, 2.0, 2.0]  # reg above the squared diameter: constant ladder
+    with pytest.raises(ValueError):
+        annealing_eps(3.0, 0.01, 0)

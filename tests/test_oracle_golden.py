@@ -157,3 +157,29 @@ def test_grid_pyramid_and_schedule():
     v = O.sinkhorn_images(a.double(), a.double().flip(-1), blur=1 / 16)
     assert v.shape == (2,) and (v > 0).all()
     assert torch.allclose(O.sinkhorn_images(a.double(), a.double()), torch.zeros(2, dtype=torch.float64), atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------
+# geomloss.ot.solve_sample (new API) — oracle restatement vs the reference's fp32 / fp64 runs
+# ------------------------------------------------------------------------------------------------
+def _ot_case(name, dtype):
+    z = load_golden(name)
+    kw = {k[3:]: float(z[k]) for k in z if k.startswith("kw_")}
+    if "max_iter" in kw:
+        kw["max_iter"] = int(kw["max_iter"])
+    if "debias" in kw:
+        kw["debias"] = bool(kw["debias"])
+    t = lambda k: torch.from_numpy(z[k]).to(dtype)  # noqa: E731
+    args = dict(X_a=t("X_a"), X_b=t("X_b"), a=t("a") if "a" in z else None, b=t("b") if "b" in z else None)
+    return z, args, kw
+
+
+@pytest.mark.parametrize("idx", range(8))
+def test_oracle_ot_solve_sample_matches_reference(idx):
+    for dtype, suffix, tol in ((torch.float64, "_f64", 1e-9), (torch.float32, "", 2e-4)):
+        z, args, kw = _ot_case(f"ot_sample_case{idx:02d}", dtype)
+        out = O.ot_solve_sample(**args, **kw)
+        for name, val in out.items():
+            ref = z[name + suffix]
+            scale = max(1.0, float(np.abs(ref).max()))
+            np.testing.assert_allclose(val.numpy(), ref, atol=tol * scale, err_msg=f"{name}{suffix} case {idx}")
