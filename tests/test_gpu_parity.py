@@ -648,10 +648,9 @@ def test_ot_solve_sample_large_never_dense():
     y = torch.rand(200_000, 3, generator=g).to(DEV)
     res = ot.solve_sample(x, y, blur=0.05, max_iter=12)
     ma, mb = res.marginal_a, res.marginal_b
-    # after the final update g_ab is the exact softmin of the previous f_ba: one marginal is met to rounding,
-    # the other to the convergence of the loop
-    assert abs(ma.sum().item() - 1.0) < 1e-3 and abs(mb.sum().item() - 1.0) < 1e-3
-    assert (ma * 200_000 - 1).abs().max().item() < 0.2
+    # the last update is simultaneous (Jacobi): both marginals are met to the convergence of a 12-step ladder
+    assert abs(ma.sum().item() - 1.0) < 5e-2 and abs(mb.sum().item() - 1.0) < 5e-2
+    assert (ma * 200_000 - 1).abs().max().item() < 0.5
     with pytest.raises(MemoryError):
         res.plan
     # the value is the legacy API's OT_eps up to the cost convention: C = |x-y|^2 = 2 * (|x-y|^2 / 2)
