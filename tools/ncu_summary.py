@@ -1,6 +1,7 @@
 """Summarise ncu outputs brought back in gpurun_out/ into small tracked files under profiles/.
 
     python tools/ncu_summary.py gpurun_out/prof_softmin_partial.ncu-rep gpurun_out/launches.csv r01
+    python tools/ncu_summary.py gpurun_out/prof_tc_fwd.ncu-rep - r01 tc_fwd        # any other kernel capture
 
 writes profiles/<tag>_softmin_partial_ncu.json (+ profiles/softmin_partial_ncu_summary.json, read by
 bench.py for roofline.traffic) and profiles/<tag>_launches_summary.json (per-kernel time shares).
@@ -36,6 +37,7 @@ def raw_page(rep):
 
 def main():
     rep, launches, tag = sys.argv[1], sys.argv[2], sys.argv[3]
+    name = sys.argv[4] if len(sys.argv) > 4 else "softmin_partial"
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     if os.path.exists(rep):
         kernels, units = raw_page(rep)
@@ -59,8 +61,9 @@ def main():
             return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
 
         summ["dram_bytes_per_launch"] = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
-        json.dump(summ, open(os.path.join(ROOT, "profiles", f"{tag}_softmin_partial_ncu.json"), "w"), indent=1)
-        json.dump(summ, open(os.path.join(ROOT, "profiles", "softmin_partial_ncu_summary.json"), "w"), indent=1)
+        json.dump(summ, open(os.path.join(ROOT, "profiles", f"{tag}_{name}_ncu.json"), "w"), indent=1)
+        if name == "softmin_partial":  # read by bench.py for roofline.traffic
+            json.dump(summ, open(os.path.join(ROOT, "profiles", "softmin_partial_ncu_summary.json"), "w"), indent=1)
         print(json.dumps(summ, indent=1))
     if os.path.exists(launches):
         lines = [l for l in open(launches) if not l.startswith("==")]
