@@ -58,10 +58,11 @@ __global__ void conv_fwd_finalize_kernel(const float* __restrict__ part, int n_s
 __global__ void conv_bwd_finalize_kernel(const float* __restrict__ part, int n_split, const float* __restrict__ x,
                                          const float* __restrict__ center, const float* __restrict__ grad_out,
                                          float* __restrict__ grad_x, int64_t N, int D, int kind, float scale,
-                                         float coef) {
+                                         float coef, const float* __restrict__ w_absmax) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  const float go = grad_out[i];
+  float go = grad_out[i];
+  if (w_absmax != nullptr && *w_absmax > 0.f) go *= *w_absmax;  // tensor-core path: weights were normalised
   if (kind == B200OT_KERNEL_GAUSSIAN) {
     const int na = D + 1;
     float a0 = 0.f;
@@ -80,6 +81,16 @@ __global__ void conv_bwd_finalize_kernel(const float* __restrict__ part, int n_s
       grad_x[i * D + k] = go * coef * a;
     }
   }
+}
+
+// max_j |w_j| into *out (zero-initialised by the caller); bit order of non-negative floats = integer order
+__global__ void absmax_kernel(const float* __restrict__ w, int64_t n, float* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f && !(m != m)) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
 }
 
 template <int MODE, int D>
@@ -134,7 +145,7 @@ using TcConvCfg = TcCfg<kTcBN, kTcEpi>;
 struct TcPlan {
   int kp, nstage, n_split, tiles_per_split;
   int64_t a_tiles, b_tiles, a_bytes, b_bytes, smem;
-  int64_t off_b, off_part, total;
+  int64_t off_b, off_part, off_misc, total;
 };
 
 bool tc_supported_dim(int D) { return D > B200OT_MAX_D && D <= 64; }
@@ -160,7 +171,8 @@ static TcPlan make_tc_plan(int64_t N, int64_t M, int D, bool bwd = false) {
   p.off_b = round_up64(p.a_tiles * p.a_bytes, 256);
   p.off_part = p.off_b + round_up64(p.b_tiles * p.b_bytes, 256);
   // partials: (m, s) pairs forward, D+1 sums per row backward
-  p.total = p.off_part + round_up64((int64_t)p.n_split * (kTcEpi / 4) * N * 4 * (bwd ? D + 1 : 2), 256);
+  p.off_misc = p.off_part + round_up64((int64_t)p.n_split * (kTcEpi / 4) * N * 4 * (bwd ? D + 1 : 2), 256);
+  p.total = p.off_misc + 256;  // [0]: max|w| of the row-gradient pass
   return p;
 }
 
@@ -170,19 +182,28 @@ int64_t tc_scratch_bytes(int64_t N, int64_t M, int D) { return make_tc_plan(N, M
 // (N, D+1) partial sums in *part_out.
 int bwd_partial_tc(int kind, const float* x, const float* y, const float* w, const float* h_a, const float* h_b,
                    float h_scale_b, const float* lse2, const float* center, float scale, int64_t N, int64_t M, int D,
-                   void* scratch, float** part_out, int* n_part_out, cudaStream_t st) {
+                   void* scratch, float** part_out, int* n_part_out, cudaStream_t st, const float** w_absmax_out) {
   const TcPlan p = make_tc_plan(N, M, D, true);
   if (p.nstage < 1) return B200OT_EINVAL;
   unsigned char* base = reinterpret_cast<unsigned char*>(scratch);
   unsigned char* a_imgs = base;
   unsigned char* b_imgs = base + p.off_b;
   float* part = reinterpret_cast<float*>(base + p.off_part);
+  float* w_absmax = nullptr;
+  if (w != nullptr) {
+    // P = w_j e_ij feeds an fp16 GEMM: normalise the weights to max|w| = 1 (undone by the finalize kernel)
+    w_absmax = reinterpret_cast<float*>(base + p.off_misc);
+    B200OT_CUDA_TRY(cudaMemsetAsync(w_absmax, 0, sizeof(float), st));
+    absmax_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(M, 256), 1024), 256, 0, st>>>(w, M, w_absmax);
+    B200OT_CUDA_TRY(cudaGetLastError());
+  }
+  if (w_absmax_out) *w_absmax_out = w_absmax;
   const int threads = 128;
   tc_pack_kernel<<<(unsigned)ceil_div64(p.a_tiles * kTcM, threads), threads, 0, st>>>(
-      x, nullptr, nullptr, nullptr, 0.f, 0.f, center, scale, N, D, p.kp, kTcM, 0, a_imgs, lse2);
+      x, nullptr, nullptr, nullptr, 0.f, 0.f, center, scale, N, D, p.kp, kTcM, 0, a_imgs, lse2, nullptr);
   B200OT_CUDA_TRY(cudaGetLastError());
   tc_pack_kernel<<<(unsigned)ceil_div64(p.b_tiles * kTcBN, threads), threads, 0, st>>>(
-      y, w, h_a, h_b, h_scale_b, kLog2e, center, scale, M, D, p.kp, kTcBN, 1, b_imgs, nullptr);
+      y, w, h_a, h_b, h_scale_b, kLog2e, center, scale, M, D, p.kp, kTcBN, 1, b_imgs, nullptr, w_absmax);
   B200OT_CUDA_TRY(cudaGetLastError());
   dim3 grid((unsigned)p.a_tiles, (unsigned)p.n_split);
   if (kind == 0) {
@@ -323,11 +344,12 @@ B200OT_API int b200ot_kernel_conv_bwd_x(const float* x, const float* y, const fl
     float* tc_part = nullptr;
     int n_part = 0;
     const float scale = sqrtf(kLog2e) / blur;
+    const float* w_absmax = nullptr;
     const int rc = bwd_partial_tc(0, x, y, w, nullptr, nullptr, 0.f, nullptr, center, scale, N, M, D, scratch,
-                                  &tc_part, &n_part, (cudaStream_t)stream);
+                                  &tc_part, &n_part, (cudaStream_t)stream, &w_absmax);
     if (rc) return rc;
     conv_bwd_finalize_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, (cudaStream_t)stream>>>(
-        tc_part, n_part, x, center, grad_out, grad_x, N, D, kind, scale, 1.0f / (scale * blur * blur));
+        tc_part, n_part, x, center, grad_out, grad_x, N, D, kind, scale, 1.0f / (scale * blur * blur), w_absmax);
     B200OT_CUDA_TRY(cudaGetLastError());
     return B200OT_OK;
   }
@@ -353,7 +375,7 @@ B200OT_API int b200ot_kernel_conv_bwd_x(const float* x, const float* y, const fl
   if (rc) return rc;
   const int threads = 256;
   conv_bwd_finalize_kernel<<<(unsigned)ceil_div64(N, threads), threads, 0, st>>>(
-      part, pl.n_split, x, center, grad_out, grad_x, N, D, kind, cs.scale, coef);
+      part, pl.n_split, x, center, grad_out, grad_x, N, D, kind, cs.scale, coef, (const float*)nullptr);
   B200OT_CUDA_TRY(cudaGetLastError());
   return B200OT_OK;
 }

@@ -176,7 +176,7 @@ B200OT_API int b200ot_softmin_bwd_x(const float* x, const float* y, const float*
     float* tc_part = nullptr;
     int n_part = 0;
     const int rc = bwd_partial_tc(1, x, y, nullptr, h_a, h_b, h_scale_b, lse2, center, softmin_coord_scale(2, eps), N, M,
-                                  D, scratch, &tc_part, &n_part, (cudaStream_t)stream);
+                                  D, scratch, &tc_part, &n_part, (cudaStream_t)stream, nullptr);
     if (rc) return rc;
     return b200ot_softmin_bwd_finalize(tc_part, n_part, x, center, grad_out, grad_x, N, D, p, eps, stream);
   }

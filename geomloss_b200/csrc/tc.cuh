@@ -38,6 +38,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// fp16 x fp16 -> fp32 (operand format code 0), both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) /* D = f32 */ | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // ---- MMA issue (one thread) + completion signal ----
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           bool accumulate) {

@@ -1,8 +1,8 @@
 // b200ot — row gradients on the tensor cores, 8 < D <= 64: TWO chained GEMMs per column tile, FlashAttention
 // style, both on tcgen05 with every intermediate in TMEM.
 //
-//   S_ij = X_i.Y_j - |X_i|^2/2 - |Y_j|^2/2 (+ H_j - lse2_i)          GEMM 1 (as in tcconv.cuh: bf16x3 split
-//                                                                    operands, six cross products, rank-one chunk)
+//   S_ij = X_i.Y_j - |X_i|^2/2 - |Y_j|^2/2 (+ H_j - lse2_i)          GEMM 1 (as in tcconv.cuh: fp16x2 split
+//                                                                    operands, three cross products, rank-one chunk)
 //   P_ij = 2^S_ij (* w_j)                                            epilogue warps: tcgen05.ld -> MUFU.EX2
 //   G_ik = sum_j P_ij Y_jk                                           GEMM 2: A = P (TMEM), B = the SAME column
 //                                                                    image read MN-major (K = column index)
@@ -12,11 +12,12 @@
 //   gaussian:  d/dx_i = go_i * sum_j k_ij w_j (y_j - x_i) / blur^2 ;  softmin: d/dx_i = go_i * (x_i - sum_j p_ij y_j)
 // i.e. per row the D+1 sums {sum_j P_ij, sum_j P_ij Y_jk}; the finalize kernels turn them into gradients.
 //
-// * P is written back IN PLACE over the S accumulator it was computed from (fp32 S -> bf16 hi | bf16 lo of P:
+// * P is written back IN PLACE over the S accumulator it was computed from (fp32 S -> fp16 hi | fp16 lo of P:
 //   a 32-column chunk of S becomes 16 columns of hi and 16 columns of lo), so TMEM holds: two S/P buffers
-//   (2 x 128 columns), the row operand X (<= 104), and G (dk <= 64 columns, lives for the whole CTA).
-// * P = hi + lo (2 bf16 terms), Y = h + m (the image's first two split terms): G = hi.h + hi.m + lo.h, error
-//   ~2^-17 |P||Y|.
+//   (2 x 128 columns), the row operand X (<= 72), and G (dk <= 64 columns, lives for the whole CTA).
+// * P = hi + lo (2 fp16 terms; |P| <= 1: softmax weights, or kernel values times weights normalised to
+//   max|w| = 1 by the pack kernel), Y = h + l (the image's two terms): G = hi.h + hi.l + lo.h, error
+//   ~2^-22 |P||Y| (+ 6e-8 absolute where P falls into fp16's subnormal range).
 // * The column image of tcconv.cuh ([kgroup][column][8 bf16], K-major for GEMM 1) is, read with k = column,
 //   exactly the canonical MN-major no-swizzle layout (core matrix = 8 columns x 16 B of one 8-dim group), so
 //   GEMM 2 needs no second copy of Y: only a descriptor with b_major = MN, LBO = 128 B (next 8 columns),
@@ -38,17 +39,18 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
-// (lo, hi) fp32 -> packed bf16x2, round to nearest even; element `lo` in bits 0..15
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+// (lo, hi) fp32 -> packed f16x2, round to nearest even; element `lo` in bits 0..15
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
-
-// bf16 x bf16 -> fp32, A K-major (TMEM), B MN-major
-__host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(int M, int N) {
-  return make_idesc_bf16(M, N) | (1u << 16);
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
 }
+
+// fp16 x fp16 -> fp32, A K-major (TMEM), B MN-major
+__host__ __device__ constexpr uint32_t make_idesc_f16_bmn(int M, int N) { return make_idesc_f16(M, N) | (1u << 16); }
 
 // MODE 2: gaussian row gradient (P = w_j 2^S), MODE 3: softmin row gradient (P = 2^(S - lse2_i): lse2 rides in the
 // row operand's rank-one chunk).  part[(split*N + row)*(D+1) + {0, 1+k}] = sum_j P_ij {1, Y_jk}
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
   constexpr int G_COL0 = 384;         // gradient accumulator (dk <= 64 columns)
   extern __shared__ __align__(1024) unsigned char smem[];
   const int a_bytes = kTcM * kp * 2;
-  const int dk = (kp - 16) / 3;
+  const int dk = tc_dk_of_kp(kp);
   const int b_bytes = BN * kp * 2 + BN * 4;
   unsigned char* sb = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * b_bytes);
@@ -114,8 +116,8 @@ __global__ void __launch_bounds__(C::THREADS, 1)
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_bf16(kTcM, BN);
-      const uint32_t idesc_g = make_idesc_bf16_bmn(kTcM, dk);
+      const uint32_t idesc_s = make_idesc_f16(kTcM, BN), idesc_r1 = make_idesc_bf16(kTcM, BN);
+      const uint32_t idesc_g = make_idesc_f16_bmn(kTcM, dk);
       const int seg = dk / 8;  // 8-element chunks per split term
       const uint32_t a_tmem = tmem_base + A_COL0, g_tmem = tmem_base + G_COL0;
       mbar_wait(bar_a, 0);
@@ -129,12 +131,12 @@ __global__ void __launch_bounds__(C::THREADS, 1)
           const uint32_t b_addr = smem_u32(sb + st * b_bytes);
           const uint32_t d_addr = tmem_base + acc * BN;
           {
-            const uint64_t db = make_smem_desc(b_addr + 3 * seg * (BN * 16), BN * 16, 128);
-            umma_bf16_ts(d_addr, a_tmem + 3 * seg * 4, db, idesc_s, false);
+            const uint64_t db = make_smem_desc(b_addr + kTcTerms * seg * (BN * 16), BN * 16, 128);
+            umma_bf16_ts(d_addr, a_tmem + kTcTerms * seg * 4, db, idesc_r1, false);
           }
 #pragma unroll
-          for (int prod = 0; prod < 6; ++prod) {
-            const int ta = (0x210100 >> (4 * prod)) & 0xF, tb = (0x012010 >> (4 * prod)) & 0xF;
+          for (int prod = 0; prod < 3; ++prod) {
+            const int ta = (prod == 2) ? 1 : 0, tb = (prod == 1) ? 1 : 0;  // hh, hl, lh
             for (int kk = 0; kk < seg / 2; ++kk) {
               const uint64_t db = make_smem_desc(b_addr + (tb * seg + 2 * kk) * (BN * 16), BN * 16, 128);
               umma_bf16_ts(d_addr, a_tmem + (ta * seg + 2 * kk) * 4, db, idesc_s, true);
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
           const uint32_t p_tmem = tmem_base + acc * BN;
 #pragma unroll
           for (int prod = 0; prod < 3; ++prod) {
-            // (P term, Y term): hi.h, hi.m, lo.h
+            // (P term, Y term): hi.h, hi.l, lo.h
             const int tp = (prod == 2) ? 1 : 0, ty = (prod == 1) ? 1 : 0;
 #pragma unroll
             for (int kk = 0; kk < BN / 16; ++kk) {
@@ -208,9 +210,10 @@ __global__ void __launch_bounds__(C::THREADS, 1)
           }
           sum0 += p0;
           sum1 += p1;
-          const uint32_t h = pack_bf16x2(p0, p1);
+          const uint32_t h = pack_f16x2(p0, p1);
+          const float2 hf = unpack_f16x2(h);
           ph[c / 2] = h;
-          pl[c / 2] = pack_bf16x2(p0 - __uint_as_float(h << 16), p1 - __uint_as_float(h & 0xFFFF0000u));
+          pl[c / 2] = pack_f16x2(p0 - hf.x, p1 - hf.y);
         }
         tmem_st16(lane_base + acc * BN + col0, ph);
         tmem_st16(lane_base + acc * BN + col0 + 16, pl);

@@ -5,12 +5,15 @@
 // (src/geomloss/_legacy/kernel_samples.py:62-68, :116-137).
 //
 // The whole exponent is produced by tcgen05.mma into TMEM:
-//   * each operand is split into three bf16 terms X = h + m + l and stored ONCE as [h | m | l] along K;
-//     the six cross products that matter (hh, hm, mh, hl, mm, lh: error ~2^-24 |X||Y|) are formed by
-//     pointing the A and B shared-memory descriptors at the matching segments — no duplicated data in
-//     shared memory or L2, 6*Dk/16 MMA instructions per tile, fp32 accumulation;
-//   * one extra 16-wide K chunk carries the rank-one terms:  A: [1,1,1, r_h,r_m,r_l, 0..],
-//     B: [c_h,c_m,c_l, 1,1,1, 0..] with r = -|X|^2/2, c = -|Y|^2/2 split in three bf16 terms,
+//   * each operand is split into TWO fp16 terms X = h + l (22 significant bits) and stored ONCE as [h | l] along
+//     K; the three cross products that matter (hh, hl, lh: error ~2^-22 |X||Y|, measured <= 3e-6 relative on the
+//     kernel value down to blur = .3 at D = 64) are formed by pointing the A and B operand addresses at the
+//     matching segments — no duplicated data in shared memory or L2, 3*Dk/16 MMA instructions per tile, fp32
+//     accumulation.  (First version: three bf16 terms and six products — twice the tensor work for accuracy the
+//     fp32 accumulation cannot use; fp16's narrow range is harmless for centred, scaled coordinates.)
+//   * one extra 16-wide K chunk, issued as a BF16 instruction (fp32 range: potentials / eps reach 1e5), carries
+//     the rank-one terms:  A: [1,1,1, r_h,r_m,r_l, 0..],  B: [c_h,c_m,c_l, 1,1,1, 0..] with r = -|X|^2/2,
+//     c = -|Y|^2/2 split in three bf16 terms,
 //   so the epilogue is  tcgen05.ld -> MUFU.EX2 -> FFMA with the column weight  and nothing else.
 //
 // Operand tiles are pre-packed in global memory by tc_pack_kernel in the exact image the UMMA descriptors
@@ -19,12 +22,13 @@
 // The ROW operand of a CTA is staged once into TMEM (tcgen05.st, lane = row, two bf16 per 32-bit column) and
 // the MMAs run in TS mode: at M = 128 an SS-mode MMA needs 128 B/clk of shared-memory reads — the whole
 // shared-memory bandwidth of the SM — and measured 1.34e12 pairs/s at D = 64; TS mode halves that and
-// reaches 1.58e12 (1.27 PFLOP/s of bf16 MMA work, profiles/r01_conv_bench.jsonl).
+// reached 1.58e12 with the six-product bf16 operands (1.27 PFLOP/s of MMA work, profiles/r01_conv_bench.jsonl).
 // CTA = TMA warp + MMA warp (one elected thread issues) + NEPI epilogue warps; smem ring of column tiles
 // with full/empty mbarriers; two accumulator buffers in TMEM so that the MMAs of tile t+1 overlap the
 // exponentials of tile t.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "tc.cuh"
@@ -34,8 +38,10 @@ namespace b200ot {
 constexpr int kTcM = 128;  // rows per CTA tile = M of the MMA
 
 __host__ __device__ inline int tc_dk(int D) { return ((D + 15) / 16) * 16; }
-// K extent of an operand image: three split terms + one 16-wide chunk of rank-one terms
-__host__ __device__ inline int tc_kp(int D) { return 3 * tc_dk(D) + 16; }
+constexpr int kTcTerms = 2;  // fp16 split terms per coordinate
+// K extent of an operand image: the split terms + one 16-wide chunk of rank-one terms
+__host__ __device__ inline int tc_kp(int D) { return kTcTerms * tc_dk(D) + 16; }
+__host__ __device__ inline int tc_dk_of_kp(int kp) { return (kp - 16) / kTcTerms; }
 __host__ __device__ inline int64_t tc_a_img_bytes(int kp) { return (int64_t)kTcM * kp * 2; }
 // column image: bf16 operand data | fp32 weights
 __host__ __device__ inline int64_t tc_b_img_bytes(int kp, int bn) { return (int64_t)bn * kp * 2 + (int64_t)bn * 4; }
@@ -43,12 +49,12 @@ __host__ __device__ inline int64_t tc_b_img_bytes(int kp, int bn) { return (int6
 // ---------------------------------------------------------------------------------------------------
 // pack: one thread per (padded) point; writes its 16-byte piece of every K chunk of its tile image
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 pack8_bf16(const __nv_bfloat16* src) {
+__device__ __forceinline__ uint4 pack8_f16(const __half* src) {
   uint4 v;
-  v.x = (uint32_t)__bfloat16_as_ushort(src[0]) | ((uint32_t)__bfloat16_as_ushort(src[1]) << 16);
-  v.y = (uint32_t)__bfloat16_as_ushort(src[2]) | ((uint32_t)__bfloat16_as_ushort(src[3]) << 16);
-  v.z = (uint32_t)__bfloat16_as_ushort(src[4]) | ((uint32_t)__bfloat16_as_ushort(src[5]) << 16);
-  v.w = (uint32_t)__bfloat16_as_ushort(src[6]) | ((uint32_t)__bfloat16_as_ushort(src[7]) << 16);
+  v.x = (uint32_t)__half_as_ushort(src[0]) | ((uint32_t)__half_as_ushort(src[1]) << 16);
+  v.y = (uint32_t)__half_as_ushort(src[2]) | ((uint32_t)__half_as_ushort(src[3]) << 16);
+  v.z = (uint32_t)__half_as_ushort(src[4]) | ((uint32_t)__half_as_ushort(src[5]) << 16);
+  v.w = (uint32_t)__half_as_ushort(src[6]) | ((uint32_t)__half_as_ushort(src[7]) << 16);
   return v;
 }
 
@@ -61,7 +67,8 @@ static __global__ void tc_pack_kernel(const float* __restrict__ pts, const float
                                       float h_scale_b, float h_scale, const float* __restrict__ center,
                                       float scale, int64_t n, int D, int kp, int tile, int is_cols,
                                       unsigned char* __restrict__ out,
-                                      const float* __restrict__ row_extra = nullptr) {
+                                      const float* __restrict__ row_extra = nullptr,
+                                      const float* __restrict__ w_absmax = nullptr) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t npad = ((n + tile - 1) / tile) * tile;
   if (p >= npad) return;
@@ -73,23 +80,21 @@ static __global__ void tc_pack_kernel(const float* __restrict__ pts, const float
   const bool live = p < n;
   float sq = 0.f;
   for (int kc = 0; kc < dk / 8; ++kc) {
-    __nv_bfloat16 term[3][8];
+    __half term[kTcTerms][8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int d = kc * 8 + k;
       float X = 0.f;
       if (live && d < D) X = scale * (pts[p * D + d] - (center ? center[d] : 0.f));
+      X = fminf(fmaxf(X, -60000.f), 60000.f);  // fp16 range (only reached when every exponent underflows anyway)
       sq = fmaf(X, X, sq);
-      const __nv_bfloat16 h = __float2bfloat16_rn(X);
-      const float r1 = X - __bfloat162float(h);
-      const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+      const __half h = __float2half_rn(X);
       term[0][k] = h;
-      term[1][k] = m;
-      term[2][k] = __float2bfloat16_rn(r1 - __bfloat162float(m));
+      term[1][k] = __float2half_rn(X - __half2float(h));
     }
 #pragma unroll
-    for (int s = 0; s < 3; ++s)
-      *reinterpret_cast<uint4*>(img + ((int64_t)(s * (dk / 8) + kc) * tile + pt) * 16) = pack8_bf16(term[s]);
+    for (int s = 0; s < kTcTerms; ++s)
+      *reinterpret_cast<uint4*>(img + ((int64_t)(s * (dk / 8) + kc) * tile + pt) * 16) = pack8_f16(term[s]);
   }
   // rank-one chunk (16 wide): rows [1,1,1, r_h,r_m,r_l, 0..]   columns [c_h,c_m,c_l, 1,1,1, 0..]
   {
@@ -121,11 +126,16 @@ static __global__ void tc_pack_kernel(const float* __restrict__ pts, const float
       v.z = b | (c << 16);
     }
     v.w = 0u;
-    const int chunk = 3 * (dk / 8);
+    const int chunk = kTcTerms * (dk / 8);
     *reinterpret_cast<uint4*>(img + ((int64_t)chunk * tile + pt) * 16) = v;
     *reinterpret_cast<uint4*>(img + ((int64_t)(chunk + 1) * tile + pt) * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
-  if (is_cols) reinterpret_cast<float*>(img + (int64_t)tile * kp * 2)[pt] = (live && w) ? w[p] : 0.f;
+  if (is_cols) {
+    // (row-gradient kernels feed P = w e to an fp16 GEMM: weights are normalised to |w| <= 1, undone in the finalize)
+    float wv = (live && w) ? w[p] : 0.f;
+    if (w_absmax != nullptr && *w_absmax > 0.f) wv /= *w_absmax;
+    reinterpret_cast<float*>(img + (int64_t)tile * kp * 2)[pt] = wv;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -140,7 +150,7 @@ struct TcCfg {
   static constexpr int NACC = 2;          // accumulator buffers in TMEM
   static constexpr int THREADS = 64 + 32 * NEPI;
   static constexpr int A_COL0 = NACC * BN;  // the row operand lives in TMEM behind the accumulators
-  static constexpr int A_COLS = 128;        // up to kp = 256 bf16 per row (D <= 64: kp = 208)
+  static constexpr int A_COLS = 128;        // up to kp = 256 halves per row (D <= 64: kp = 144)
   static constexpr int TMEM_COLS = (A_COL0 + A_COLS <= 256) ? 256 : 512;
   static_assert(NEPI == 4 || NEPI == 8, "epilogue warps come in groups of four (one per TMEM lane quarter)");
   static_assert(BN % 64 == 0 && BN <= 256, "unsupported column tile");
@@ -207,7 +217,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kTcM, BN);
+      const uint32_t idesc = make_idesc_f16(kTcM, BN), idesc_r1 = make_idesc_bf16(kTcM, BN);
       mbar_wait(bar_a, 0);
       tc_fence_after();
       for (int k = 0; k < nt; ++k) {
@@ -217,16 +227,16 @@ __global__ void __launch_bounds__(C::THREADS, 1)
         tc_fence_after();
         const uint32_t a_tmem = tmem_base + C::A_COL0, b_addr = smem_u32(sb + st * b_bytes);
         const uint32_t d_addr = tmem_base + acc * BN;
-        // rank-one chunk first (overwrites the accumulator), then the six split cross products
-        const int seg = (kp - 16) / 3 / 8;  // 8-element chunks per split term
+        // rank-one chunk first (bf16; overwrites the accumulator), then the three fp16 cross products
+        const int seg = tc_dk_of_kp(kp) / 8;  // 8-element chunks per split term
         {
-          const uint64_t db = make_smem_desc(b_addr + 3 * seg * (BN * 16), BN * 16, 128);
-          umma_bf16_ts(d_addr, a_tmem + 3 * seg * 4, db, idesc, false);  // 4 TMEM columns per 8-element chunk
+          const uint64_t db = make_smem_desc(b_addr + kTcTerms * seg * (BN * 16), BN * 16, 128);
+          umma_bf16_ts(d_addr, a_tmem + kTcTerms * seg * 4, db, idesc_r1, false);  // 4 TMEM columns per 8-element chunk
         }
 #pragma unroll
-        for (int prod = 0; prod < 6; ++prod) {
-          // (A term, B term): hh, hm, mh, hl, mm, lh
-          const int ta = (0x210100 >> (4 * prod)) & 0xF, tb = (0x012010 >> (4 * prod)) & 0xF;
+        for (int prod = 0; prod < 3; ++prod) {
+          // (A term, B term): hh, hl, lh
+          const int ta = (prod == 2) ? 1 : 0, tb = (prod == 1) ? 1 : 0;
           for (int kk = 0; kk < seg / 2; ++kk) {
             const uint64_t db = make_smem_desc(b_addr + (tb * seg + 2 * kk) * (BN * 16), BN * 16, 128);
             umma_bf16_ts(d_addr, a_tmem + (ta * seg + 2 * kk) * 4, db, idesc, true);
