@@ -139,12 +139,13 @@ static int conv_pack(const float* y, const float* w, const float* center, int64_
 // tensor-core path (gaussian, 8 < D <= 64): see tcconv.cuh
 // ---------------------------------------------------------------------------------------------------
 constexpr int kTcBN = 128;    // columns per MMA tile
-constexpr int kTcEpi = 8;     // epilogue warps
+constexpr int kTcEpi = 16;    // epilogue warps of the forward kernels: 4 per TMEM lane quarter hide the tcgen05.ld latency
 using TcConvCfg = TcCfg<kTcBN, kTcEpi>;
+using TcBwdCfg = TcCfg<kTcBN, 8>;  // the two-GEMM kernel's in-place P layout assumes 8
 
 struct TcPlan {
   int kp, nstage, n_split, tiles_per_split;
-  int64_t a_tiles, b_tiles, a_bytes, b_bytes, smem;
+  int64_t a_tiles, a_tiles_pad, b_tiles, a_bytes, b_bytes, smem;
   int64_t off_b, off_part, off_misc, total;
 };
 
@@ -154,6 +155,7 @@ static TcPlan make_tc_plan(int64_t N, int64_t M, int D, bool bwd = false) {
   TcPlan p;
   p.kp = tc_kp(D);
   p.a_tiles = ceil_div64(N, kTcM);
+  p.a_tiles_pad = ceil_div64(p.a_tiles, kTcRT) * kTcRT;  // forward CTAs own kTcRT row tiles
   p.b_tiles = ceil_div64(M, kTcBN);
   p.a_bytes = tc_a_img_bytes(p.kp);
   p.b_bytes = tc_b_img_bytes(p.kp, kTcBN);
@@ -162,13 +164,13 @@ static TcPlan make_tc_plan(int64_t N, int64_t M, int D, bool bwd = false) {
   int64_t ns = avail / p.b_bytes;
   p.nstage = (int)(ns > kTcMaxStage ? kTcMaxStage : ns);
   p.smem = p.nstage * p.b_bytes + bar_bytes;
-  int64_t want = ceil_div64((int64_t)num_sms() * 4, p.a_tiles);
+  int64_t want = ceil_div64((int64_t)num_sms() * 4, bwd ? p.a_tiles : p.a_tiles_pad / kTcRT);
   if (want < 1) want = 1;
   if (want > 64) want = 64;
   if (want > p.b_tiles) want = p.b_tiles;
   p.tiles_per_split = (int)ceil_div64(p.b_tiles, want);
   p.n_split = (int)ceil_div64(p.b_tiles, p.tiles_per_split);
-  p.off_b = round_up64(p.a_tiles * p.a_bytes, 256);
+  p.off_b = round_up64(p.a_tiles_pad * p.a_bytes, 256);
   p.off_part = p.off_b + round_up64(p.b_tiles * p.b_bytes, 256);
   // partials: (m, s) pairs forward, D+1 sums per row backward
   p.off_misc = p.off_part + round_up64((int64_t)p.n_split * (kTcEpi / 4) * N * 4 * (bwd ? D + 1 : 2), 256);
@@ -176,7 +178,10 @@ static TcPlan make_tc_plan(int64_t N, int64_t M, int D, bool bwd = false) {
   return p;
 }
 
-int64_t tc_scratch_bytes(int64_t N, int64_t M, int D) { return make_tc_plan(N, M, D, true).total; }
+int64_t tc_scratch_bytes(int64_t N, int64_t M, int D) {
+  // forward and row-gradient launches split the columns differently: size for the larger of the two
+  return std::max(make_tc_plan(N, M, D, false).total, make_tc_plan(N, M, D, true).total);
+}
 
 // Row gradients on the tensor-core path (gaussian conv: kind 0 / softmin p=2: kind 1).  Leaves n_part sets of
 // (N, D+1) partial sums in *part_out.
@@ -199,23 +204,23 @@ int bwd_partial_tc(int kind, const float* x, const float* y, const float* w, con
   }
   if (w_absmax_out) *w_absmax_out = w_absmax;
   const int threads = 128;
-  tc_pack_kernel<<<(unsigned)ceil_div64(p.a_tiles * kTcM, threads), threads, 0, st>>>(
-      x, nullptr, nullptr, nullptr, 0.f, 0.f, center, scale, N, D, p.kp, kTcM, 0, a_imgs, lse2, nullptr);
+  tc_pack_kernel<<<(unsigned)ceil_div64(p.a_tiles_pad * kTcM, threads), threads, 0, st>>>(
+      x, nullptr, nullptr, nullptr, 0.f, 0.f, center, scale, N, D, p.kp, kTcM, 0, a_imgs, lse2, nullptr, kTcRT);
   B200OT_CUDA_TRY(cudaGetLastError());
   tc_pack_kernel<<<(unsigned)ceil_div64(p.b_tiles * kTcBN, threads), threads, 0, st>>>(
       y, w, h_a, h_b, h_scale_b, kLog2e, center, scale, M, D, p.kp, kTcBN, 1, b_imgs, nullptr, w_absmax);
   B200OT_CUDA_TRY(cudaGetLastError());
   dim3 grid((unsigned)p.a_tiles, (unsigned)p.n_split);
   if (kind == 0) {
-    auto kern = tc_bwd_kernel<TcConvCfg, 2>;
+    auto kern = tc_bwd_kernel<TcBwdCfg, 2>;
     B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    kern<<<grid, TcConvCfg::THREADS, (size_t)p.smem, st>>>(a_imgs, b_imgs, part, N, p.kp, (int)p.b_tiles,
-                                                          p.tiles_per_split, p.nstage, D);
+    kern<<<grid, TcBwdCfg::THREADS, (size_t)p.smem, st>>>(a_imgs, b_imgs, part, N, p.kp, (int)p.b_tiles,
+                                                         p.tiles_per_split, p.nstage, D);
   } else {
-    auto kern = tc_bwd_kernel<TcConvCfg, 3>;
+    auto kern = tc_bwd_kernel<TcBwdCfg, 3>;
     B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    kern<<<grid, TcConvCfg::THREADS, (size_t)p.smem, st>>>(a_imgs, b_imgs, part, N, p.kp, (int)p.b_tiles,
-                                                          p.tiles_per_split, p.nstage, D);
+    kern<<<grid, TcBwdCfg::THREADS, (size_t)p.smem, st>>>(a_imgs, b_imgs, part, N, p.kp, (int)p.b_tiles,
+                                                         p.tiles_per_split, p.nstage, D);
   }
   B200OT_CUDA_TRY(cudaGetLastError());
   *part_out = part;
@@ -236,15 +241,15 @@ int softmin_partial_tc(const float* x, const float* y, const float* h_a, const f
   float* part = reinterpret_cast<float*>(base + p.off_part);
   const float scale = softmin_coord_scale(2, eps);
   const int threads = 128;
-  tc_pack_kernel<<<(unsigned)ceil_div64(p.a_tiles * kTcM, threads), threads, 0, st>>>(
-      x, nullptr, nullptr, nullptr, 0.f, 0.f, center, scale, N, D, p.kp, kTcM, 0, a_imgs);
+  tc_pack_kernel<<<(unsigned)ceil_div64(p.a_tiles_pad * kTcM, threads), threads, 0, st>>>(
+      x, nullptr, nullptr, nullptr, 0.f, 0.f, center, scale, N, D, p.kp, kTcM, 0, a_imgs, nullptr, nullptr, kTcRT);
   B200OT_CUDA_TRY(cudaGetLastError());
   tc_pack_kernel<<<(unsigned)ceil_div64(p.b_tiles * kTcBN, threads), threads, 0, st>>>(
       y, nullptr, h_a, h_b, h_scale_b, kLog2e, center, scale, M, D, p.kp, kTcBN, 1, b_imgs);
   B200OT_CUDA_TRY(cudaGetLastError());
   auto kern = tc_reduce_kernel<TcConvCfg, 1>;
   B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-  dim3 grid((unsigned)p.a_tiles, (unsigned)p.n_split);
+  dim3 grid((unsigned)(p.a_tiles_pad / kTcRT), (unsigned)p.n_split);
   kern<<<grid, TcConvCfg::THREADS, (size_t)p.smem, st>>>(a_imgs, b_imgs, part, N, p.kp, (int)p.b_tiles,
                                                         p.tiles_per_split, p.nstage, D);
   B200OT_CUDA_TRY(cudaGetLastError());
@@ -263,15 +268,15 @@ static int conv_fwd_tc(const float* x, const float* y, const float* w, const flo
   float* part = reinterpret_cast<float*>(base + p.off_part);
   const float scale = sqrtf(kLog2e) / blur;
   const int threads = 128;
-  tc_pack_kernel<<<(unsigned)ceil_div64(p.a_tiles * kTcM, threads), threads, 0, st>>>(
-      x, nullptr, nullptr, nullptr, 0.f, 0.f, center, scale, N, D, p.kp, kTcM, 0, a_imgs);
+  tc_pack_kernel<<<(unsigned)ceil_div64(p.a_tiles_pad * kTcM, threads), threads, 0, st>>>(
+      x, nullptr, nullptr, nullptr, 0.f, 0.f, center, scale, N, D, p.kp, kTcM, 0, a_imgs, nullptr, nullptr, kTcRT);
   B200OT_CUDA_TRY(cudaGetLastError());
   tc_pack_kernel<<<(unsigned)ceil_div64(p.b_tiles * kTcBN, threads), threads, 0, st>>>(
       y, w, nullptr, nullptr, 0.f, 0.f, center, scale, M, D, p.kp, kTcBN, 1, b_imgs);
   B200OT_CUDA_TRY(cudaGetLastError());
   auto kern = tc_reduce_kernel<TcConvCfg, 0>;
   B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-  dim3 grid((unsigned)p.a_tiles, (unsigned)p.n_split);
+  dim3 grid((unsigned)(p.a_tiles_pad / kTcRT), (unsigned)p.n_split);
   kern<<<grid, TcConvCfg::THREADS, (size_t)p.smem, st>>>(a_imgs, b_imgs, part, N, p.kp, (int)p.b_tiles,
                                                         p.tiles_per_split, p.nstage, D);
   B200OT_CUDA_TRY(cudaGetLastError());
@@ -289,7 +294,7 @@ extern "C" {
 
 B200OT_API int64_t b200ot_kernel_conv_scratch_bytes(int64_t N, int64_t M, int32_t D) {
   if (N <= 0 || M <= 0 || D <= 0) return 0;
-  if (tc_supported_dim(D)) return make_tc_plan(N, M, D, true).total;
+  if (tc_supported_dim(D)) return tc_scratch_bytes(N, M, D);
   const ReducePlan pl = make_plan(N, M);
   const int64_t cols = b200ot_packed_cols_floats(M, D, 2) * 4;
   const int64_t part = (int64_t)pl.n_split * N * 4 * (D + 1);

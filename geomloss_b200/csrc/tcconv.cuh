@@ -68,9 +68,10 @@ static __global__ void tc_pack_kernel(const float* __restrict__ pts, const float
                                       float scale, int64_t n, int D, int kp, int tile, int is_cols,
                                       unsigned char* __restrict__ out,
                                       const float* __restrict__ row_extra = nullptr,
-                                      const float* __restrict__ w_absmax = nullptr) {
+                                      const float* __restrict__ w_absmax = nullptr, int pad_tiles = 1) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t npad = ((n + tile - 1) / tile) * tile;
+  const int64_t group = (int64_t)tile * pad_tiles;  // images are written for a multiple of pad_tiles tiles
+  const int64_t npad = ((n + group - 1) / group) * group;
   if (p >= npad) return;
   const int64_t t = p / tile;
   const int pt = (int)(p % tile);
@@ -142,30 +143,37 @@ static __global__ void tc_pack_kernel(const float* __restrict__ pts, const float
 // the reduction kernel
 // ---------------------------------------------------------------------------------------------------
 constexpr int kTcMaxStage = 4;
+constexpr int kTcRT = 2;  // row tiles per CTA in the forward kernels (each column tile is used twice from shared memory)
 
 template <int BN_, int NEPI_>
 struct TcCfg {
   static constexpr int BN = BN_;          // columns per tile = N of the MMA
-  static constexpr int NEPI = NEPI_;      // epilogue warps (4 or 8)
-  static constexpr int NACC = 2;          // accumulator buffers in TMEM
+  static constexpr int NEPI = NEPI_;      // epilogue warps (4, 8 or 16)
   static constexpr int THREADS = 64 + 32 * NEPI;
-  static constexpr int A_COL0 = NACC * BN;  // the row operand lives in TMEM behind the accumulators
-  static constexpr int A_COLS = 128;        // up to kp = 256 halves per row (D <= 64: kp = 144)
-  static constexpr int TMEM_COLS = (A_COL0 + A_COLS <= 256) ? 256 : 512;
-  static_assert(NEPI == 4 || NEPI == 8, "epilogue warps come in groups of four (one per TMEM lane quarter)");
-  static_assert(BN % 64 == 0 && BN <= 256, "unsupported column tile");
+  static constexpr int A_COL0 = kTcRT * BN;  // the row operands live in TMEM behind the accumulators
+  static constexpr int A_COLS = 80;          // per row tile: kp/2 <= 72 columns (D <= 64: kp = 144 halves)
+  static constexpr int TMEM_COLS = 512;
+  static_assert(A_COL0 + kTcRT * A_COLS <= 512, "TMEM budget");
+  static_assert(NEPI == 4 || NEPI == 8 || NEPI == 16, "epilogue warps come in groups of four (one per TMEM lane quarter)");
+  static_assert(BN % 64 == 0 && BN <= 128, "unsupported column tile");
 };
 
 // MODE 0: gaussian kernel conv  part[(split*NH + half)*N + row]   = sum_j w_j 2^S_ij
 // MODE 1: softmin               part2[(split*NH + half)*N + row]  = (m, s) with sum_j 2^S_ij = s 2^m  (lazy max,
 //         sum-guarded exactly like softmin.cuh; same partial format as softmin_partial_kernel)
 // (row gradients — modes 2 and 3 — are a two-GEMM kernel of their own: tcbwd.cuh)
+//
+// A CTA owns kTcRT = 2 row tiles (2 x 128 rows) and ping-pongs between them: step (k, r) multiplies row tile r by
+// column tile k into accumulator r, so (i) every column tile fetched from L2 feeds 2 x 128 rows — at one row tile
+// per CTA the kernel was L2 -> shared-memory bound (5.8 TB/s at D = 64) — and (ii) the MMAs of step (k, 1) overlap
+// the exponentials of step (k, 0), those of (k+1, 0) the exponentials of (k, 1): the two accumulators double as
+// the double buffer.
 template <class C, int MODE>
 __global__ void __launch_bounds__(C::THREADS, 1)
     tc_reduce_kernel(const unsigned char* __restrict__ a_imgs, const unsigned char* __restrict__ b_imgs,
                      float* __restrict__ part, int64_t N, int kp, int ntiles_b, int tiles_per_split, int NSTAGE,
                      int D) {
-  constexpr int BN = C::BN, NEPI = C::NEPI, NACC = C::NACC;
+  constexpr int BN = C::BN, NEPI = C::NEPI, RT = kTcRT;
   static_assert(MODE == 0 || MODE == 1, "row gradients live in tcbwd.cuh");
   extern __shared__ __align__(1024) unsigned char smem[];
   const int a_bytes = kTcM * kp * 2;
@@ -176,23 +184,23 @@ __global__ void __launch_bounds__(C::THREADS, 1)
   uint64_t* full_b = bars + 1;
   uint64_t* empty_b = full_b + kTcMaxStage;
   uint64_t* tmem_full = empty_b + kTcMaxStage;
-  uint64_t* tmem_empty = tmem_full + NACC;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + NACC);
+  uint64_t* tmem_empty = tmem_full + RT;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + RT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row_tile = blockIdx.x;
+  const int row_tile0 = blockIdx.x * RT;  // (the row images are padded to a multiple of RT tiles)
   const int split = blockIdx.y;
   const int t0 = split * tiles_per_split;
   const int t1 = min(ntiles_b, t0 + tiles_per_split);
   const int nt = t1 - t0;
 
   if (threadIdx.x == 0) {
-    mbar_init(bar_a, 4);  // the four lane quarters of the row operand
+    mbar_init(bar_a, 4);  // the four lane quarters of the row operands
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&full_b[s], 1);
       mbar_init(&empty_b[s], 1 + NEPI);  // MMA completion + every epilogue warp (it reads the weights)
     }
-    for (int a = 0; a < NACC; ++a) {
+    for (int a = 0; a < RT; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], NEPI);
     }
@@ -218,125 +226,143 @@ __global__ void __launch_bounds__(C::THREADS, 1)
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(kTcM, BN), idesc_r1 = make_idesc_bf16(kTcM, BN);
+      const int seg = tc_dk_of_kp(kp) / 8;  // 8-element chunks per split term
       mbar_wait(bar_a, 0);
       tc_fence_after();
       for (int k = 0; k < nt; ++k) {
-        const int st = k % NSTAGE, acc = k % NACC;
+        const int st = k % NSTAGE;
         mbar_wait(&full_b[st], (k / NSTAGE) & 1);
-        if (k >= NACC) mbar_wait(&tmem_empty[acc], ((k / NACC) + 1) & 1);
-        tc_fence_after();
-        const uint32_t a_tmem = tmem_base + C::A_COL0, b_addr = smem_u32(sb + st * b_bytes);
-        const uint32_t d_addr = tmem_base + acc * BN;
-        // rank-one chunk first (bf16; overwrites the accumulator), then the three fp16 cross products
-        const int seg = tc_dk_of_kp(kp) / 8;  // 8-element chunks per split term
-        {
-          const uint64_t db = make_smem_desc(b_addr + kTcTerms * seg * (BN * 16), BN * 16, 128);
-          umma_bf16_ts(d_addr, a_tmem + kTcTerms * seg * 4, db, idesc_r1, false);  // 4 TMEM columns per 8-element chunk
-        }
+        const uint32_t b_addr = smem_u32(sb + st * b_bytes);
 #pragma unroll
-        for (int prod = 0; prod < 3; ++prod) {
-          // (A term, B term): hh, hl, lh
-          const int ta = (prod == 2) ? 1 : 0, tb = (prod == 1) ? 1 : 0;
-          for (int kk = 0; kk < seg / 2; ++kk) {
-            const uint64_t db = make_smem_desc(b_addr + (tb * seg + 2 * kk) * (BN * 16), BN * 16, 128);
-            umma_bf16_ts(d_addr, a_tmem + (ta * seg + 2 * kk) * 4, db, idesc, true);
+        for (int r = 0; r < RT; ++r) {
+          if (k >= 1) mbar_wait(&tmem_empty[r], (k + 1) & 1);
+          tc_fence_after();
+          const uint32_t a_tmem = tmem_base + C::A_COL0 + r * C::A_COLS;
+          const uint32_t d_addr = tmem_base + r * BN;
+          // rank-one chunk first (bf16; overwrites the accumulator), then the three fp16 cross products
+          {
+            const uint64_t db = make_smem_desc(b_addr + kTcTerms * seg * (BN * 16), BN * 16, 128);
+            umma_bf16_ts(d_addr, a_tmem + kTcTerms * seg * 4, db, idesc_r1, false);  // 4 TMEM columns per 8 elements
           }
+#pragma unroll
+          for (int prod = 0; prod < 3; ++prod) {
+            // (A term, B term): hh, hl, lh
+            const int ta = (prod == 2) ? 1 : 0, tb = (prod == 1) ? 1 : 0;
+            for (int kk = 0; kk < seg / 2; ++kk) {
+              const uint64_t db = make_smem_desc(b_addr + (tb * seg + 2 * kk) * (BN * 16), BN * 16, 128);
+              umma_bf16_ts(d_addr, a_tmem + (ta * seg + 2 * kk) * 4, db, idesc, true);
+            }
+          }
+          umma_commit(&tmem_full[r]);  // accumulator r ready for the epilogue
         }
-        umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
-        umma_commit(&empty_b[st]);     // operand slot consumed
+        umma_commit(&empty_b[st]);  // operand slot consumed by both row tiles
       }
     }
   } else {
     // ===== epilogue: TMEM -> exp2 -> weighted row sums =====
     const int ew = warp - 2;
     const int quarter = warp & 3;              // TMEM lanes this warp may touch: 32*quarter .. +31
-    const int half = ew / 4;                   // column share when two warps cover one lane quarter
+    const int half = ew / 4;                   // column share when several warps cover one lane quarter
     constexpr int NH = NEPI / 4;
     constexpr int CW = BN / NH;                // columns per warp per tile
-    const int64_t row = (int64_t)row_tile * kTcM + quarter * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     if (ew < 4) {
-      // stage this CTA's row operand into TMEM once: thread = row (TMEM lane), 16 bf16 (8 columns) at a time
-      const unsigned char* src = a_imgs + (int64_t)row_tile * a_bytes + (quarter * 32 + lane) * 16;
-      for (int c2 = 0; c2 < kp / 16; ++c2) {
-        const uint4 lo = *reinterpret_cast<const uint4*>(src + (int64_t)(2 * c2) * kTcM * 16);
-        const uint4 hi = *reinterpret_cast<const uint4*>(src + (int64_t)(2 * c2 + 1) * kTcM * 16);
-        const uint32_t r[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-        tmem_st8(tmem_base + ((uint32_t)(quarter * 32) << 16) + C::A_COL0 + c2 * 8, r);
+      // stage this CTA's row operands into TMEM once: thread = row (TMEM lane), 16 halves (8 columns) at a time
+      for (int r = 0; r < RT; ++r) {
+        const unsigned char* src = a_imgs + (int64_t)(row_tile0 + r) * a_bytes + (quarter * 32 + lane) * 16;
+        for (int c2 = 0; c2 < kp / 16; ++c2) {
+          const uint4 lo = *reinterpret_cast<const uint4*>(src + (int64_t)(2 * c2) * kTcM * 16);
+          const uint4 hi = *reinterpret_cast<const uint4*>(src + (int64_t)(2 * c2 + 1) * kTcM * 16);
+          const uint32_t v8[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+          tmem_st8(lane_base + C::A_COL0 + r * C::A_COLS + c2 * 8, v8);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_a);
     }
-    float acc0 = 0.f, acc1 = 0.f;      // MODE 0: weighted sums
-    float m = kNegBig, srun = 0.f;     // MODE 1: running (m, s)
+    float acc[RT];                 // MODE 0: weighted sums
+    float m[RT], srun[RT];         // MODE 1: running (m, s)
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      acc[r] = 0.f;
+      m[r] = kNegBig;
+      srun[r] = 0.f;
+    }
     for (int k = 0; k < nt; ++k) {
-      const int st = k % NSTAGE, acc = k % NACC;
-      mbar_wait(&tmem_full[acc], (k / NACC) & 1);
-      tc_fence_after();
+      const int st = k % NSTAGE;
       const float* wts = reinterpret_cast<const float*>(sb + st * b_bytes + BN * kp * 2);
-      float ts0 = 0.f, ts1 = 0.f;
 #pragma unroll
-      for (int c0 = 0; c0 < CW; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * CW + c0, v);
-        if constexpr (MODE == 0) {
-          const float4* w4 = reinterpret_cast<const float4*>(wts + half * CW + c0);
+      for (int r = 0; r < RT; ++r) {
+        mbar_wait(&tmem_full[r], k & 1);
+        tc_fence_after();
+        float ts0 = 0.f, ts1 = 0.f;
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            const float4 w = w4[c / 4];
-            ts0 = fmaf(ex2_approx(v[c + 0]), w.x, ts0);
-            ts1 = fmaf(ex2_approx(v[c + 1]), w.y, ts1);
-            ts0 = fmaf(ex2_approx(v[c + 2]), w.z, ts0);
-            ts1 = fmaf(ex2_approx(v[c + 3]), w.w, ts1);
-          }
-        } else {
-          float cs0 = 0.f, cs1 = 0.f;
+        for (int c0 = 0; c0 < CW; c0 += 32) {
+          float v[32];
+          tmem_ld32(lane_base + r * BN + half * CW + c0, v);
+          if constexpr (MODE == 0) {
+            const float4* w4 = reinterpret_cast<const float4*>(wts + half * CW + c0);
 #pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            cs0 += ex2_approx(v[c] - m);
-            cs1 += ex2_approx(v[c + 1] - m);
-          }
-          if (!(cs0 + cs1 <= 1.8446744e19f)) {
-            // outdated max (a term above 2^64 or an overflow): rebase on this chunk's max and redo it
-            float cm = v[0];
-#pragma unroll
-            for (int c = 1; c < 32; ++c) cm = fmaxf(cm, v[c]);
-            const float sc = ex2_approx(m - cm);
-            srun *= sc;
-            ts0 *= sc;
-            ts1 *= sc;
-            m = cm;
-            cs0 = 0.f;
-            cs1 = 0.f;
+            for (int c = 0; c < 32; c += 4) {
+              const float4 w = w4[c / 4];
+              ts0 = fmaf(ex2_approx(v[c + 0]), w.x, ts0);
+              ts1 = fmaf(ex2_approx(v[c + 1]), w.y, ts1);
+              ts0 = fmaf(ex2_approx(v[c + 2]), w.z, ts0);
+              ts1 = fmaf(ex2_approx(v[c + 3]), w.w, ts1);
+            }
+          } else {
+            float cs0 = 0.f, cs1 = 0.f;
 #pragma unroll
             for (int c = 0; c < 32; c += 2) {
-              cs0 += ex2_approx(v[c] - m);
-              cs1 += ex2_approx(v[c + 1] - m);
+              cs0 += ex2_approx(v[c] - m[r]);
+              cs1 += ex2_approx(v[c + 1] - m[r]);
             }
+            if (!(cs0 + cs1 <= 1.8446744e19f)) {
+              // outdated max (a term above 2^64 or an overflow): rebase on this chunk's max and redo it
+              float cm = v[0];
+#pragma unroll
+              for (int c = 1; c < 32; ++c) cm = fmaxf(cm, v[c]);
+              const float sc = ex2_approx(m[r] - cm);
+              srun[r] *= sc;
+              ts0 *= sc;
+              ts1 *= sc;
+              m[r] = cm;
+              cs0 = 0.f;
+              cs1 = 0.f;
+#pragma unroll
+              for (int c = 0; c < 32; c += 2) {
+                cs0 += ex2_approx(v[c] - m[r]);
+                cs1 += ex2_approx(v[c + 1] - m[r]);
+              }
+            }
+            ts0 += cs0;
+            ts1 += cs1;
           }
-          ts0 += cs0;
-          ts1 += cs1;
+        }
+        if constexpr (MODE == 0) {
+          acc[r] += ts0 + ts1;
+        } else {
+          srun[r] += ts0 + ts1;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&tmem_empty[r]);
+          if (r == RT - 1) mbar_arrive(&empty_b[st]);
         }
       }
-      if constexpr (MODE == 0) {
-        acc0 += ts0;
-        acc1 += ts1;
-      } else {
-        srun += ts0 + ts1;
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&tmem_empty[acc]);
-        mbar_arrive(&empty_b[st]);
-      }
     }
-    if (row < N) {
-      if constexpr (MODE == 0) {
-        part[((int64_t)split * NH + half) * N + row] = acc0 + acc1;
-      } else {
-        reinterpret_cast<float2*>(part)[((int64_t)split * NH + half) * N + row] = make_float2(m, srun);
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      const int64_t row = (int64_t)(row_tile0 + r) * kTcM + quarter * 32 + lane;
+      if (row < N) {
+        if constexpr (MODE == 0) {
+          part[((int64_t)split * NH + half) * N + row] = acc[r];
+        } else {
+          reinterpret_cast<float2*>(part)[((int64_t)split * NH + half) * N + row] = make_float2(m[r], srun[r]);
+        }
       }
     }
   }
