@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(C::THREADS, 1)
     tc_bwd_kernel(const unsigned char* __restrict__ a_imgs, const unsigned char* __restrict__ b_imgs,
                   float* __restrict__ part, int64_t N, int kp, int ntiles_b, int tiles_per_split, int NSTAGE, int D) {
   constexpr int BN = C::BN, NEPI = C::NEPI, NACC = 2;
-  static_assert(BN == 128 && NEPI == 8, "layout below assumes 128-column tiles and 8 epilogue warps");
+  static_assert(BN == 128 && (NEPI == 8 || NEPI == 16), "layout below assumes 128-column tiles, 8 or 16 epilogue warps");
+  constexpr int NH = NEPI / 4;   // warps per TMEM lane quarter = column shares of a tile
+  constexpr int CW = BN / NH;    // columns per warp per tile (64 or 32)
   constexpr int A_COL0 = NACC * BN;   // row operand X behind the two S/P buffers
   constexpr int G_COL0 = 384;         // gradient accumulator (dk <= 64 columns)
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -75,7 +77,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
   uint64_t* p_ready = s_full + NACC;          // P(k) written by all epilogue warps
   uint64_t* g_done = p_ready + NACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_done + 1);
-  float* sp_x = reinterpret_cast<float*>(tmem_slot + 2);  // [128] sum_j P of the second column half
+  float* sp_x = reinterpret_cast<float*>(tmem_slot + 2);  // [NH-1][128] sum_j P of the other column shares
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row_tile = blockIdx.x;
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
     // ===== epilogue warps: S -> P (in place), row sums of P =====
     const int ew = warp - 2;
     const int quarter = warp & 3;  // TMEM lanes 32*quarter .. +31
-    const int half = ew / 4;       // columns 64*half .. +63 of every tile
+    const int half = ew / 4;       // column share: columns CW*half .. +CW-1 of every tile
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int64_t row = (int64_t)row_tile * kTcM + quarter * 32 + lane;
     if (ew < 4) {
@@ -195,8 +197,8 @@ __global__ void __launch_bounds__(C::THREADS, 1)
       tc_fence_after();
       const float* wts = reinterpret_cast<const float*>(sb + st * b_bytes + BN * kp * 2);
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        const int col0 = half * 64 + c0;
+      for (int c0 = 0; c0 < CW; c0 += 32) {
+        const int col0 = half * CW + c0;
         float v[32];
         tmem_ld32(lane_base + acc * BN + col0, v);
         uint32_t ph[16], pl[16];
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
       if (lane == 0) mbar_arrive(&p_ready[acc]);
     }
     // ---- G is complete once every MMA has retired: read it back, add the row sums of the two halves ----
-    if (half == 1) sp_x[quarter * 32 + lane] = sum0 + sum1;
+    if (half >= 1) sp_x[(half - 1) * 128 + quarter * 32 + lane] = sum0 + sum1;
     asm volatile("bar.sync 1, %0;" ::"r"(32 * NEPI) : "memory");
     mbar_wait(g_done, 0);
     tc_fence_after();
@@ -233,13 +235,16 @@ __global__ void __launch_bounds__(C::THREADS, 1)
       tmem_ld32(lane_base + G_COL0 + half * 32, g);
       if (row < N) {
         float* dst = part + ((int64_t)split * N + row) * (D + 1);
-        if (half == 0) dst[0] = sum0 + sum1 + sp_x[quarter * 32 + lane];
+        if (half == 0) {
+          float tot = sum0 + sum1;
+#pragma unroll
+          for (int h2 = 1; h2 < NH; ++h2) tot += sp_x[(h2 - 1) * 128 + quarter * 32 + lane];
+          dst[0] = tot;
+        }
 #pragma unroll
         for (int c = 0; c < 32; ++c)
           if (half * 32 + c < D) dst[1 + half * 32 + c] = g[c];
       }
-    } else if (half == 0) {
-      // (unreachable: half 0 always owns columns)
     }
   }
   tc_fence_before();
