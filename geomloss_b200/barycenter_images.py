@@ -54,46 +54,61 @@ def _softmin(eps, p, h):
     return softmin_grid(eps, p, h.detach())
 
 
-def barycenter_iteration(f_k, g_k, d_log, eps, p, ak_log, w_k):
-    """One debiased barycenter step (wasserstein_barycenter_images.py:6-34)."""
-    w = w_k[:, :, None, None]
-    ft_k = _softmin(eps, p, ak_log + g_k / eps) / eps  # pseudo-step: measures -> barycenter
-    bar_log = d_log - (ft_k * w).sum(1, keepdim=True)
-    ft_k = _softmin(eps, p, ak_log + g_k / eps)  # symmetric Sinkhorn updates
-    gt_k = _softmin(eps, p, bar_log + f_k / eps)
-    f_k = (f_k + ft_k) / 2
-    g_k = (g_k + gt_k) / 2
-    ft_k = _softmin(eps, p, ak_log + g_k / eps) / eps
-    bar_log = d_log - (ft_k * w).sum(1, keepdim=True)
-    d_log = 0.5 * (d_log + bar_log + _softmin(eps, p, d_log) / eps)  # de-biasing measure
-    return f_k, g_k, d_log, bar_log
+class _Descent:
+    """State of the debiased barycenter scheme at one resolution: the K pairs of dual potentials (`to_bar` lives
+    on the barycenter side, `to_meas` on the measures' side), the log of the de-biasing density and the current
+    log-barycenter.  One `step` = wasserstein_barycenter_images.py:6-34."""
+
+    def __init__(self, log_meas0, weights, p):
+        self.p, self.weights = p, weights  # (the broadcast view is taken per use: it must see the live grad mode)
+        start = _softmin(1.0, p, log_meas0)
+        self.to_bar, self.to_meas = start, start.clone() if start.requires_grad else start
+        flat = torch.ones_like(log_meas0).sum(dim=1, keepdim=True)
+        self.debias = flat - flat.logsumexp([2, 3], keepdim=True)  # uniform probability on the coarsest grid
+        self.log_bar = None
+
+    def _pull(self, eps, log_meas):
+        """log-barycenter implied by the measures-side potentials: debias - sum_k lam_k softmin_k / eps."""
+        transported = _softmin(eps, self.p, log_meas + self.to_meas / eps)
+        return self.debias - (transported * self.weights[:, :, None, None]).sum(1, keepdim=True) / eps
+
+    def step(self, eps, log_meas):
+        p = self.p
+        bar = self._pull(eps, log_meas)
+        # symmetric (averaged) Sinkhorn updates between every measure and the current barycenter estimate
+        new_to_bar = 0.5 * (self.to_bar + _softmin(eps, p, log_meas + self.to_meas / eps))
+        new_to_meas = 0.5 * (self.to_meas + _softmin(eps, p, bar + self.to_bar / eps))
+        self.to_bar, self.to_meas = new_to_bar, new_to_meas
+        self.log_bar = self._pull(eps, log_meas)
+        self.debias = 0.5 * (self.debias + self.log_bar + _softmin(eps, p, self.debias) / eps)
+
+    def refine(self):
+        self.to_bar, self.to_meas, self.debias = upsample(self.to_bar), upsample(self.to_meas), upsample(self.debias)
 
 
 def ImagesBarycenter(measures, weights, blur=0, p=2, scaling_N=10, backward_iterations=5):
     """Barycenter of ``measures`` (B, K, N, N) with barycentric ``weights`` (B, K); returns (B, 1, N, N).
 
-    Same arguments and iteration counts as the reference (wasserstein_barycenter_images.py:37-93)."""
-    a_k, w_k = measures, weights
-    if a_k.dim() != 4 or a_k.shape[-1] != a_k.shape[-2]:
+    Same arguments, schedule (``scaling_N`` steps per resolution 2x2 .. NxN, the blur scale halved per
+    resolution down to ``blur``, default one pixel) and autograd contract as the reference
+    (wasserstein_barycenter_images.py:37-93)."""
+    if measures.dim() != 4 or measures.shape[-1] != measures.shape[-2]:
         raise ValueError("measures must be a (B, K, N, N) batch of square images")
-    if blur == 0:
-        blur = 1 / a_k.shape[-1]
+    floor = blur if blur != 0 else 1 / measures.shape[-1]
+    shrink = 2 ** (-1 / scaling_N)
     with torch.set_grad_enabled(torch.is_grad_enabled() and backward_iterations == 0):
-        ak_s = pyramid(a_k)[1:]
-        ak_log_s = [log_dens(t) for t in ak_s]
-        sigma = 1
-        eps = sigma**p
-        f_k, g_k = _softmin(eps, p, ak_log_s[0]), _softmin(eps, p, ak_log_s[0])
-        d_log = torch.ones_like(ak_log_s[0]).sum(dim=1, keepdim=True)
-        d_log = d_log - d_log.logsumexp([2, 3], keepdim=True)
-        for n, ak_log in enumerate(ak_log_s):
+        levels = [log_dens(t) for t in pyramid(measures)[1:]]  # 2x2, 4x4, .. NxN; the 1-pixel level is dropped
+        state = _Descent(levels[0], weights, p)
+        sigma = 1.0
+        for depth, log_meas in enumerate(levels):
             for _ in range(scaling_N):
                 eps = sigma**p
-                f_k, g_k, d_log, bar_log = barycenter_iteration(f_k, g_k, d_log, eps, p, ak_log, w_k)
-                sigma = max(sigma * (2 ** (-1 / scaling_N)), blur)
-            if n + 1 < len(ak_s):
-                f_k, g_k, d_log = upsample(f_k), upsample(g_k), upsample(d_log)
-    if (measures.requires_grad or weights.requires_grad) and backward_iterations > 0:
+                state.step(eps, log_meas)
+                sigma = max(sigma * shrink, floor)
+            if depth + 1 < len(levels):
+                state.refine()
+    if backward_iterations > 0 and (measures.requires_grad or weights.requires_grad):
+        # extra differentiable steps at the final resolution and temperature, from detached potentials
         for _ in range(backward_iterations):
-            f_k, g_k, d_log, bar_log = barycenter_iteration(f_k, g_k, d_log, eps, p, ak_log, w_k)
-    return bar_log.exp()
+            state.step(eps, log_meas)
+    return state.log_bar.exp()
