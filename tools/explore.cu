@@ -3,8 +3,9 @@
 // 1. pipe micro-benchmarks (MUFU.EX2, FFMA, FFMA2, FMNMX3, mixes) -> per-SM-per-clock rates;
 // 2. softmin partial-kernel variants on synthetic uniform clouds: CUDA-event timing + fp64 CPU check
 //    of a sample of rows.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -Iinclude -Igeomloss_b200/csrc
-//        tools/explore.cu geomloss_b200/csrc/b200ot_core.cu -o build/explore
+// Build (after __graft_entry__.build(); links the packing / micro-benchmark entry points from the library):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Iinclude -Igeomloss_b200/csrc tools/explore.cu \
+//        -Lgeomloss_b200 -lb200ot -Xlinker -rpath -Xlinker '$ORIGIN/../geomloss_b200' -o build/explore
 // Usage: explore [N] [M] [eps] [reps]
 #include <math.h>
 #include <stdio.h>
