@@ -59,8 +59,8 @@ def _check_clouds(x, y, max_d=None):
         raise ValueError("empty point cloud")
     if x.shape[1] > max_d:
         raise NotImplementedError(f"D = {x.shape[1]} > {max_d}: not instantiated in this build (CUDA-core kernels "
-                                  f"serve D <= {MAX_D}; the tensor-core path serves the gaussian forward up to "
-                                  f"D = {MAX_D_TC})")
+                                  f"serve D <= {MAX_D}; the tensor-core kernels serve the p = 2 softmin and the "
+                                  f"gaussian kernel, forward and row gradients, up to D = {MAX_D_TC})")
     if x.device != y.device:
         raise ValueError("x and y must be on the same device")
 

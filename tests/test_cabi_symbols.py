@@ -86,3 +86,30 @@ def test_product_requires_cuda_tensors():
         SamplesLoss("sinkhorn")(x, y)
     with pytest.raises(_lib.B200OTError):
         SamplesLoss("gaussian")(x, y)
+
+
+def test_scratch_plans_cover_every_shape(L):
+    """Host-side launch plans (no GPU work): scratch sizes are positive, 256-byte granular, monotone in the cloud
+    sizes, and large enough for the packed columns plus one set of partials, across the CUDA-core dimensions, the
+    tensor-core dimensions (8 < D <= 64: operand images, padded to two row tiles) and extreme shapes."""
+    shapes = [(1, 1), (1, 5000), (5000, 1), (129, 65), (10**4, 10**4), (10**6, 10**6), (10**7, 3 * 10**6)]
+    for D in (1, 3, 8, 9, 16, 33, 64):
+        prev = 0
+        for N, M in shapes:
+            sb = L.b200ot_softmin_scratch_bytes(N, M, D)
+            kb = L.b200ot_kernel_conv_scratch_bytes(N, M, D)
+            assert sb > 0 and kb > 0 and sb % 256 == 0 and kb % 256 == 0, (N, M, D, sb, kb)
+            if D <= 8:
+                assert sb >= L.b200ot_packed_cols_floats(M, D, 1) * 4 + N * 8
+                assert kb >= L.b200ot_packed_cols_floats(M, D, 2) * 4 + N * 4
+                ns = L.b200ot_softmin_num_splits(N, M, D)
+                assert 1 <= ns <= max(1, -(-M // 256)), (N, M, D, ns)
+            else:
+                # operand images: 2 fp16 terms + a 16-wide rank-one chunk per point, 128-point tiles
+                dk = -(-D // 16) * 16
+                assert sb >= (N + M) * (2 * dk + 16) * 2, (N, M, D, sb)
+        assert L.b200ot_softmin_scratch_bytes(10**6, 10**6, D) >= L.b200ot_softmin_scratch_bytes(10**5, 10**5, D)
+    assert L.b200ot_softmin_scratch_bytes(10, 10, 65) == 0 or L.b200ot_softmin_scratch_bytes(10, 10, 65) > 0  # no crash
+    r, c = ctypes.c_int32(0), ctypes.c_int32(0)
+    L.b200ot_sparse_tile_shape(ctypes.byref(r), ctypes.byref(c))
+    assert r.value > 0 and c.value > 0 and c.value % 16 == 0
