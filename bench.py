@@ -157,6 +157,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # rank 0 alone runs and prints the reference line
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the reference arm is entitled to all host threads it can use
+    if os.environ.get("OMP_NUM_THREADS") == "1" and "LOCAL_RANK" in os.environ:
+        try:
+            torch.set_num_threads(len(os.sched_getaffinity(0)))
+        except (AttributeError, OSError):
+            torch.set_num_threads(os.cpu_count() or 1)
     n = args.cpu_n
     O, eps, a_log, C, pots = dense_iteration_state(n, args.blur)
     with torch.no_grad():
