@@ -256,3 +256,29 @@ def test_ot_solve_sample_host_logic(monkeypatch, idx):
     assert (out - P @ s).abs().max() <= 1e-4 * (P @ s.abs()).max()
     res.cache_clear()
     assert abs(res.value.item() - ref) <= 2e-5 * abs(ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# numerics of the tensor-core operand format (csrc/tcconv.cuh): X = h + l in fp16, products hh + hl + lh
+# ------------------------------------------------------------------------------------------------
+def test_fp16_two_term_split_error_bound():
+    """CPU emulation of the split the tensor-core kernels use for 8 < D <= 64: the exponent
+    S = X.Y - |X|^2/2 - |Y|^2/2 formed from two fp16 terms per coordinate and three cross products (exact
+    accumulation emulated in fp64) stays within 2^-20 |X||Y| of the fp64 value — i.e. the fp32 accumulator, not the
+    16-bit operands, bounds the accuracy of the kernel value."""
+    g = torch.Generator().manual_seed(0)
+    D, n = 64, 300
+    x = torch.rand(n, D, generator=g, dtype=torch.float64)
+    y = torch.rand(n, D, generator=g, dtype=torch.float64)
+    for blur in (2.0, 0.7, 0.3):
+        s = np.sqrt(np.log2(np.e)) / blur
+        X, Y = ((x - 0.5) * s).float(), ((y - 0.5) * s).float()
+        Xh, Yh = X.half(), Y.half()
+        Xl, Yl = (X - Xh.float()).half(), (Y - Yh.float()).half()
+        dot = Xh.double() @ Yh.double().T + Xh.double() @ Yl.double().T + Xl.double() @ Yh.double().T
+        exact = X.double() @ Y.double().T
+        bound = 2.0**-20 * X.double().norm(dim=1)[:, None] * Y.double().norm(dim=1)[None, :]
+        err = (dot - exact).abs()
+        assert bool((err <= bound).all()), (blur, float((err / bound).max()))
+        # relative error of the kernel value 2^S: below 1e-5 down to blur = .3 (|X|^2 ~ 86)
+        assert float(err.max()) * np.log(2) < 1e-5, (blur, float(err.max()))
