@@ -17,8 +17,12 @@ at N = M = 1e6 like the rest of the engine.  Conventions of THIS API (they diffe
 Mapping onto the kernel (which evaluates ``-e log sum_j exp(h_j - (|x-y|^2/2)/e)``): with ``e = reg/2``,
 ``-reg log sum_j b_j exp((g_j - |x-y|^2)/reg) = 2 * softmin_kernel(e; h = log b + g/reg)``.
 
-Forward only: the result attributes are computed without autograd (the reference's torch path is differentiable
-through the last update; use ``SamplesLoss`` for gradients).  Inputs: float32 CUDA tensors; no CPU path.
+Autograd: like the reference, ``result.value`` is differentiable w.r.t. ``X_a``, ``X_b`` (through the cost in the
+LAST update only — log-weights and incoming potentials are detached, sinkhorn_ot.py:419-436) and w.r.t. ``a``, ``b``
+(their direct appearance in the value formula).  Unlike ``SamplesLoss`` the last update is differentiated w.r.t.
+BOTH clouds of every softmin: the column gradient  sum_i u_i p_ij 2 (y_j - x_i)  is the row-gradient kernel run on
+the swapped problem with column "log-weights" log u_i + softmin_i/eps (see ``_LastUpdate``).  The other attributes
+(potentials, marginals, plan) are returned detached.  Inputs: float32 CUDA tensors; no CPU path.
 Parity: pinned — ``tests/golden/ot_sample_case*.npz`` hold fp32 and fp64 runs of the real reference.
 """
 from __future__ import annotations
@@ -109,6 +113,48 @@ class _Softmin:
         return (damp * (f - 0.5 * w_rows.double() * f)).float()
 
 
+class _LastUpdate(torch.autograd.Function):
+    """``damp * softmin(eps, log_w, C(rows, cols), pot)`` of the new API, differentiable w.r.t. rows AND cols.
+
+    With p_ij the softmax weights of row i over the columns and u = damp * grad_output:
+      d/d rows_i = u_i 2 (rows_i - sum_j p_ij cols_j)                    -> b200ot_softmin_bwd_x as is;
+      d/d cols_j = sum_i u_i p_ij 2 (cols_j - rows_i) = 2 W_j (cols_j - sum_i q_ji rows_i),
+         W_j = sum_i u_i p_ij = exp(log_w_j + pot_j/eps) sum_i exp(log u_i + softmin_i/eps - C_ij/eps),
+      i.e. the SAME row-gradient kernel on the swapped problem (rows <- cols, column log-weights log u_i, column
+      potential softmin_i), one extra softmin for its normaliser W; signed u is split into its two parts."""
+
+    @staticmethod
+    def forward(ctx, rows, cols, log_w, pot, eps, damp, center):
+        out, lse2 = ops.softmin_raw(0.5 * eps, rows.detach(), cols.detach(), log_w, pot, 1.0 / eps, p=2, center=center,
+                                    beta=2.0 * damp, want_lse2=True)
+        ctx.save_for_backward(rows.detach(), cols.detach(), log_w, pot, out, lse2, center)
+        ctx.meta = (float(eps), float(damp))
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        rows, cols, log_w, pot, out, lse2, center = ctx.saved_tensors
+        eps, damp = ctx.meta
+        e2, inv = 0.5 * eps, 1.0 / eps
+        u_all = (damp * go).float().contiguous()
+        g_rows = g_cols = None
+        if ctx.needs_input_grad[0]:
+            g_rows = ops.softmin_grad_rows(e2, rows, cols, log_w, pot, inv, lse2, 2.0 * u_all, p=2, center=center)
+        if ctx.needs_input_grad[1]:
+            sm_und = out / damp  # undamped softmin values, new-API scale
+            g_cols = torch.zeros_like(cols)
+            for sign in (1.0, -1.0):
+                u = (sign * u_all).clamp_min(0.0)
+                if not bool((u > 0).any()):
+                    continue
+                lu = log_weights(u)
+                sm_t, lse2_t = ops.softmin_raw(e2, cols, rows, lu, sm_und, inv, p=2, center=center, want_lse2=True)
+                W = torch.exp((log_w.double() + pot.double() * inv - sm_t.double() / e2)).float()
+                g_cols = g_cols + sign * ops.softmin_grad_rows(e2, cols, rows, lu, sm_und, inv, lse2_t,
+                                                               (2.0 * W).contiguous(), p=2, center=center)
+        return g_rows, g_cols, None, None, None, None, None
+
+
 def solve_sample(X_a, X_b, a=None, b=None, cost="sqeuclidean", debias=False, reg=None, unbalanced=None,
                  unbalanced_type="KL", method="auto", max_iter=None, tol=None, blur=None, reach=None):
     """Entropic (un)balanced OT between two point clouds; mirrors ``geomloss.ot.solve_sample`` (sample.py:190-395).
@@ -140,7 +186,7 @@ def solve_sample(X_a, X_b, a=None, b=None, cost="sqeuclidean", debias=False, reg
     a = _check_marginal(a, X_a[:, 0], N, "a")
     b = _check_marginal(b, X_b[:, 0], M, "b")
     if unbalanced is None:
-        sa, sb = float(a.sum()), float(b.sum())
+        sa, sb = float(a.detach().sum()), float(b.detach().sum())
         if abs(sa - sb) / (sa + sb) > 1e-3:
             raise ValueError("The two arrays of marginal weights 'a' and 'b' do not sum up to the same value. As a "
                              "consequence, the balanced OT problem is not feasible. To fix this error, you may either "
@@ -151,6 +197,8 @@ def solve_sample(X_a, X_b, a=None, b=None, cost="sqeuclidean", debias=False, reg
     reg = float(reg)
     rho = None if unbalanced is None else float(unbalanced)
 
+    live = (X_a, X_b, a, b)  # the caller's tensors: the value stays attached to them when they require grad
+    want_grad = torch.is_grad_enabled() and any(t.requires_grad for t in live)
     with torch.no_grad():
         X_a, X_b, a, b = X_a.detach(), X_b.detach(), a.detach(), b.detach()
         eps_list = annealing_eps(max_diameter(X_a, X_b) ** p, reg, int(max_iter))
@@ -174,15 +222,25 @@ def solve_sample(X_a, X_b, a=None, b=None, cost="sqeuclidean", debias=False, reg
                 f_aa = sm(eps, X_a, X_a, log_a, f_aa, damp=lam, old=f_aa)
                 g_bb = sm(eps, X_b, X_b, log_b, g_bb, damp=lam, old=g_bb)
             f_ba, g_ab = ft_ba, gt_ab
-        # last, non-averaged update (last_extrapolation=True, sinkhorn_ot.py:419-436)
-        new_f = sm(eps, X_a, X_b, log_b, g_ab, damp=lam)
-        new_g = sm(eps, X_b, X_a, log_a, f_ba, damp=lam)
+        if not want_grad:
+            # last, non-averaged update (last_extrapolation=True, sinkhorn_ot.py:419-436)
+            new_f = sm(eps, X_a, X_b, log_b, g_ab, damp=lam)
+            new_g = sm(eps, X_b, X_a, log_a, f_ba, damp=lam)
+            f_ba, g_ab = new_f, new_g
+            if debias:
+                f_aa = sm(eps, X_a, X_a, log_a, f_aa, damp=lam)
+                g_bb = sm(eps, X_b, X_b, log_b, g_bb, damp=lam)
+    if want_grad:
+        # the same update, attached to the caller's clouds through the cost (both arguments of every softmin)
+        xa, xb = live[0], live[1]
+        last = lambda rows, cols, lw, pot: _LastUpdate.apply(rows, cols, lw, pot, eps, lam, sm.center)  # noqa: E731
+        new_f, new_g = last(xa, xb, log_b, g_ab), last(xb, xa, log_a, f_ba)
         f_ba, g_ab = new_f, new_g
         if debias:
-            f_aa = sm(eps, X_a, X_a, log_a, f_aa, damp=lam)
-            g_bb = sm(eps, X_b, X_b, log_b, g_bb, damp=lam)
-        else:
-            f_aa = g_bb = None
+            f_aa, g_bb = last(xa, xa, log_a, f_aa), last(xb, xb, log_b, g_bb)
+        a, b = live[2], live[3]
+    if not debias:
+        f_aa = g_bb = None
     return OTResultSample(X_a=X_a, X_b=X_b, a=a, b=b, reg=reg, unbalanced=rho, debias=bool(debias),
                           potentials=(f_aa, g_bb, g_ab, f_ba), softmin=sm)
 
@@ -240,9 +298,10 @@ class OTResultSample:
     without KeOps)."""
 
     def __init__(self, *, X_a, X_b, a, b, reg, unbalanced, debias, potentials, softmin):
-        self._X_a, self._X_b, self._a, self._b = X_a, X_b, a, b
+        self._X_a, self._X_b, self._a, self._b = X_a, X_b, a.detach(), b.detach()
         self._reg, self._unbalanced, self._debias = reg, unbalanced, debias
-        self._f_aa, self._g_bb, self._g_ab, self._f_ba = potentials
+        self._live = (a, b) + tuple(potentials)  # possibly attached to the caller's graph: used by `value` only
+        self._f_aa, self._g_bb, self._g_ab, self._f_ba = (None if t is None else t.detach() for t in potentials)
         self._sm = softmin
 
     # ---- dual potentials --------------------------------------------------------------------------
@@ -271,10 +330,8 @@ class OTResultSample:
     # ---- value                                                   unbalanced_ot.py:25-185 ----------
     @cached_property
     def value(self):
-        a, b, eps, rho = self._a.double(), self._b.double(), self._reg, self._unbalanced
-        f_ba, g_ab = self._f_ba.double(), self._g_ab.double()
-        if self._debias:
-            f_aa, g_bb = self._f_aa.double(), self._g_bb.double()
+        a, b, f_aa, g_bb, g_ab, f_ba = (None if t is None else t.double() for t in self._live)
+        eps, rho = self._reg, self._unbalanced
         if rho is None:
             F, G = (f_ba - f_aa, g_ab - g_bb) if self._debias else (f_ba, g_ab)
         elif not self._debias:

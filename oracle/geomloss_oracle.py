@@ -562,20 +562,25 @@ def ot_solve_sample(X_a, X_b, a=None, b=None, debias=False, reg=None, unbalanced
         # offset" is the per-point 0.5 * a_i * f_i, not half the mean of f (torch.py:28-32, sinkhorn_ot.py:24-27)
         return lam * (f - 0.5 * lw_self.exp() * f)
 
-    lam = damp(eps_list[0])
-    f_ba, g_ab = init(log_a, log_b, C_xy), init(log_b, log_a, C_yx)
-    if debias:
-        f_aa, g_bb = init(log_a, log_a, C_xx), init(log_b, log_b, C_yy)
-    for eps in eps_list:
-        lam = damp(eps)
-        ft_ba, gt_ab = lam * ot_softmin(eps, log_b, C_xy, g_ab), lam * ot_softmin(eps, log_a, C_yx, f_ba)
+    # autograd contract (sinkhorn_ot.py:240-262, :419-436): the loop runs without a graph; the last update is
+    # differentiated through the COST MATRICES only (log-weights and incoming potentials detached), and the value
+    # formula keeps its direct dependence on a and b
+    with torch.no_grad():
+        lam = damp(eps_list[0])
+        f_ba, g_ab = init(log_a, log_b, C_xy), init(log_b, log_a, C_yx)
         if debias:
-            ft_aa, gt_bb = lam * ot_softmin(eps, log_a, C_xx, f_aa), lam * ot_softmin(eps, log_b, C_yy, g_bb)
-            f_aa, g_bb = 0.5 * (f_aa + ft_aa), 0.5 * (g_bb + gt_bb)
-        f_ba, g_ab = 0.5 * (f_ba + ft_ba), 0.5 * (g_ab + gt_ab)
-    f_ba, g_ab = lam * ot_softmin(eps, log_b, C_xy, g_ab), lam * ot_softmin(eps, log_a, C_yx, f_ba)
+            f_aa, g_bb = init(log_a, log_a, C_xx), init(log_b, log_b, C_yy)
+        for eps in eps_list:
+            lam = damp(eps)
+            ft_ba, gt_ab = lam * ot_softmin(eps, log_b, C_xy, g_ab), lam * ot_softmin(eps, log_a, C_yx, f_ba)
+            if debias:
+                ft_aa, gt_bb = lam * ot_softmin(eps, log_a, C_xx, f_aa), lam * ot_softmin(eps, log_b, C_yy, g_bb)
+                f_aa, g_bb = 0.5 * (f_aa + ft_aa), 0.5 * (g_bb + gt_bb)
+            f_ba, g_ab = 0.5 * (f_ba + ft_ba), 0.5 * (g_ab + gt_ab)
+    la, lb = log_a.detach(), log_b.detach()
+    f_ba, g_ab = (lam * ot_softmin(eps, lb, C_xy, g_ab.detach()), lam * ot_softmin(eps, la, C_yx, f_ba.detach()))
     if debias:
-        f_aa, g_bb = lam * ot_softmin(eps, log_a, C_xx, f_aa), lam * ot_softmin(eps, log_b, C_yy, g_bb)
+        f_aa, g_bb = lam * ot_softmin(eps, la, C_xx, f_aa.detach()), lam * ot_softmin(eps, lb, C_yy, g_bb.detach())
     else:
         f_aa = g_bb = None
     density = torch.exp((f_ba[:, None] + g_ab[None, :] - C_xy) / reg)  # sample.py:511-561

@@ -611,6 +611,31 @@ def test_ot_solve_sample_vs_reference_goldens(idx):
     assert res.plan_operator.shape == (n, m) and res.lazy_plan is None
 
 
+@pytest.mark.parametrize("idx", range(8))
+def test_ot_solve_sample_gradients_vs_reference(idx):
+    """d value / d (X_a, X_b, a, b): the last update differentiated w.r.t. BOTH clouds (row-gradient kernel + the same
+    kernel on the swapped problem) against the real reference's fp64 autograd (tests/golden/make_golden_ot.py)."""
+    from geomloss_b200 import ot
+
+    z = load_golden(f"ot_sample_case{idx:02d}")
+    kw = {k[3:]: float(z[k]) for k in z if k.startswith("kw_")}
+    kw["max_iter"] = int(kw["max_iter"])
+    if "debias" in kw:
+        kw["debias"] = bool(kw["debias"])
+    n, m = z["X_a"].shape[0], z["X_b"].shape[0]
+    a0 = torch.from_numpy(z["a"]) if "a" in z else torch.full((n,), 1.0 / n)
+    b0 = torch.from_numpy(z["b"]) if "b" in z else torch.full((m,), 1.0 / m)
+    leaves = [t.to(DEV).requires_grad_(True) for t in (torch.from_numpy(z["X_a"]), torch.from_numpy(z["X_b"]), a0, b0)]
+    res = ot.solve_sample(leaves[0], leaves[1], a=leaves[2], b=leaves[3], **kw)
+    ref = float(z["value_f64"])
+    assert abs(res.value.item() - ref) <= 1e-4 * abs(ref)
+    grads = torch.autograd.grad(res.value, leaves)
+    for g, name in zip(grads, ("grad_X_a", "grad_X_b", "grad_a", "grad_b")):
+        r = z[name + "_f64"]
+        np.testing.assert_allclose(g.cpu().numpy(), r, atol=2e-3 * float(np.abs(r).max()), err_msg=name)
+    assert not res.potential_a.requires_grad and not res.marginal_b.requires_grad
+
+
 def test_ot_solve_sample_diracs_and_doc_example():
     """The reference's own checks for this solver: tests/test_ot_solve_sample.py::test_correct_values_diracs
     (one point per side: value = C, potentials = C/2, plan = 1, any reg / max_iter) and the doctest of

@@ -228,6 +228,46 @@ def _dense_softmin_raw(eps, x, y, h_a, h_b=None, h_scale_b=0.0, *, p=2, center=N
     return val.float(), None
 
 
+def _dense_softmin_grad_rows(eps, x, y, h_a, h_b, h_scale_b, lse2, grad_out, *, p=2, center=None):
+    """Stand-in for b200ot_softmin_bwd_x: grad_out_i * (x_i - sum_j w_ij y_j), softmax weights re-normalised by
+    their own sum (lse2 only guards the kernel against overflow)."""
+    from oracle import geomloss_oracle as O
+
+    h = h_a.double() if h_b is None else h_a.double() + h_scale_b * h_b.double()
+    w = torch.softmax(h[None, :] - O.cost_matrix(x.double(), y.double(), p) / eps, dim=1)
+    return (grad_out.double()[:, None] * (x.double() - w @ y.double())).float()
+
+
+@pytest.mark.parametrize("idx", range(8))
+def test_ot_solve_sample_gradients_host_logic(monkeypatch, idx):
+    """d value / d (X_a, X_b, a, b) of the facade (last update differentiated w.r.t. BOTH clouds: row-gradient
+    kernel + the same kernel on the swapped problem for the columns) against the real reference's autograd."""
+    from conftest import load_golden
+    from geomloss_b200 import ops, ot
+
+    monkeypatch.setattr(ops, "softmin_raw", _dense_softmin_raw)
+    monkeypatch.setattr(ops, "softmin_grad_rows", _dense_softmin_grad_rows)
+    z = load_golden(f"ot_sample_case{idx:02d}")
+    kw = {k[3:]: float(z[k]) for k in z if k.startswith("kw_")}
+    kw["max_iter"] = int(kw["max_iter"])
+    if "debias" in kw:
+        kw["debias"] = bool(kw["debias"])
+    n, m = z["X_a"].shape[0], z["X_b"].shape[0]
+    a0 = torch.from_numpy(z["a"]) if "a" in z else torch.full((n,), 1.0 / n)
+    b0 = torch.from_numpy(z["b"]) if "b" in z else torch.full((m,), 1.0 / m)
+    leaves = [t.clone().requires_grad_(True) for t in (torch.from_numpy(z["X_a"]), torch.from_numpy(z["X_b"]), a0, b0)]
+    res = ot.solve_sample(leaves[0], leaves[1], a=leaves[2], b=leaves[3], **kw)
+    assert abs(res.value.item() - float(z["value_f64"])) <= 2e-5 * abs(float(z["value_f64"]))
+    grads = torch.autograd.grad(res.value, leaves)
+    for g, name in zip(grads, ("grad_X_a", "grad_X_b", "grad_a", "grad_b")):
+        ref = z[name + "_f64"]
+        np.testing.assert_allclose(g.numpy(), ref, atol=2e-4 * float(np.abs(ref).max()), err_msg=name)
+    assert not res.potential_a.requires_grad and not res.marginal_a.requires_grad  # accessors are detached
+    # without requires_grad (or under no_grad) nothing is attached
+    with torch.no_grad():
+        assert not ot.solve_sample(leaves[0], leaves[1], a=leaves[2], b=leaves[3], **kw).value.requires_grad
+
+
 @pytest.mark.parametrize("idx", range(8))
 def test_ot_solve_sample_host_logic(monkeypatch, idx):
     from conftest import load_golden

@@ -183,3 +183,15 @@ def test_oracle_ot_solve_sample_matches_reference(idx):
             ref = z[name + suffix]
             scale = max(1.0, float(np.abs(ref).max()))
             np.testing.assert_allclose(val.numpy(), ref, atol=tol * scale, err_msg=f"{name}{suffix} case {idx}")
+    # autograd contract of the new API (last update differentiated through the cost matrices; direct dependence of
+    # the value on a and b): gradients of the reference's fp64 run
+    z, args, kw = _ot_case(f"ot_sample_case{idx:02d}", torch.float64)
+    n, m = args["X_a"].shape[0], args["X_b"].shape[0]
+    if args["a"] is None:
+        args["a"], args["b"] = torch.full((n,), 1.0 / n, dtype=torch.float64), torch.full((m,), 1.0 / m, dtype=torch.float64)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in args.items()}
+    val = O.ot_solve_sample(**leaves, **kw)["value"]
+    grads = torch.autograd.grad(val, [leaves[k] for k in ("X_a", "X_b", "a", "b")])
+    for g, name in zip(grads, ("grad_X_a", "grad_X_b", "grad_a", "grad_b")):
+        ref = z[name + "_f64"]
+        np.testing.assert_allclose(g.numpy(), ref, atol=1e-9 * max(1.0, float(np.abs(ref).max())), err_msg=name)
