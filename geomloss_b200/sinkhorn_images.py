@@ -13,7 +13,6 @@ only the weights receive gradients (the potentials), through the final value for
 """
 from __future__ import annotations
 
-import ctypes
 
 import numpy as np
 import torch

@@ -29,7 +29,6 @@ Reference map (all paths under ``src/geomloss/_legacy/``):
 """
 from __future__ import annotations
 
-import math
 
 import numpy as np
 import torch
