@@ -322,3 +322,30 @@ def test_fp16_two_term_split_error_bound():
         assert bool((err <= bound).all()), (blur, float((err / bound).max()))
         # relative error of the kernel value 2^S: below 1e-5 down to blur = .3 (|X|^2 ~ 86)
         assert float(err.max()) * np.log(2) < 1e-5, (blur, float(err.max()))
+
+
+# ------------------------------------------------------------------------------------------------
+# sinkhorn_images.sinkhorn_divergence host logic on CPU (pyramid, jumps, up-sampling, value formulas) with the
+# dense grid operator standing in for b200ot_softmin_grid
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(2, 1, 16, 16), (1, 2, 8, 8, 8)])
+@pytest.mark.parametrize("kw", [dict(p=2), dict(p=1, reach=0.3), dict(p=2, debias=False, scaling=0.7)])
+def test_sinkhorn_images_host_logic(monkeypatch, shape, kw):
+    from geomloss_b200 import sinkhorn_images as SI
+    from oracle import geomloss_oracle as O
+
+    monkeypatch.setattr(SI, "softmin_grid", _dense_grid_softmin)
+    g = torch.Generator().manual_seed(sum(shape))
+    a = torch.rand(*shape, generator=g, dtype=torch.float64) + 0.01
+    b = torch.rand(*shape, generator=g, dtype=torch.float64) + 0.01
+    dims = tuple(range(2, len(shape)))
+    a, b = a / a.sum(dims, keepdim=True), 1.2 * b / b.sum(dims, keepdim=True) if "reach" in kw else b / b.sum(dims, keepdim=True)
+    ours = SI.sinkhorn_divergence(a, b, **kw)
+    ref = O.sinkhorn_images(a, b, **kw)
+    assert ours.shape == (shape[0],)
+    assert (ours - ref).abs().max() <= 1e-9 * ref.abs().max() + 1e-15
+    F, G = SI.sinkhorn_divergence(a, b, potentials=True, **kw)
+    Fr, Gr = O.sinkhorn_images(a, b, potentials=True, **kw)
+    assert F.shape == a.shape and (F - Fr).abs().max() <= 1e-9 and (G - Gr).abs().max() <= 1e-9
+    with pytest.raises(ValueError):
+        SI.sinkhorn_divergence(a, b, scaling=0.3)
