@@ -57,7 +57,8 @@ def parse():
 # clocks: sample SM clock / throttle reasons DURING the timed region (NVML, 100 ms period)
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler:
-    def __init__(self, index: int):
+    def __init__(self, index: int, period: float = 0.1):
+        self.period = period
         self.samples, self.reasons, self.power = [], set(), []
         self.max_mhz = None
         self._stop = threading.Event()
@@ -89,7 +90,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(self.period)
 
     def __enter__(self):
         if self.nv is not None:

@@ -7,7 +7,7 @@ import sys
 import torch
 
 sys.path.insert(0, ".")
-from geomloss_b200 import ops  # noqa: E402
+from geomloss_b200 import ops  # noqa: E402  (bench.py, imported below for its NVML clock sampler, lives at the repo root)
 
 dev = "cuda:0"
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
@@ -33,8 +33,25 @@ for D in dims:
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         ms = min(ts)
+        # sustained run with the SM clock sampled under load (tensor-heavy kernels do not hold 1965 MHz: a
+        # pairs/s figure only compares to a per-clock roofline at the clock it was measured at)
+        from bench import ClockSampler  # noqa: E402
+
+        reps = max(4, int(1500 / max(ms, 1e-3)))
+        with ClockSampler(0, period=0.02) as cs:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                out = ops.kernel_conv_raw(kind, x, y, w, blur, center=c)
+            e1.record()
+            torch.cuda.synchronize()
+        sus = e0.elapsed_time(e1) / reps
+        clk = cs.summary()
         print(json.dumps({"conv": kind, "N": N, "M": N, "D": D, "ms": round(ms, 3),
-                          "Tpairs_s": round(N * N / (ms * 1e-3) / 1e12, 3), "sum": float(out.sum())}))
+                          "Tpairs_s": round(N * N / (ms * 1e-3) / 1e12, 3), "sustained_ms": round(sus, 3),
+                          "sustained_Tpairs_s": round(N * N / (sus * 1e-3) / 1e12, 3), "sm_mhz": clk.get("sm_mhz"),
+                          "sm_min_mhz": clk.get("sm_min_mhz"), "power_w_max": clk.get("power_w_max"),
+                          "reasons": clk.get("reasons"), "sum": float(out.sum())}))
 
 # forward + backward of the gaussian MMD at D = 64 (BASELINE configs[2] protocol: L = Loss(x, y); L.backward())
 if 64 in dims:
