@@ -8,7 +8,7 @@
 
 namespace b200ot {
 
-static char g_last_cuda_error[512] = "";
+static thread_local char g_last_cuda_error[512] = "";  // per host thread: concurrent callers do not race on it
 
 void set_last_cuda_error(cudaError_t e, const char* where) {
   snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s (%s)", where, cudaGetErrorName(e),
