@@ -6,11 +6,12 @@ algorithm the reference's ``backend="tensorized"`` path runs.  It exists so that
 ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference`` legs may
 import it; the product package never does (``tests/test_host_logic.py`` enforces this).
 
-Parity status: PINNED for the point-cloud path (everything above the "grids" block at the end of this
-file, which is UNPINNED — see the note there).  ``tests/golden/make_golden.py`` imports the real reference from
-``/root/reference/src`` in the build container, runs it on seeded inputs and stores its outputs in
-``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks every function below against those
-fixtures (the reference itself ships no test for this path — SURVEY.md section 4).
+Parity status: PINNED for every block of this file.  ``tests/golden/make_golden*.py`` import the real reference
+from ``/root/reference/src`` in the build container, run it on seeded inputs (fp32 and fp64) and store its outputs
+in ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` and ``tests/test_oracle_golden_keops.py`` check every
+function below against those fixtures (the reference itself ships no test for this path — SURVEY.md section 4).
+The reference's pykeops-backed code (online / multiscale backends, grids, barycenters) is executed UNMODIFIED on
+``tests/golden/pykeops_shim``, a dense torch stand-in for the pykeops calls it makes.
 
 Reference map (all paths under ``src/geomloss/_legacy/``):
     sqdist / dist            utils.py:26-61          (|x|^2 - 2 x.y + |y|^2 ; sqrt(clamp_min(., 1e-8)))
@@ -306,12 +307,11 @@ def pair_interactions(n_eps: int, N: int, M: int, debias: bool = True) -> float:
 # ------------------------------------------------------------------------------------------------
 # grids (images / volumes)                  utils.py:69-108, :190-279 ; sinkhorn_images.py:26-202
 #
-# PARITY UNPINNED for this block: the reference's softmin_grid needs pykeops (absent, un-vendored), so no
-# golden output of the reference exists for it.  The restatement below follows the reference line by
-# line with dense torch broadcasting in place of the KeOps LazyTensor reduction, and
-# tests/test_oracle_golden.py::test_grid_softmin_is_the_full_grid_softmin checks it against the PINNED
-# point-cloud softmin evaluated on the explicit pixel coordinates (the separable form must equal the
-# full N^D x N^D soft-C-transform).
+# PARITY PINNED: tests/golden/img_*.npz (make_golden_images.py: the unmodified reference on the dense pykeops
+# shim; operator, divergence values / gradients / potentials in 2-D and 3-D, fp32 and fp64).  The restatement
+# follows the reference line by line with dense torch broadcasting in place of the KeOps LazyTensor reduction;
+# tests/test_oracle_golden.py::test_grid_softmin_is_the_full_grid_softmin additionally checks the separable
+# form against the full N^D x N^D soft-C-transform of the point-cloud oracle.
 # ------------------------------------------------------------------------------------------------
 
 
@@ -403,93 +403,219 @@ def sinkhorn_images(a, b, p=2, blur=None, reach=None, scaling=0.5, debias=True, 
 
 
 # ------------------------------------------------------------------------------------------------
-# multiscale (two-scale Sinkhorn with kernel truncation)     sinkhorn_samples.py:453-681,
-#                                                            sinkhorn_divergence.py:519-606
-# PARITY UNPINNED (pykeops: grid_cluster, cluster_ranges_centroids, from_matrix are not installable here;
-# their semantics are restated from SURVEY.md appendix B).  Dense torch: the block-sparse reduction of the
-# reference is emulated with a point-level -inf mask built from the cluster-level `keep` matrix.
+# pykeops-backed point-cloud backends ("online", "multiscale")
+#     sinkhorn_online      sinkhorn_samples.py:349-424     softmin_online :337-346, lazytensor :229-290
+#     sinkhorn_multiscale  sinkhorn_samples.py:547-681     clusterize :453-490, kernel_truncation :493-530,
+#                          extrapolate_samples :533-544, jump branch sinkhorn_divergence.py:519-606
+#     kernel_multiscale    kernel_samples.py:177-271
+# PARITY PINNED: tests/golden/ms_*.npz and online_*.npz are produced by the UNMODIFIED reference running on
+# tests/golden/pykeops_shim (a dense torch stand-in for the pykeops calls; make_golden_multiscale.py), in
+# fp32 and fp64.  Dense torch here: the block-sparse reduction of the reference is emulated with a
+# point-level -inf / 0 mask built from the cluster-level `keep` matrix.
+#
+# Semantics that differ from the tensorized path and are restated on purpose:
+#   * KeOps formulas use explicit differences: SqDist(X,Y)/2 and Norm2(X-Y) — NO 1e-8 clamp for p = 1
+#     (sinkhorn_samples.py:303-306; sqrt(0) = 0 with a zero gradient, KeOps' convention);
+#   * the parameter P = torch.Tensor([1/eps]).type_as(x) is rounded to fp32 even for fp64 inputs (:344, :449);
+#   * sinkhorn_multiscale passes the LEAKED loop variable `eps` of its jump search (:594-597) to
+#     sinkhorn_cost (:669): the unbalanced weight (rho + eps/2) uses the temperature at which the search stopped
+#     (or the last temperature when it never breaks), not blur**p;
+#   * kernel_truncation evaluates the coarse cost with the CLAMPED tensorized routine (cost_routines[p], :610).
 # ------------------------------------------------------------------------------------------------
 
 
+def keops_sqdist(x, y):
+    return ((x.unsqueeze(-2) - y.unsqueeze(-3)) ** 2).sum(-1)
+
+
+def keops_norm2(x, y):
+    sq = keops_sqdist(x, y)
+    pos = sq > 0
+    return torch.where(pos, sq, torch.ones_like(sq)).sqrt() * pos.to(sq.dtype)
+
+
+def keops_cost(x, y, p):
+    if p == 2:
+        return keops_sqdist(x, y) / 2
+    if p == 1:
+        return keops_norm2(x, y)
+    raise KeyError(p)
+
+
+def keops_softmin(eps, x, y, h, p=2, mask=None):
+    """-eps * LSE_j(h_j - P * C(x_i, y_j)) with P = fp32(1/eps); x:(..., N, D), y:(..., M, D), h:(..., M)."""
+    P = torch.Tensor([1 / eps]).type_as(x)
+    t = h.unsqueeze(-2) - P * keops_cost(x, y, p)
+    if mask is not None:
+        t = t.masked_fill(~mask, -float("inf"))
+    return -eps * torch.logsumexp(t, dim=-1)
+
+
+def sinkhorn_online(a, x, b, y, p=2, blur=0.05, reach=None, diameter=None, scaling=0.5, debias=True,
+                    potentials=False):
+    """backend="online" on batched inputs a:(B,N) x:(B,N,D).                    sinkhorn_samples.py:349-424"""
+    def softmin(eps, C, h):
+        return keops_softmin(eps, C[0], C[1], h, p)
+
+    C_xy, C_yx = (x, y.detach()), (y, x.detach())
+    C_xx, C_yy = ((x, x.detach()), (y, y.detach())) if debias else (None, None)
+    diameter, eps, eps_list, rho = scaling_parameters(x, y, p, blur, reach, diameter, scaling)
+    f_aa, g_bb, g_ab, f_ba = sinkhorn_loop(softmin, log_weights(a), log_weights(b), C_xx, C_yy, C_xy, C_yx,
+                                           eps_list, rho, debias=debias)
+    return sinkhorn_value(eps, rho, a, b, f_aa, g_bb, g_ab, f_ba, debias=debias, potentials=potentials)
+
+
+def keops_kernel_matrix(name, x, y, blur):
+    """kernel_samples.py:62-82 with use_keops=True: explicit differences, unclamped sqrt."""
+    if name == "gaussian":
+        return (-keops_sqdist(x / blur, y / blur) / 2).exp()
+    if name == "laplacian":
+        return (-keops_norm2(x / blur, y / blur)).exp()
+    if name == "energy":
+        return -keops_norm2(x, y)
+    raise KeyError(name)
+
+
+def mmd_online(a, x, b, y, name, blur=0.05, potentials=False, masks=None):
+    """kernel_loss(use_keops=True) on (B,N,D) or (N,D) inputs; ``masks`` = point-level (xx, yy, xy) boolean
+    masks of the block-sparse reductions (kernel_multiscale).                     kernel_samples.py:92-146"""
+    dg = _TwiceGrad.apply
+    K_xx = keops_kernel_matrix(name, dg(x), x.detach(), blur)
+    K_yy = keops_kernel_matrix(name, dg(y), y.detach(), blur)
+    K_xy = keops_kernel_matrix(name, x, y, blur)
+    if masks is not None:
+        K_xx, K_yy, K_xy = K_xx * masks[0], K_yy * masks[1], K_xy * masks[2]
+    a_x = (K_xx @ a.detach().unsqueeze(-1)).squeeze(-1)
+    b_y = (K_yy @ b.detach().unsqueeze(-1)).squeeze(-1)
+    b_x = (K_xy @ b.unsqueeze(-1)).squeeze(-1)
+    if potentials:
+        a_y = (K_xy.transpose(-1, -2) @ a.unsqueeze(-1)).squeeze(-1)
+        return a_x - b_x, b_y - a_y
+    if x.dim() > 2:
+        return 0.5 * _dot(dg(a), a_x) + 0.5 * _dot(dg(b), b_y) - _dot(a, b_x)
+    return 0.5 * (dg(a) * a_x).sum() + 0.5 * (dg(b) * b_y).sum() - (a * b_x).sum()
+
+
 def ms_grid_labels(x, scale):
+    """pykeops grid_cluster: voxel indices mixed with (2^20, 2^10, 1), relabelled 0..C-1 in increasing key order."""
     ij = torch.floor((x - x.min(0).values) / scale).long()
-    key = ij[:, 0]
-    for k in range(1, x.shape[1]):
-        key = key * (int(ij[:, k].max()) + 1) + ij[:, k]
+    w = {1: [1], 2: [2**10, 1], 3: [2**20, 2**10, 1]}[x.shape[1]]
+    key = (ij * torch.tensor(w)).sum(1)
     return torch.unique(key, sorted=True, return_inverse=True)[1]
 
 
-def ms_clusterize(a, x, scale):
-    lab = ms_grid_labels(x, scale)
-    C = int(lab.max()) + 1
-    a_c = torch.zeros(C, dtype=a.dtype).index_add_(0, lab, a)
-    x_c = torch.zeros(C, x.shape[1], dtype=x.dtype).index_add_(0, lab, a[:, None] * x) / a_c[:, None]
-    return a_c, x_c, lab
+def ms_clusterize(a, x, scale=None, labels=None):
+    """Weighted centroids + summed weights per cluster (cluster_ranges_centroids); no autograd through them."""
+    lab = ms_grid_labels(x.detach(), scale) if labels is None else labels.long().view(-1)
+    a_d, x_d = a.detach(), x.detach()
+    a_c = torch.bincount(lab, weights=a_d)
+    a_c[a_c.abs() <= 1e-9] = 1e-9
+    x_c = torch.stack([torch.bincount(lab, weights=x_d[:, d] * a_d) / a_c for d in range(x.shape[1])], dim=1)
+    return a_c.to(a.dtype), x_c.to(x.dtype), lab
 
 
 def sinkhorn_multiscale_dense(a, x, b, y, p=2, blur=0.05, reach=None, diameter=None, scaling=0.5, truncate=5,
-                              cluster_scale=None, debias=True, potentials=False):
+                              cluster_scale=None, debias=True, potentials=False, labels_x=None, labels_y=None):
     """The reference's two-scale scheme on unbatched clouds, evaluated densely (no sort needed: the sort of
-    the reference only makes clusters contiguous for KeOps)."""
+    the reference only makes clusters contiguous for KeOps; the potentials are returned in input order, which
+    is what the reference's un-permutation :675-679 restores)."""
     diameter, eps_final, eps_list, rho = scaling_parameters(x, y, p, blur, reach, diameter, scaling)
     D = x.shape[1]
     if cluster_scale is None:
         cluster_scale = diameter / (np.sqrt(D) * 2000 ** (1 / D))
-    a_c, x_c, lab_x = ms_clusterize(a, x, cluster_scale)
-    b_c, y_c, lab_y = ms_clusterize(b, y, cluster_scale)
+    a_c, x_c, lab_x = ms_clusterize(a, x, cluster_scale, labels_x)
+    b_c, y_c, lab_y = ms_clusterize(b, y, cluster_scale, labels_y)
     jump = len(eps_list) - 1
-    for i, eps in enumerate(eps_list[2:]):
-        if cluster_scale**p > eps:
+    eps_value = eps_list[-1]  # the `eps` that leaks out of the search loop below (sinkhorn_samples.py:594-597)
+    for i, eps_i in enumerate(eps_list[2:]):
+        eps_value = eps_i
+        if cluster_scale**p > eps_i:
             jump = i + 1
             break
 
     def sm(eps, u, v, h, mask=None):
-        t = h[None, :] - cost_matrix(u, v, p) / eps
-        if mask is not None:
-            t = t.masked_fill(~mask, -float("inf"))
-        return -eps * torch.logsumexp(t, dim=1)
+        return keops_softmin(eps, u, v, h, p, mask)
 
-    ac_log, bc_log, a_log, b_log = log_weights(a_c), log_weights(b_c), log_weights(a), log_weights(b)
-    eps = eps_list[0]
-    lam = damping(eps, rho)
-    g_ab, f_ba = lam * sm(eps, y_c, x_c, ac_log), lam * sm(eps, x_c, y_c, bc_log)
-    f_aa, g_bb = lam * sm(eps, x_c, x_c, ac_log), lam * sm(eps, y_c, y_c, bc_log)
-    for i in range(jump + 1):
-        eps = eps_list[i]
+    ac_log, bc_log, a_log, b_log = log_weights(a_c), log_weights(b_c), log_weights(a.detach()), log_weights(b.detach())
+    xd, yd = x.detach(), y.detach()
+    with torch.no_grad():
+        eps = eps_list[0]
         lam = damping(eps, rho)
-        ft_ba = lam * sm(eps, x_c, y_c, bc_log + g_ab / eps)
-        gt_ab = lam * sm(eps, y_c, x_c, ac_log + f_ba / eps)
-        ft_aa = lam * sm(eps, x_c, x_c, ac_log + f_aa / eps)
-        gt_bb = lam * sm(eps, y_c, y_c, bc_log + g_bb / eps)
-        f_ba, g_ab = 0.5 * (f_ba + ft_ba), 0.5 * (g_ab + gt_ab)
-        f_aa, g_bb = 0.5 * (f_aa + ft_aa), 0.5 * (g_bb + gt_bb)
-    masks = {}
-    if jump < len(eps_list) - 1 and truncate is not None:
-        k_xy = f_ba[:, None] + g_ab[None, :] > cost_matrix(x_c, y_c, p) - truncate * eps
-        k_xx = f_aa[:, None] + f_aa[None, :] > cost_matrix(x_c, x_c, p) - truncate * eps
-        k_yy = g_bb[:, None] + g_bb[None, :] > cost_matrix(y_c, y_c, p) - truncate * eps
-        masks = {"xy": k_xy[lab_x][:, lab_y], "yx": k_xy.t()[lab_y][:, lab_x], "xx": k_xx[lab_x][:, lab_x],
-                 "yy": k_yy[lab_y][:, lab_y]}
-    # extrapolation: fine rows x coarse columns, all four from the OLD coarse potentials
-    f_ba, g_ab, f_aa, g_bb = (lam * sm(eps, x, y_c, bc_log + g_ab / eps), lam * sm(eps, y, x_c, ac_log + f_ba / eps),
-                              lam * sm(eps, x, x_c, ac_log + f_aa / eps), lam * sm(eps, y, y_c, bc_log + g_bb / eps))
-    if jump < len(eps_list) - 1:
-        for i in range(jump + 1, len(eps_list)):
+        g_ab, f_ba = lam * sm(eps, y_c, x_c, ac_log), lam * sm(eps, x_c, y_c, bc_log)
+        f_aa, g_bb = lam * sm(eps, x_c, x_c, ac_log), lam * sm(eps, y_c, y_c, bc_log)
+        for i in range(jump + 1):
             eps = eps_list[i]
             lam = damping(eps, rho)
-            ft_ba = lam * sm(eps, x, y, b_log + g_ab / eps, masks.get("xy"))
-            gt_ab = lam * sm(eps, y, x, a_log + f_ba / eps, masks.get("yx"))
-            ft_aa = lam * sm(eps, x, x, a_log + f_aa / eps, masks.get("xx"))
-            gt_bb = lam * sm(eps, y, y, b_log + g_bb / eps, masks.get("yy"))
+            ft_ba = lam * sm(eps, x_c, y_c, bc_log + g_ab / eps)
+            gt_ab = lam * sm(eps, y_c, x_c, ac_log + f_ba / eps)
+            ft_aa = lam * sm(eps, x_c, x_c, ac_log + f_aa / eps)
+            gt_bb = lam * sm(eps, y_c, y_c, bc_log + g_bb / eps)
             f_ba, g_ab = 0.5 * (f_ba + ft_ba), 0.5 * (g_ab + gt_ab)
             f_aa, g_bb = 0.5 * (f_aa + ft_aa), 0.5 * (g_bb + gt_bb)
-        f_ba, g_ab = (lam * sm(eps, x, y, b_log + g_ab / eps, masks.get("xy")),
-                      lam * sm(eps, y, x, a_log + f_ba / eps, masks.get("yx")))
-        f_aa = lam * sm(eps, x, x, a_log + f_aa / eps, masks.get("xx"))
-        g_bb = lam * sm(eps, y, y, b_log + g_bb / eps, masks.get("yy"))
-    out = sinkhorn_value(eps_final, rho, a[None], b[None], f_aa[None], g_bb[None], g_ab[None], f_ba[None],
+        masks = {}
+        if jump < len(eps_list) - 1 and truncate is not None:
+            # coarse cost through the tensorized (expansion, clamped) routine: cost_routines[p]
+            k_xy = f_ba[:, None] + g_ab[None, :] > cost_matrix(x_c, y_c, p) - truncate * eps
+            k_xx = f_aa[:, None] + f_aa[None, :] > cost_matrix(x_c, x_c, p) - truncate * eps
+            k_yy = g_bb[:, None] + g_bb[None, :] > cost_matrix(y_c, y_c, p) - truncate * eps
+            masks = {"xy": k_xy[lab_x][:, lab_y], "yx": k_xy.t()[lab_y][:, lab_x], "xx": k_xx[lab_x][:, lab_x],
+                     "yy": k_yy[lab_y][:, lab_y]}
+    last_is_jump = jump >= len(eps_list) - 1
+    # extrapolation: fine rows x coarse columns, all four from the OLD coarse potentials; it carries the graph
+    # when the jump is the last iteration (sinkhorn_divergence.py:520-526)
+    with torch.set_grad_enabled(last_is_jump and torch.is_grad_enabled()):
+        xr, yr = (x, y) if last_is_jump else (xd, yd)
+        f_ba, g_ab, f_aa, g_bb = (lam * sm(eps, xr, y_c, bc_log + g_ab / eps), lam * sm(eps, yr, x_c, ac_log + f_ba / eps),
+                                  lam * sm(eps, xr, x_c, ac_log + f_aa / eps), lam * sm(eps, yr, y_c, bc_log + g_bb / eps))
+    if not last_is_jump:
+        with torch.no_grad():
+            for i in range(jump + 1, len(eps_list)):
+                eps = eps_list[i]
+                lam = damping(eps, rho)
+                ft_ba = lam * sm(eps, xd, yd, b_log + g_ab / eps, masks.get("xy"))
+                gt_ab = lam * sm(eps, yd, xd, a_log + f_ba / eps, masks.get("yx"))
+                ft_aa = lam * sm(eps, xd, xd, a_log + f_aa / eps, masks.get("xx"))
+                gt_bb = lam * sm(eps, yd, yd, b_log + g_bb / eps, masks.get("yy"))
+                f_ba, g_ab = 0.5 * (f_ba + ft_ba), 0.5 * (g_ab + gt_ab)
+                f_aa, g_bb = 0.5 * (f_aa + ft_aa), 0.5 * (g_bb + gt_bb)
+        f_ba, g_ab = (lam * sm(eps, x, yd, (b_log + g_ab / eps).detach(), masks.get("xy")),
+                      lam * sm(eps, y, xd, (a_log + f_ba / eps).detach(), masks.get("yx")))
+        f_aa = lam * sm(eps, x, xd, (a_log + f_aa / eps).detach(), masks.get("xx"))
+        g_bb = lam * sm(eps, y, yd, (b_log + g_bb / eps).detach(), masks.get("yy"))
+    out = sinkhorn_value(eps_value, rho, a[None], b[None], f_aa[None], g_bb[None], g_ab[None], f_ba[None],
                          debias=debias, potentials=potentials)
     return (out[0][0], out[1][0]) if potentials else out[0]
+
+
+def kernel_multiscale_dense(a, x, b, y, name, blur=0.05, truncate=5, diameter=None, cluster_scale=None,
+                            potentials=False):
+    """Truncated block-sparse kernel norm on unbatched clouds.                   kernel_samples.py:177-271
+
+    Clusters are voxels of the blur-normalised, centred clouds; a cluster pair is kept when the squared
+    distance of its centroids (expansion form, utils.py:41-53) is <= (truncate + cell diagonal)^2."""
+    if truncate is None or name == "energy":
+        return mmd_online(a, x, b, y, name, blur=blur, potentials=potentials)
+    center = (x.mean(-2, keepdim=True) + y.mean(-2, keepdim=True)) / 2
+    x, y = x - center, y - center
+    x_, y_ = x / blur, y / blur
+    D = x.shape[-1]
+    if cluster_scale is None:
+        diameter = max_diameter(x_.detach(), y_.detach()) if diameter is None else diameter / blur
+        cluster_scale = diameter / (np.sqrt(D) * 2000 ** (1 / D))
+    cell = cluster_scale * np.sqrt(D)
+    _, x_c, lab_x = ms_clusterize(a, x_, cluster_scale)
+    _, y_c, lab_y = ms_clusterize(b, y_, cluster_scale)
+    thr = (truncate + cell) ** 2
+    k_xx, k_yy, k_xy = sqdist(x_c, x_c) <= thr, sqdist(y_c, y_c) <= thr, sqdist(x_c, y_c) <= thr
+    masks = (k_xx[lab_x][:, lab_x], k_yy[lab_y][:, lab_y], k_xy[lab_x][:, lab_y])
+    out = mmd_online(a, x, b, y, name, blur=blur, potentials=potentials, masks=masks)
+    if potentials:
+        # quirk kept: kernel_multiscale sorts the clouds by cluster (sort_clusters, :243-244) and never undoes
+        # the sort, so the potentials come back in CLUSTER-SORTED order; the order inside a cluster is whatever
+        # torch.sort (not stable) produced.  ``sorted_labels`` lets the tests compare cluster by cluster.
+        px, py = torch.sort(lab_x)[1], torch.sort(lab_y)[1]
+        return out[0][px], out[1][py], lab_x[px], lab_y[py]
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -593,8 +719,9 @@ def ot_solve_sample(X_a, X_b, a=None, b=None, debias=False, reg=None, unbalanced
 
 # ------------------------------------------------------------------------------------------------
 # ImagesBarycenter                          _legacy/wasserstein_barycenter_images.py:6-93
-# PARITY UNPINNED (the reference's softmin_grid needs pykeops); dense torch, differentiable end to end, so the
-# tests can check the CUDA path's closed-form softmin_grid backward against plain autograd.
+# PARITY PINNED: tests/golden/img_bary_*.npz (barycenters and autograd gradients of the unmodified reference on the
+# dense pykeops shim).  Dense torch, differentiable end to end, so the tests can check the CUDA path's closed-form
+# softmin_grid backward against plain autograd.
 # ------------------------------------------------------------------------------------------------
 def images_barycenter(measures, weights, blur=0, p=2, scaling_N=10, backward_iterations=5):
     sm = softmin_grid_dense

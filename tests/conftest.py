@@ -39,3 +39,13 @@ def load_golden(name):
 
 def golden_names(prefix):
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, prefix + "*.npz")))
+
+
+def golden_kwargs(g):
+    """Hyper-parameters stored as ``kw_<name>`` entries by make_golden_multiscale.py / make_golden_images.py."""
+    out = {}
+    for k, v in g.items():
+        if k.startswith("kw_"):
+            v = v.item()
+            out[k[3:]] = None if v == "None" else v
+    return out
