@@ -34,14 +34,18 @@ _SIGNATURES = {
     "b200ot_softmin_num_splits": (c_int32, [c_int64, c_int64, c_int32]),
     "b200ot_softmin_partial": (c_int32, [_P, _P, _P, _P, c_int32, c_int64, c_int64, c_int32, c_int32, c_float, _P]),
     "b200ot_softmin_finalize": (c_int32, [_P, c_int32, _P, c_float, c_float, _P, _P, c_int64, c_float, _P]),
-    "b200ot_sparse_tile_shape": (None, [ctypes.POINTER(c_int32), ctypes.POINTER(c_int32)]),
-    "b200ot_softmin_partial_sparse": (c_int32, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int32, c_int32, c_float,
-                                                _P]),
+    "b200ot_ranges_shape": (None, [c_int32, ctypes.POINTER(c_int32), ctypes.POINTER(c_int32),
+                                   ctypes.POINTER(c_int32)]),
+    "b200ot_softmin_pack_gather": (c_int32, [_P, _P, _P, c_float, _P, _P, c_int64, c_int32, c_int32, c_float, _P, _P]),
+    "b200ot_softmin_partial_ranges": (c_int32, [_P, _P, _P, _P, c_int64, _P, _P, c_int64, c_int32, c_int32, c_float,
+                                                c_int32, _P]),
     "b200ot_softmin_merge": (c_int32, [_P, c_int32, _P, c_int64, _P]),
     "b200ot_softmin_bwd_partial": (c_int32, [_P, _P, _P, _P, _P, c_int32, c_int64, c_int64, c_int32, c_int32,
                                              c_float, _P]),
-    "b200ot_softmin_bwd_partial_sparse": (c_int32, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int32, c_int32,
-                                                    c_float, _P]),
+    "b200ot_softmin_bwd_partial_ranges": (c_int32, [_P, _P, _P, _P, _P, c_int64, _P, _P, c_int64, c_int32, c_int32,
+                                                    c_float, c_int32, _P]),
+    "b200ot_softmin_bwd_sums": (c_int32, [_P, _P, _P, _P, c_float, _P, _P, _P, c_int64, c_int64, c_int32, c_int32,
+                                          c_float, _P, c_int64, _P]),
     "b200ot_rowsum_merge": (c_int32, [_P, c_int32, c_int32, _P, c_int64, _P]),
     "b200ot_softmin_bwd_finalize": (c_int32, [_P, c_int32, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_float, _P]),
     "b200ot_kernel_conv_scratch_bytes": (c_int64, [c_int64, c_int64, c_int32]),
@@ -49,6 +53,12 @@ _SIGNATURES = {
                                          c_int64, _P]),
     "b200ot_kernel_conv_bwd_x": (c_int32, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int32, c_int32, c_float, _P,
                                            c_int64, _P]),
+    "b200ot_kernel_conv_pack_gather": (c_int32, [_P, _P, _P, _P, c_int64, c_int32, c_int32, c_float, _P, _P]),
+    "b200ot_kernel_conv_partial_ranges": (c_int32, [_P, _P, _P, _P, c_int64, _P, _P, c_int64, c_int32, c_int32,
+                                                    c_float, c_int32, c_int32, _P]),
+    "b200ot_kernel_conv_finalize": (c_int32, [_P, c_int32, _P, c_int64, c_int32, _P]),
+    "b200ot_kernel_conv_bwd_finalize": (c_int32, [_P, c_int32, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_float,
+                                                  _P]),
     "b200ot_softmin_grid": (c_int32, [_P, _P, c_float, _P, c_float, c_float, _P, c_int64, c_int32, c_int32, c_int32,
                                       c_float, _P]),
     "b200ot_ubench": (c_int32, [c_int32, c_int32, c_int32, _P, ctypes.POINTER(c_int32), _P]),

@@ -23,8 +23,9 @@
 
 namespace b200ot {
 
-constexpr int kGridTW = 32;  // lines per CTA tile (one per lane)
-constexpr int kGridRS = kGridTW + 1;
+constexpr int kGridTW = 32;  // lines per CTA tile (one per lane); 16 for N > 880, where two 32-line tiles of
+                             // N x 33 floats no longer fit the 227 KB of shared memory (two lanes then share a
+                             // line and split its outputs)
 constexpr int kGridR = 8;  // outputs per thread per sweep
 constexpr int kGridWarps = 8;
 
@@ -38,13 +39,14 @@ struct GridPassArgs {
   int64_t outer, inner;
 };
 
-template <int P>
+template <int P, int TW>
 __global__ void __launch_bounds__(kGridWarps * 32) grid_pass_kernel(GridPassArgs A) {
+  constexpr int kGridTW = TW, kGridRS = TW + 1, NSUB = 32 / TW;
   extern __shared__ float smem_f[];
   float* tile = smem_f;                      // [N][33] inputs
   float* otile = smem_f + A.N * kGridRS;     // [N][33] outputs
   const int N = A.N;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = (threadIdx.x & 31) % TW, warp = (threadIdx.x >> 5) * NSUB + (threadIdx.x & 31) / TW;
   const bool last_axis = (A.inner == 1);
   int64_t o, w0;
   int nw;  // live lines in this tile
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(kGridWarps * 32) grid_pass_kernel(GridPassArgs
   __syncthreads();
 
   // ---- sweep: warp g owns outputs [g*per_warp, (g+1)*per_warp) of every line of the tile ----
-  const int per_warp = (N + kGridWarps - 1) / kGridWarps;
+  const int per_warp = (N + kGridWarps * NSUB - 1) / (kGridWarps * NSUB);
   const int i_end = min(N, (warp + 1) * per_warp);
   for (int ib = warp * per_warp; ib < i_end; ib += kGridR) {
     float xi[kGridR], m[kGridR], s[kGridR];
@@ -182,8 +184,10 @@ B200OT_API int b200ot_softmin_grid(const float* h_a, const float* h_b, float h_s
   // pixel coordinates x = arange(N)/N, scaled so that the log2-domain exponent is in - (X_i - X_j)^2  (p = 2)
   // or in - |X_i - X_j|  (p = 1)                                                          (utils.py:235-242)
   const float xscale = (p == 2 ? sqrtf(kLog2e / (2.0f * eps)) : kLog2e / eps) / (float)N;
-  const size_t smem = (size_t)2 * N * kGridRS * sizeof(float);
-  auto kern = (p == 2) ? grid_pass_kernel<2> : grid_pass_kernel<1>;
+  const int tw = ((size_t)2 * N * (kGridTW + 1) * sizeof(float) <= 227 * 1024) ? kGridTW : 16;
+  const size_t smem = (size_t)2 * N * (tw + 1) * sizeof(float);
+  auto kern = (tw == kGridTW) ? ((p == 2) ? grid_pass_kernel<2, kGridTW> : grid_pass_kernel<1, kGridTW>)
+                              : ((p == 2) ? grid_pass_kernel<2, 16> : grid_pass_kernel<1, 16>);
   B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // pass order of the reference: last axis first, then the others (the passes commute mathematically)
   for (int k = 0; k < dim; ++k) {
@@ -206,8 +210,7 @@ B200OT_API int b200ot_softmin_grid(const float* h_a, const float* h_b, float h_s
     for (int d = axis + 1; d < dim; ++d) inner *= N;
     a.inner = inner;
     a.outer = total / ((int64_t)N * inner);
-    const int64_t blocks =
-        (inner == 1) ? ceil_div64(a.outer, kGridTW) : a.outer * ceil_div64(inner, kGridTW);
+    const int64_t blocks = (inner == 1) ? ceil_div64(a.outer, tw) : a.outer * ceil_div64(inner, tw);
     kern<<<(unsigned)blocks, kGridWarps * 32, smem, st>>>(a);
     B200OT_CUDA_TRY(cudaGetLastError());
   }

@@ -23,8 +23,16 @@ struct ConvScales {
   int extra;
 };
 
-static ConvScales conv_scales(int kind, float blur) {
+// `kind` may carry B200OT_KERNEL_UNCLAMPED (laplacian / energy with pykeops' unclamped sqrt)
+static int kind_base(int kind) { return kind & 0xff; }
+static bool valid_kind(int kind) {
+  return kind_base(kind) >= 0 && kind_base(kind) <= 2 && (kind & ~(0xff | B200OT_KERNEL_UNCLAMPED)) == 0;
+}
+
+static ConvScales conv_scales(int kind_flags, float blur) {
   ConvScales c;
+  const int kind = kind_base(kind_flags);
+  const float clamp = cost_clamp(kind_flags);  // B200OT_KERNEL_UNCLAMPED == B200OT_P_UNCLAMPED
   if (kind == B200OT_KERNEL_GAUSSIAN) {
     c.scale = sqrtf(kLog2e) / blur;  // 2^(-|X-Y|^2/2) = exp(-|x-y|^2 / (2 blur^2))
     c.clampq = 0.f;
@@ -32,12 +40,12 @@ static ConvScales conv_scales(int kind, float blur) {
     c.extra = 2;
   } else if (kind == B200OT_KERNEL_LAPLACIAN) {
     c.scale = kLog2e / blur;  // 2^(-|X-Y|) = exp(-|x-y| / blur)
-    c.clampq = kLog2e * kLog2e * 1e-8f;
+    c.clampq = kLog2e * kLog2e * clamp;
     c.direct = 1;
     c.extra = 1;
   } else {
     c.scale = 1.f;
-    c.clampq = 1e-8f;
+    c.clampq = clamp;
     c.direct = 1;
     c.extra = 1;
   }
@@ -95,44 +103,68 @@ __global__ void absmax_kernel(const float* __restrict__ w, int64_t n, float* __r
 
 template <int MODE, int D>
 static int launch_rowsum(const ReducePlan& pl, cudaStream_t st, const float* x, const float* center, float scale,
-                         float clampq, const float* cols, float* part, int64_t N) {
+                         float clampq, const float* cols, float* part, int64_t N, const int4* seg = nullptr,
+                         const int2* pieces = nullptr) {
   if (pl.small) {
     using C = RowSumCfg<MODE, D, kSmallR, kSmallNT, kSmallTJ, 3, 4>;
     return launch_reduce<C>(rowsum_partial_kernel<C>, pl, st, x, center, scale, clampq, cols,
-                            (const float*)nullptr, part, N, pl.ntiles, pl.tiles_per_split, (const int*)nullptr, (const int*)nullptr);
+                            (const float*)nullptr, part, N, pl.ntiles, pl.tiles_per_split, seg, pieces);
   }
   // D >= 5: one row per thread (same 512 rows per CTA) keeps the 2 x (D+1) accumulator pairs in registers
   using C = std::conditional_t<(D <= 4), RowSumCfg<MODE, D, kBigR, kBigNT, kBigTJ, 3, 2>,
                                RowSumCfg<MODE, D, 1, kBigR * kBigNT, kBigTJ, 3, 1>>;
   return launch_reduce<C>(rowsum_partial_kernel<C>, pl, st, x, center, scale, clampq, cols, (const float*)nullptr,
-                          part, N, pl.ntiles, pl.tiles_per_split, (const int*)nullptr, (const int*)nullptr);
+                          part, N, pl.ntiles, pl.tiles_per_split, seg, pieces);
 }
 
 template <int MODE>
 static int launch_rowsum_d(int D, const ReducePlan& pl, cudaStream_t st, const float* x, const float* center,
-                           float scale, float clampq, const float* cols, float* part, int64_t N) {
+                           float scale, float clampq, const float* cols, float* part, int64_t N,
+                           const int4* seg = nullptr, const int2* pieces = nullptr) {
   switch (D) {
-    case 1: return launch_rowsum<MODE, 1>(pl, st, x, center, scale, clampq, cols, part, N);
-    case 2: return launch_rowsum<MODE, 2>(pl, st, x, center, scale, clampq, cols, part, N);
-    case 3: return launch_rowsum<MODE, 3>(pl, st, x, center, scale, clampq, cols, part, N);
-    case 4: return launch_rowsum<MODE, 4>(pl, st, x, center, scale, clampq, cols, part, N);
-    case 5: return launch_rowsum<MODE, 5>(pl, st, x, center, scale, clampq, cols, part, N);
-    case 6: return launch_rowsum<MODE, 6>(pl, st, x, center, scale, clampq, cols, part, N);
-    case 7: return launch_rowsum<MODE, 7>(pl, st, x, center, scale, clampq, cols, part, N);
-    case 8: return launch_rowsum<MODE, 8>(pl, st, x, center, scale, clampq, cols, part, N);
+    case 1: return launch_rowsum<MODE, 1>(pl, st, x, center, scale, clampq, cols, part, N, seg, pieces);
+    case 2: return launch_rowsum<MODE, 2>(pl, st, x, center, scale, clampq, cols, part, N, seg, pieces);
+    case 3: return launch_rowsum<MODE, 3>(pl, st, x, center, scale, clampq, cols, part, N, seg, pieces);
+    case 4: return launch_rowsum<MODE, 4>(pl, st, x, center, scale, clampq, cols, part, N, seg, pieces);
+    case 5: return launch_rowsum<MODE, 5>(pl, st, x, center, scale, clampq, cols, part, N, seg, pieces);
+    case 6: return launch_rowsum<MODE, 6>(pl, st, x, center, scale, clampq, cols, part, N, seg, pieces);
+    case 7: return launch_rowsum<MODE, 7>(pl, st, x, center, scale, clampq, cols, part, N, seg, pieces);
+    case 8: return launch_rowsum<MODE, 8>(pl, st, x, center, scale, clampq, cols, part, N, seg, pieces);
     default: return B200OT_EINVAL;
   }
 }
 
 static int conv_pack(const float* y, const float* w, const float* center, int64_t M, int D, const ConvScales& cs,
-                     float* cols, cudaStream_t st) {
+                     float* cols, cudaStream_t st, const int* src = nullptr) {
   const int nf2 = colfmt_nf2(D, cs.extra);
   const int64_t mpad = round_up64(M, kPackPad);
   const int threads = 256;
   pack_cols_kernel<<<(unsigned)ceil_div64(mpad, threads), threads, 0, st>>>(
-      y, nullptr, nullptr, 0.f, 0.f, w, center, cs.scale, cs.direct, D, nf2, M, mpad, cols);
+      y, nullptr, nullptr, 0.f, 0.f, w, center, cs.scale, cs.direct, D, nf2, M, mpad, cols, src);
   B200OT_CUDA_TRY(cudaGetLastError());
   return B200OT_OK;
+}
+
+// the N x M launch of a CUDA-core kernel convolution (dense plan, or ranges when seg != null)
+static int conv_partial(int kind_flags, bool bwd, const ReducePlan& pl, cudaStream_t st, const float* x,
+                        const float* center, const ConvScales& cs, const float* cols, float* part, int64_t N, int D,
+                        const int4* seg = nullptr, const int2* pieces = nullptr) {
+  const int kind = kind_base(kind_flags);
+  if (kind == B200OT_KERNEL_GAUSSIAN)
+    return bwd ? launch_rowsum_d<kGaussBwd>(D, pl, st, x, center, cs.scale, cs.clampq, cols, part, N, seg, pieces)
+               : launch_rowsum_d<kGaussFwd>(D, pl, st, x, center, cs.scale, cs.clampq, cols, part, N, seg, pieces);
+  if (kind == B200OT_KERNEL_LAPLACIAN)
+    return bwd ? launch_rowsum_d<kLaplaceBwd>(D, pl, st, x, center, cs.scale, cs.clampq, cols, part, N, seg, pieces)
+               : launch_rowsum_d<kLaplaceFwd>(D, pl, st, x, center, cs.scale, cs.clampq, cols, part, N, seg, pieces);
+  return bwd ? launch_rowsum_d<kEnergyBwd>(D, pl, st, x, center, cs.scale, cs.clampq, cols, part, N, seg, pieces)
+             : launch_rowsum_d<kEnergyFwd>(D, pl, st, x, center, cs.scale, cs.clampq, cols, part, N, seg, pieces);
+}
+
+static float conv_bwd_coef(int kind_flags, const ConvScales& cs, float blur) {
+  const int kind = kind_base(kind_flags);
+  if (kind == B200OT_KERNEL_GAUSSIAN) return 1.0f / (cs.scale * blur * blur);
+  if (kind == B200OT_KERNEL_LAPLACIAN) return -1.0f / blur;
+  return -1.0f;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -301,14 +333,66 @@ B200OT_API int64_t b200ot_kernel_conv_scratch_bytes(int64_t N, int64_t M, int32_
   return round_up64(cols, 256) + round_up64(part, 256);
 }
 
+B200OT_API int b200ot_kernel_conv_finalize(const float* part, int32_t n_part, float* out, int64_t N, int32_t kind,
+                                           void* stream) {
+  if (!part || !out || n_part <= 0 || N <= 0 || !valid_kind(kind)) return B200OT_EINVAL;
+  const int threads = 256;
+  conv_fwd_finalize_kernel<<<(unsigned)ceil_div64(N, threads), threads, 0, (cudaStream_t)stream>>>(
+      part, n_part, kind_base(kind) == B200OT_KERNEL_ENERGY ? -1.f : 1.f, out, N);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  return B200OT_OK;
+}
+
+B200OT_API int b200ot_kernel_conv_bwd_finalize(const float* part, int32_t n_part, const float* x, const float* center,
+                                               const float* grad_out, float* grad_x, int64_t N, int32_t D,
+                                               int32_t kind, float blur, void* stream) {
+  if (!part || !x || !grad_out || !grad_x || n_part <= 0 || N <= 0 || !supported_simt_dim(D) || !valid_kind(kind))
+    return B200OT_EINVAL;
+  if (kind_base(kind) != B200OT_KERNEL_ENERGY && !(blur > 0.f)) return B200OT_EINVAL;
+  const ConvScales cs = conv_scales(kind, blur);
+  const int threads = 256;
+  conv_bwd_finalize_kernel<<<(unsigned)ceil_div64(N, threads), threads, 0, (cudaStream_t)stream>>>(
+      part, n_part, x, center, grad_out, grad_x, N, D, kind_base(kind), cs.scale, conv_bwd_coef(kind, cs, blur),
+      (const float*)nullptr);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  return B200OT_OK;
+}
+
+B200OT_API int b200ot_kernel_conv_pack_gather(const float* y, const float* w, const float* center,
+                                              const int32_t* src_index, int64_t n_slots, int32_t D, int32_t kind,
+                                              float blur, float* cols_out, void* stream) {
+  if (!y || !w || !src_index || !cols_out || n_slots <= 0 || !supported_simt_dim(D) || !valid_kind(kind))
+    return B200OT_EINVAL;
+  if (kind_base(kind) != B200OT_KERNEL_ENERGY && !(blur > 0.f)) return B200OT_EINVAL;
+  if (((uintptr_t)cols_out) & 15) return B200OT_EALIGN;
+  return conv_pack(y, w, center, n_slots, D, conv_scales(kind, blur), cols_out, (cudaStream_t)stream,
+                   reinterpret_cast<const int*>(src_index));
+}
+
+// part: (N) sums (forward) or (N, width) sums (row gradients: width = D + 1 gaussian, D otherwise)
+B200OT_API int b200ot_kernel_conv_partial_ranges(const float* x, const float* center, const float* cols,
+                                                 const b200ot_segment* seg, int64_t n_seg,
+                                                 const b200ot_piece* pieces, float* part, int64_t N, int32_t D,
+                                                 int32_t kind, float blur, int32_t backward, int32_t variant,
+                                                 void* stream) {
+  if (!x || !cols || !seg || !pieces || !part || N <= 0 || n_seg <= 0 || n_seg > 0x7fffffff ||
+      !supported_simt_dim(D) || !valid_kind(kind) ||
+      (variant != B200OT_RANGES_BIG && variant != B200OT_RANGES_SMALL))
+    return B200OT_EINVAL;
+  if (kind_base(kind) != B200OT_KERNEL_ENERGY && !(blur > 0.f)) return B200OT_EINVAL;
+  if ((((uintptr_t)cols) & 15) || (((uintptr_t)seg) & 15) || (((uintptr_t)pieces) & 7)) return B200OT_EALIGN;
+  return conv_partial(kind, backward != 0, ranges_plan(variant, n_seg), (cudaStream_t)stream, x, center,
+                      conv_scales(kind, blur), cols, part, N, D, reinterpret_cast<const int4*>(seg),
+                      reinterpret_cast<const int2*>(pieces));
+}
+
 B200OT_API int b200ot_kernel_conv_fwd(const float* x, const float* y, const float* w, const float* center,
                                       float* out, int64_t N, int64_t M, int32_t D, int32_t kind, float blur,
                                       void* scratch, int64_t scratch_bytes, void* stream) {
-  const bool tc = (kind == B200OT_KERNEL_GAUSSIAN) && tc_supported_dim(D);
-  if (!x || !y || !w || !out || !scratch || N <= 0 || M <= 0 || (!supported_simt_dim(D) && !tc) || kind < 0 ||
-      kind > 2)
+  const bool tc = (kind_base(kind) == B200OT_KERNEL_GAUSSIAN) && tc_supported_dim(D);
+  if (!x || !y || !w || !out || !scratch || N <= 0 || M <= 0 || (!supported_simt_dim(D) && !tc) || !valid_kind(kind))
     return B200OT_EINVAL;
-  if (kind != B200OT_KERNEL_ENERGY && !(blur > 0.f)) return B200OT_EINVAL;
+  if (kind_base(kind) != B200OT_KERNEL_ENERGY && !(blur > 0.f)) return B200OT_EINVAL;
   if (((uintptr_t)scratch) & 15) return B200OT_EALIGN;
   if (scratch_bytes < b200ot_kernel_conv_scratch_bytes(N, M, D)) return B200OT_ESCRATCH;
   if (tc) return conv_fwd_tc(x, y, w, center, out, N, M, D, blur, scratch, (cudaStream_t)stream);
@@ -320,29 +404,20 @@ B200OT_API int b200ot_kernel_conv_fwd(const float* x, const float* y, const floa
   cudaStream_t st = (cudaStream_t)stream;
   int rc = conv_pack(y, w, center, M, D, cs, cols, st);
   if (rc) return rc;
-  if (kind == B200OT_KERNEL_GAUSSIAN)
-    rc = launch_rowsum_d<kGaussFwd>(D, pl, st, x, center, cs.scale, cs.clampq, cols, part, N);
-  else if (kind == B200OT_KERNEL_LAPLACIAN)
-    rc = launch_rowsum_d<kLaplaceFwd>(D, pl, st, x, center, cs.scale, cs.clampq, cols, part, N);
-  else
-    rc = launch_rowsum_d<kEnergyFwd>(D, pl, st, x, center, cs.scale, cs.clampq, cols, part, N);
+  rc = conv_partial(kind, false, pl, st, x, center, cs, cols, part, N, D);
   if (rc) return rc;
-  const int threads = 256;
-  conv_fwd_finalize_kernel<<<(unsigned)ceil_div64(N, threads), threads, 0, st>>>(
-      part, pl.n_split, kind == B200OT_KERNEL_ENERGY ? -1.f : 1.f, out, N);
-  B200OT_CUDA_TRY(cudaGetLastError());
-  return B200OT_OK;
+  return b200ot_kernel_conv_finalize(part, pl.n_split, out, N, kind, stream);
 }
 
 B200OT_API int b200ot_kernel_conv_bwd_x(const float* x, const float* y, const float* w, const float* center,
                                         const float* grad_out, float* grad_x, int64_t N, int64_t M, int32_t D,
                                         int32_t kind, float blur, void* scratch, int64_t scratch_bytes,
                                         void* stream) {
-  const bool tc = (kind == B200OT_KERNEL_GAUSSIAN) && tc_supported_dim(D);
+  const bool tc = (kind_base(kind) == B200OT_KERNEL_GAUSSIAN) && tc_supported_dim(D);
   if (!x || !y || !w || !grad_out || !grad_x || !scratch || N <= 0 || M <= 0 || (!supported_simt_dim(D) && !tc) ||
-      kind < 0 || kind > 2)
+      !valid_kind(kind))
     return B200OT_EINVAL;
-  if (kind != B200OT_KERNEL_ENERGY && !(blur > 0.f)) return B200OT_EINVAL;
+  if (kind_base(kind) != B200OT_KERNEL_ENERGY && !(blur > 0.f)) return B200OT_EINVAL;
   if (((uintptr_t)scratch) & 15) return B200OT_EALIGN;
   if (scratch_bytes < b200ot_kernel_conv_scratch_bytes(N, M, D)) return B200OT_ESCRATCH;
   if (tc) {
@@ -354,7 +429,7 @@ B200OT_API int b200ot_kernel_conv_bwd_x(const float* x, const float* y, const fl
                                   &tc_part, &n_part, (cudaStream_t)stream, &w_absmax);
     if (rc) return rc;
     conv_bwd_finalize_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, (cudaStream_t)stream>>>(
-        tc_part, n_part, x, center, grad_out, grad_x, N, D, kind, scale, 1.0f / (scale * blur * blur), w_absmax);
+        tc_part, n_part, x, center, grad_out, grad_x, N, D, 0, scale, 1.0f / (scale * blur * blur), w_absmax);
     B200OT_CUDA_TRY(cudaGetLastError());
     return B200OT_OK;
   }
@@ -366,23 +441,9 @@ B200OT_API int b200ot_kernel_conv_bwd_x(const float* x, const float* y, const fl
   cudaStream_t st = (cudaStream_t)stream;
   int rc = conv_pack(y, w, center, M, D, cs, cols, st);
   if (rc) return rc;
-  float coef;
-  if (kind == B200OT_KERNEL_GAUSSIAN) {
-    rc = launch_rowsum_d<kGaussBwd>(D, pl, st, x, center, cs.scale, cs.clampq, cols, part, N);
-    coef = 1.0f / (cs.scale * blur * blur);
-  } else if (kind == B200OT_KERNEL_LAPLACIAN) {
-    rc = launch_rowsum_d<kLaplaceBwd>(D, pl, st, x, center, cs.scale, cs.clampq, cols, part, N);
-    coef = -1.0f / blur;
-  } else {
-    rc = launch_rowsum_d<kEnergyBwd>(D, pl, st, x, center, cs.scale, cs.clampq, cols, part, N);
-    coef = -1.0f;
-  }
+  rc = conv_partial(kind, true, pl, st, x, center, cs, cols, part, N, D);
   if (rc) return rc;
-  const int threads = 256;
-  conv_bwd_finalize_kernel<<<(unsigned)ceil_div64(N, threads), threads, 0, st>>>(
-      part, pl.n_split, x, center, grad_out, grad_x, N, D, kind, cs.scale, coef, (const float*)nullptr);
-  B200OT_CUDA_TRY(cudaGetLastError());
-  return B200OT_OK;
+  return b200ot_kernel_conv_bwd_finalize(part, pl.n_split, x, center, grad_out, grad_x, N, D, kind, blur, stream);
 }
 
 }  // extern "C"

@@ -77,51 +77,57 @@ struct Variants {
 
 template <class C>
 static int launch_partial(const float* x, const float* center, float scale, float clampq, const float* cols,
-                          float* part, const ReducePlan& pl, int64_t N, cudaStream_t st) {
+                          float* part, const ReducePlan& pl, int64_t N, cudaStream_t st, const int4* seg,
+                          const int2* pieces) {
   return launch_reduce<C>(softmin_partial_kernel<C>, pl, st, x, center, scale, clampq, cols,
-                          reinterpret_cast<float2*>(part), N, pl.ntiles, pl.tiles_per_split, (const int*)nullptr,
-                          (const int*)nullptr);
+                          reinterpret_cast<float2*>(part), N, pl.ntiles, pl.tiles_per_split, seg, pieces);
 }
 
 template <int D>
 static int partial_for_d(int p, const float* x, const float* center, float scale, float clampq, const float* cols,
-                         float* part, const ReducePlan& pl, int64_t N, cudaStream_t st) {
+                         float* part, const ReducePlan& pl, int64_t N, cudaStream_t st, const int4* seg,
+                         const int2* pieces) {
   if (p == 2) {
     using V = Variants<D, 2, false>;
-    return pl.small ? launch_partial<typename V::Small>(x, center, scale, clampq, cols, part, pl, N, st)
-                    : launch_partial<typename V::Big>(x, center, scale, clampq, cols, part, pl, N, st);
+    return pl.small ? launch_partial<typename V::Small>(x, center, scale, clampq, cols, part, pl, N, st, seg, pieces)
+                    : launch_partial<typename V::Big>(x, center, scale, clampq, cols, part, pl, N, st, seg, pieces);
   } else {
     using V = Variants<D, 1, true>;
-    return pl.small ? launch_partial<typename V::Small>(x, center, scale, clampq, cols, part, pl, N, st)
-                    : launch_partial<typename V::Big>(x, center, scale, clampq, cols, part, pl, N, st);
+    return pl.small ? launch_partial<typename V::Small>(x, center, scale, clampq, cols, part, pl, N, st, seg, pieces)
+                    : launch_partial<typename V::Big>(x, center, scale, clampq, cols, part, pl, N, st, seg, pieces);
   }
 }
 
+// `p` may carry B200OT_P_UNCLAMPED; M = number of column slots (gather mode: src maps slots to columns)
 int softmin_pack_impl(const float* y, const float* h_a, const float* h_b, float h_scale_b, const float* center,
-                      int64_t M, int D, int p, float eps, float* cols_out, cudaStream_t st) {
+                      int64_t M, int D, int p, float eps, float* cols_out, cudaStream_t st, const int* src) {
+  const int pe = p_exponent(p);
   const int nf2 = colfmt_nf2(D, 1);
   const int64_t mpad = round_up64(M, kPackPad);
   const int threads = 256;
   pack_cols_kernel<<<(unsigned)ceil_div64(mpad, threads), threads, 0, st>>>(
-      y, h_a, h_b, h_scale_b, kLog2e, nullptr, center, softmin_coord_scale(p, eps), p == 1 ? 1 : 0, D, nf2, M, mpad,
-      cols_out);
+      y, h_a, h_b, h_scale_b, kLog2e, nullptr, center, softmin_coord_scale(pe, eps), pe == 1 ? 1 : 0, D, nf2, M,
+      mpad, cols_out, src);
   B200OT_CUDA_TRY(cudaGetLastError());
   return B200OT_OK;
 }
 
 static int softmin_partial_impl(const float* x, const float* center, const float* cols, float* part,
-                                const ReducePlan& pl, int64_t N, int D, int p, float eps, cudaStream_t st) {
-  const float scale = softmin_coord_scale(p, eps);
-  const float clampq = scale * scale * 1e-8f;  // reference clamp on |x-y|^2 (utils.py:61), in scaled units
+                                const ReducePlan& pl, int64_t N, int D, int p, float eps, cudaStream_t st,
+                                const int4* seg = nullptr, const int2* pieces = nullptr) {
+  const int pe = p_exponent(p);
+  const float scale = softmin_coord_scale(pe, eps);
+  // reference clamp on |x-y|^2 (utils.py:61) — or none (pykeops' Norm2) — in scaled units
+  const float clampq = scale * scale * cost_clamp(p);
   switch (D) {
-    case 1: return partial_for_d<1>(p, x, center, scale, clampq, cols, part, pl, N, st);
-    case 2: return partial_for_d<2>(p, x, center, scale, clampq, cols, part, pl, N, st);
-    case 3: return partial_for_d<3>(p, x, center, scale, clampq, cols, part, pl, N, st);
-    case 4: return partial_for_d<4>(p, x, center, scale, clampq, cols, part, pl, N, st);
-    case 5: return partial_for_d<5>(p, x, center, scale, clampq, cols, part, pl, N, st);
-    case 6: return partial_for_d<6>(p, x, center, scale, clampq, cols, part, pl, N, st);
-    case 7: return partial_for_d<7>(p, x, center, scale, clampq, cols, part, pl, N, st);
-    case 8: return partial_for_d<8>(p, x, center, scale, clampq, cols, part, pl, N, st);
+    case 1: return partial_for_d<1>(pe, x, center, scale, clampq, cols, part, pl, N, st, seg, pieces);
+    case 2: return partial_for_d<2>(pe, x, center, scale, clampq, cols, part, pl, N, st, seg, pieces);
+    case 3: return partial_for_d<3>(pe, x, center, scale, clampq, cols, part, pl, N, st, seg, pieces);
+    case 4: return partial_for_d<4>(pe, x, center, scale, clampq, cols, part, pl, N, st, seg, pieces);
+    case 5: return partial_for_d<5>(pe, x, center, scale, clampq, cols, part, pl, N, st, seg, pieces);
+    case 6: return partial_for_d<6>(pe, x, center, scale, clampq, cols, part, pl, N, st, seg, pieces);
+    case 7: return partial_for_d<7>(pe, x, center, scale, clampq, cols, part, pl, N, st, seg, pieces);
+    case 8: return partial_for_d<8>(pe, x, center, scale, clampq, cols, part, pl, N, st, seg, pieces);
     default: return B200OT_EINVAL;
   }
 }
@@ -156,16 +162,16 @@ B200OT_API int64_t b200ot_softmin_scratch_bytes(int64_t N, int64_t M, int32_t D)
 B200OT_API int b200ot_softmin_pack(const float* y, const float* h_a, const float* h_b, float h_scale_b,
                                    const float* center, int64_t M, int32_t D, int32_t p, float eps,
                                    float* cols_out, void* stream) {
-  if (!y || !h_a || !cols_out || M <= 0 || !supported_simt_dim(D) || (p != 1 && p != 2) || !(eps > 0.f))
+  if (!y || !h_a || !cols_out || M <= 0 || !supported_simt_dim(D) || !valid_p(p) || !(eps > 0.f))
     return B200OT_EINVAL;
   if (((uintptr_t)cols_out) & 15) return B200OT_EALIGN;
-  return softmin_pack_impl(y, h_a, h_b, h_scale_b, center, M, D, p, eps, cols_out, (cudaStream_t)stream);
+  return softmin_pack_impl(y, h_a, h_b, h_scale_b, center, M, D, p, eps, cols_out, (cudaStream_t)stream, nullptr);
 }
 
 B200OT_API int b200ot_softmin_partial(const float* x, const float* center, const float* cols, float* part,
                                       int32_t n_split, int64_t N, int64_t M, int32_t D, int32_t p, float eps,
                                       void* stream) {
-  if (!x || !cols || !part || N <= 0 || M <= 0 || !supported_simt_dim(D) || (p != 1 && p != 2) || !(eps > 0.f))
+  if (!x || !cols || !part || N <= 0 || M <= 0 || !supported_simt_dim(D) || !valid_p(p) || !(eps > 0.f))
     return B200OT_EINVAL;
   if ((((uintptr_t)cols) & 15) || (((uintptr_t)part) & 7)) return B200OT_EALIGN;
   const ReducePlan pl = make_plan(N, M);
@@ -173,48 +179,37 @@ B200OT_API int b200ot_softmin_partial(const float* x, const float* center, const
   return softmin_partial_impl(x, center, cols, part, pl, N, D, p, eps, (cudaStream_t)stream);
 }
 
-B200OT_API void b200ot_sparse_tile_shape(int32_t* rows_per_tile, int32_t* cols_per_tile) {
-  if (rows_per_tile) *rows_per_tile = kBigNT * kBigR;
-  if (cols_per_tile) *cols_per_tile = kBigTJ;
+B200OT_API void b200ot_ranges_shape(int32_t variant, int32_t* max_rows_per_segment, int32_t* max_cols_per_piece,
+                                    int32_t* col_align) {
+  const bool small = (variant == B200OT_RANGES_SMALL);
+  if (max_rows_per_segment) *max_rows_per_segment = small ? kSmallNT * kSmallR : kBigNT * kBigR;
+  if (max_cols_per_piece) *max_cols_per_piece = small ? kSmallTJ : kBigTJ;
+  if (col_align) *col_align = kRangesAlign;
 }
 
-B200OT_API int b200ot_softmin_partial_sparse(const float* x, const float* center, const float* cols,
-                                             const int32_t* tile_ptr, const int32_t* tile_list, float* part,
-                                             int64_t N, int64_t M, int32_t D, int32_t p, float eps, void* stream) {
-  if (!x || !cols || !tile_ptr || !tile_list || !part || N <= 0 || M <= 0 || !supported_simt_dim(D) ||
-      (p != 1 && p != 2) || !(eps > 0.f))
+B200OT_API int b200ot_softmin_pack_gather(const float* y, const float* h_a, const float* h_b, float h_scale_b,
+                                          const float* center, const int32_t* src_index, int64_t n_slots, int32_t D,
+                                          int32_t p, float eps, float* cols_out, void* stream) {
+  if (!y || !h_a || !src_index || !cols_out || n_slots <= 0 || !supported_simt_dim(D) || !valid_p(p) || !(eps > 0.f))
     return B200OT_EINVAL;
-  if ((((uintptr_t)cols) & 15) || (((uintptr_t)part) & 7)) return B200OT_EALIGN;
-  ReducePlan pl;
-  pl.small = false;
-  pl.tj = kBigTJ;
-  pl.rows_cta = kBigNT * kBigR;
-  pl.ntiles = (int)(round_up64(M, kBigTJ) / kBigTJ);
-  pl.tiles_per_split = pl.ntiles;
-  pl.n_split = 1;
-  pl.row_tiles = ceil_div64(N, pl.rows_cta);
-  const float scale = softmin_coord_scale(p, eps);
-  const float clampq = scale * scale * 1e-8f;
-  cudaStream_t st = (cudaStream_t)stream;
-  auto go = [&](auto cfg) -> int {
-    using C = decltype(cfg);
-    return launch_reduce<C>(softmin_partial_kernel<C>, pl, st, x, center, scale, clampq, cols,
-                            reinterpret_cast<float2*>(part), N, pl.ntiles, pl.tiles_per_split,
-                            reinterpret_cast<const int*>(tile_ptr), reinterpret_cast<const int*>(tile_list));
-  };
-  if (D > 3) return B200OT_EINVAL;  // multiscale clustering is a low-dimensional device (reference: D <= 3)
-  if (p == 2) {
-    switch (D) {
-      case 1: return go(typename Variants<1, 2, false>::Big{});
-      case 2: return go(typename Variants<2, 2, false>::Big{});
-      default: return go(typename Variants<3, 2, false>::Big{});
-    }
-  }
-  switch (D) {
-    case 1: return go(typename Variants<1, 1, true>::Big{});
-    case 2: return go(typename Variants<2, 1, true>::Big{});
-    default: return go(typename Variants<3, 1, true>::Big{});
-  }
+  if (((uintptr_t)cols_out) & 15) return B200OT_EALIGN;
+  return softmin_pack_impl(y, h_a, h_b, h_scale_b, center, n_slots, D, p, eps, cols_out, (cudaStream_t)stream,
+                           reinterpret_cast<const int*>(src_index));
+}
+
+B200OT_API int b200ot_softmin_partial_ranges(const float* x, const float* center, const float* cols,
+                                             const b200ot_segment* seg, int64_t n_seg, const b200ot_piece* pieces,
+                                             float* part, int64_t N, int32_t D, int32_t p, float eps,
+                                             int32_t variant, void* stream) {
+  if (!x || !cols || !seg || !pieces || !part || N <= 0 || n_seg <= 0 || n_seg > 0x7fffffff ||
+      !supported_simt_dim(D) || !valid_p(p) || !(eps > 0.f) ||
+      (variant != B200OT_RANGES_BIG && variant != B200OT_RANGES_SMALL))
+    return B200OT_EINVAL;
+  if ((((uintptr_t)cols) & 15) || (((uintptr_t)part) & 7) || (((uintptr_t)seg) & 15) || (((uintptr_t)pieces) & 7))
+    return B200OT_EALIGN;
+  const ReducePlan pl = ranges_plan(variant, n_seg);
+  return softmin_partial_impl(x, center, cols, part, pl, N, D, p, eps, (cudaStream_t)stream,
+                              reinterpret_cast<const int4*>(seg), reinterpret_cast<const int2*>(pieces));
 }
 
 B200OT_API int b200ot_softmin_merge(const float* part, int32_t n_part, float* merged, int64_t N, void* stream) {
@@ -243,8 +238,8 @@ B200OT_API int b200ot_softmin_fwd(const float* x, const float* y, const float* h
                                   float h_scale_b, const float* center, const float* out_old, float alpha_old,
                                   float beta, float* out, float* lse2_out, int64_t N, int64_t M, int32_t D,
                                   int32_t p, float eps, void* scratch, int64_t scratch_bytes, void* stream) {
-  const bool tc = tc_supported_dim(D) && p == 2;  // 8 < D <= 64: exponent from the tensor cores (tcconv.cuh)
-  if (!x || !y || !h_a || !scratch || N <= 0 || M <= 0 || (!supported_simt_dim(D) && !tc) || (p != 1 && p != 2) ||
+  const bool tc = tc_supported_dim(D) && p_exponent(p) == 2;  // 8 < D <= 64: exponent from the tensor cores (tcconv.cuh)
+  if (!x || !y || !h_a || !scratch || N <= 0 || M <= 0 || (!supported_simt_dim(D) && !tc) || !valid_p(p) ||
       !(eps > 0.f) || (!out && !lse2_out))
     return B200OT_EINVAL;
   if (((uintptr_t)scratch) & 15) return B200OT_EALIGN;
@@ -262,7 +257,7 @@ B200OT_API int b200ot_softmin_fwd(const float* x, const float* y, const float* h
   float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) +
                                          round_up64(b200ot_packed_cols_floats(M, D, 1) * 4, 256));
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = softmin_pack_impl(y, h_a, h_b, h_scale_b, center, M, D, p, eps, cols, st);
+  int rc = softmin_pack_impl(y, h_a, h_b, h_scale_b, center, M, D, p, eps, cols, st, nullptr);
   if (rc) return rc;
   rc = softmin_partial_impl(x, center, cols, part, pl, N, D, p, eps, st);
   if (rc) return rc;

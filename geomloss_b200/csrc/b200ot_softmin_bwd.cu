@@ -23,7 +23,8 @@ __global__ void softmin_bwd_finalize_kernel(const float* __restrict__ part, int 
   const int na = D + 1;
   float sw = 0.f;
   for (int s = 0; s < n_split; ++s) sw += part[((int64_t)s * N + i) * na];
-  const float inv = 1.0f / sw;
+  // a row whose (block-sparse) column list is empty has no weight at all: zero gradient, not 0/0
+  const float inv = sw > 0.f ? 1.0f / sw : 0.f;
   const float go = grad_out[i];
   for (int k = 0; k < D; ++k) {
     float a = 0.f;
@@ -52,7 +53,7 @@ __global__ void rowsum_merge_kernel(const float* __restrict__ part, int n_part, 
 template <int MODE, int D>
 static int launch_rowsum(const ReducePlan& pl, cudaStream_t st, const float* x, const float* center, float scale,
                          float clampq, const float* cols, const float* lse2, float* part, int64_t N,
-                         const int* tile_ptr = nullptr, const int* tile_list = nullptr) {
+                         const int4* tile_ptr = nullptr, const int2* tile_list = nullptr) {
   if (pl.small) {
     using C = RowSumCfg<MODE, D, kSmallR, kSmallNT, kSmallTJ, 3, 4>;
     return launch_reduce<C>(rowsum_partial_kernel<C>, pl, st, x, center, scale, clampq, cols, lse2, part, N,
@@ -68,16 +69,16 @@ static int launch_rowsum(const ReducePlan& pl, cudaStream_t st, const float* x, 
 template <int MODE>
 static int launch_rowsum_d(int D, const ReducePlan& pl, cudaStream_t st, const float* x, const float* center,
                            float scale, float clampq, const float* cols, const float* lse2, float* part,
-                           int64_t N) {
+                           int64_t N, const int4* seg = nullptr, const int2* pieces = nullptr) {
   switch (D) {
-    case 1: return launch_rowsum<MODE, 1>(pl, st, x, center, scale, clampq, cols, lse2, part, N);
-    case 2: return launch_rowsum<MODE, 2>(pl, st, x, center, scale, clampq, cols, lse2, part, N);
-    case 3: return launch_rowsum<MODE, 3>(pl, st, x, center, scale, clampq, cols, lse2, part, N);
-    case 4: return launch_rowsum<MODE, 4>(pl, st, x, center, scale, clampq, cols, lse2, part, N);
-    case 5: return launch_rowsum<MODE, 5>(pl, st, x, center, scale, clampq, cols, lse2, part, N);
-    case 6: return launch_rowsum<MODE, 6>(pl, st, x, center, scale, clampq, cols, lse2, part, N);
-    case 7: return launch_rowsum<MODE, 7>(pl, st, x, center, scale, clampq, cols, lse2, part, N);
-    case 8: return launch_rowsum<MODE, 8>(pl, st, x, center, scale, clampq, cols, lse2, part, N);
+    case 1: return launch_rowsum<MODE, 1>(pl, st, x, center, scale, clampq, cols, lse2, part, N, seg, pieces);
+    case 2: return launch_rowsum<MODE, 2>(pl, st, x, center, scale, clampq, cols, lse2, part, N, seg, pieces);
+    case 3: return launch_rowsum<MODE, 3>(pl, st, x, center, scale, clampq, cols, lse2, part, N, seg, pieces);
+    case 4: return launch_rowsum<MODE, 4>(pl, st, x, center, scale, clampq, cols, lse2, part, N, seg, pieces);
+    case 5: return launch_rowsum<MODE, 5>(pl, st, x, center, scale, clampq, cols, lse2, part, N, seg, pieces);
+    case 6: return launch_rowsum<MODE, 6>(pl, st, x, center, scale, clampq, cols, lse2, part, N, seg, pieces);
+    case 7: return launch_rowsum<MODE, 7>(pl, st, x, center, scale, clampq, cols, lse2, part, N, seg, pieces);
+    case 8: return launch_rowsum<MODE, 8>(pl, st, x, center, scale, clampq, cols, lse2, part, N, seg, pieces);
     default: return B200OT_EINVAL;
   }
 }
@@ -101,94 +102,103 @@ B200OT_API int b200ot_rowsum_merge(const float* part, int32_t n_part, int32_t wi
 B200OT_API int b200ot_softmin_bwd_partial(const float* x, const float* center, const float* cols, const float* lse2,
                                           float* part, int32_t n_split, int64_t N, int64_t M, int32_t D, int32_t p,
                                           float eps, void* stream) {
-  if (!x || !cols || !lse2 || !part || N <= 0 || M <= 0 || !supported_simt_dim(D) || (p != 1 && p != 2) ||
+  if (!x || !cols || !lse2 || !part || N <= 0 || M <= 0 || !supported_simt_dim(D) || !valid_p(p) ||
       !(eps > 0.f))
     return B200OT_EINVAL;
   if (((uintptr_t)cols) & 15) return B200OT_EALIGN;
   const ReducePlan pl = make_plan(N, M);
   if (n_split != pl.n_split) return B200OT_EINVAL;
-  const float scale = softmin_coord_scale(p, eps);
-  const float clampq = scale * scale * 1e-8f;
+  const int pe = p_exponent(p);
+  const float scale = softmin_coord_scale(pe, eps);
+  const float clampq = scale * scale * cost_clamp(p);
   cudaStream_t st = (cudaStream_t)stream;
-  return (p == 2) ? launch_rowsum_d<kSoftminBwdP2>(D, pl, st, x, center, scale, clampq, cols, lse2, part, N)
-                  : launch_rowsum_d<kSoftminBwdP1>(D, pl, st, x, center, scale, clampq, cols, lse2, part, N);
+  return (pe == 2) ? launch_rowsum_d<kSoftminBwdP2>(D, pl, st, x, center, scale, clampq, cols, lse2, part, N)
+                   : launch_rowsum_d<kSoftminBwdP1>(D, pl, st, x, center, scale, clampq, cols, lse2, part, N);
 }
 
-B200OT_API int b200ot_softmin_bwd_partial_sparse(const float* x, const float* center, const float* cols,
-                                                 const float* lse2, const int32_t* tile_ptr,
-                                                 const int32_t* tile_list, float* part, int64_t N, int64_t M,
-                                                 int32_t D, int32_t p, float eps, void* stream) {
-  if (!x || !cols || !lse2 || !tile_ptr || !tile_list || !part || N <= 0 || M <= 0 || D < 1 || D > 3 ||
-      (p != 1 && p != 2) || !(eps > 0.f))
+B200OT_API int b200ot_softmin_bwd_partial_ranges(const float* x, const float* center, const float* cols,
+                                                 const float* lse2, const b200ot_segment* seg, int64_t n_seg,
+                                                 const b200ot_piece* pieces, float* part, int64_t N, int32_t D,
+                                                 int32_t p, float eps, int32_t variant, void* stream) {
+  if (!x || !cols || !lse2 || !seg || !pieces || !part || N <= 0 || n_seg <= 0 || n_seg > 0x7fffffff ||
+      !supported_simt_dim(D) || !valid_p(p) || !(eps > 0.f) ||
+      (variant != B200OT_RANGES_BIG && variant != B200OT_RANGES_SMALL))
     return B200OT_EINVAL;
-  if (((uintptr_t)cols) & 15) return B200OT_EALIGN;
-  ReducePlan pl;
-  pl.small = false;
-  pl.tj = kBigTJ;
-  pl.rows_cta = kBigNT * kBigR;
-  pl.ntiles = (int)(round_up64(M, kBigTJ) / kBigTJ);
-  pl.tiles_per_split = pl.ntiles;
-  pl.n_split = 1;
-  pl.row_tiles = ceil_div64(N, pl.rows_cta);
-  const float scale = softmin_coord_scale(p, eps);
-  const float clampq = scale * scale * 1e-8f;
+  if ((((uintptr_t)cols) & 15) || (((uintptr_t)seg) & 15) || (((uintptr_t)pieces) & 7)) return B200OT_EALIGN;
+  const ReducePlan pl = ranges_plan(variant, n_seg);
+  const int pe = p_exponent(p);
+  const float scale = softmin_coord_scale(pe, eps);
+  const float clampq = scale * scale * cost_clamp(p);
   cudaStream_t st = (cudaStream_t)stream;
-  const int* tp = reinterpret_cast<const int*>(tile_ptr);
-  const int* tl = reinterpret_cast<const int*>(tile_list);
-  if (p == 2) {
-    switch (D) {
-      case 1: return launch_rowsum<kSoftminBwdP2, 1>(pl, st, x, center, scale, clampq, cols, lse2, part, N, tp, tl);
-      case 2: return launch_rowsum<kSoftminBwdP2, 2>(pl, st, x, center, scale, clampq, cols, lse2, part, N, tp, tl);
-      default: return launch_rowsum<kSoftminBwdP2, 3>(pl, st, x, center, scale, clampq, cols, lse2, part, N, tp, tl);
-    }
-  }
-  switch (D) {
-    case 1: return launch_rowsum<kSoftminBwdP1, 1>(pl, st, x, center, scale, clampq, cols, lse2, part, N, tp, tl);
-    case 2: return launch_rowsum<kSoftminBwdP1, 2>(pl, st, x, center, scale, clampq, cols, lse2, part, N, tp, tl);
-    default: return launch_rowsum<kSoftminBwdP1, 3>(pl, st, x, center, scale, clampq, cols, lse2, part, N, tp, tl);
-  }
+  const int4* sg = reinterpret_cast<const int4*>(seg);
+  const int2* pc = reinterpret_cast<const int2*>(pieces);
+  return (pe == 2) ? launch_rowsum_d<kSoftminBwdP2>(D, pl, st, x, center, scale, clampq, cols, lse2, part, N, sg, pc)
+                   : launch_rowsum_d<kSoftminBwdP1>(D, pl, st, x, center, scale, clampq, cols, lse2, part, N, sg, pc);
 }
 
 B200OT_API int b200ot_softmin_bwd_finalize(const float* part, int32_t n_part, const float* x, const float* center,
                                            const float* grad_out, float* grad_x, int64_t N, int32_t D, int32_t p,
                                            float eps, void* stream) {
   if (!part || n_part <= 0 || !x || !grad_out || !grad_x || N <= 0 ||
-      (!supported_simt_dim(D) && !(tc_supported_dim(D) && p == 2)) || (p != 1 && p != 2) || !(eps > 0.f))
+      (!supported_simt_dim(D) && !(tc_supported_dim(D) && p_exponent(p) == 2)) || !valid_p(p) || !(eps > 0.f))
     return B200OT_EINVAL;
   const int threads = 256;
   softmin_bwd_finalize_kernel<<<(unsigned)ceil_div64(N, threads), threads, 0, (cudaStream_t)stream>>>(
-      part, n_part, x, center, grad_out, grad_x, N, D, p, 1.0f / softmin_coord_scale(p, eps));
+      part, n_part, x, center, grad_out, grad_x, N, D, p_exponent(p), 1.0f / softmin_coord_scale(p_exponent(p), eps));
   B200OT_CUDA_TRY(cudaGetLastError());
   return B200OT_OK;
+}
+
+// Runs pack + partial reduction of the row-gradient pass and leaves n_part sets of (N, D+1) sums in scratch.
+static int softmin_bwd_partials(const float* x, const float* y, const float* h_a, const float* h_b, float h_scale_b,
+                                const float* center, const float* lse2, int64_t N, int64_t M, int32_t D, int32_t p,
+                                float eps, void* scratch, int64_t scratch_bytes, void* stream, float** part_out,
+                                int* n_part_out) {
+  const bool tc = tc_supported_dim(D) && p_exponent(p) == 2;
+  if (!x || !y || !h_a || !lse2 || !scratch || N <= 0 || M <= 0 || (!supported_simt_dim(D) && !tc) || !valid_p(p) ||
+      !(eps > 0.f))
+    return B200OT_EINVAL;
+  if (((uintptr_t)scratch) & 15) return B200OT_EALIGN;
+  if (scratch_bytes < b200ot_softmin_scratch_bytes(N, M, D)) return B200OT_ESCRATCH;
+  if (tc)
+    return bwd_partial_tc(1, x, y, nullptr, h_a, h_b, h_scale_b, lse2, center, softmin_coord_scale(2, eps), N, M, D,
+                          scratch, part_out, n_part_out, (cudaStream_t)stream, nullptr);
+  const ReducePlan pl = make_plan(N, M);
+  float* cols = reinterpret_cast<float*>(scratch);
+  float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) +
+                                         round_up64(b200ot_packed_cols_floats(M, D, 1) * 4, 256));
+  int rc = softmin_pack_impl(y, h_a, h_b, h_scale_b, center, M, D, p, eps, cols, (cudaStream_t)stream, nullptr);
+  if (rc) return rc;
+  rc = b200ot_softmin_bwd_partial(x, center, cols, lse2, part, pl.n_split, N, M, D, p, eps, stream);
+  *part_out = part;
+  *n_part_out = pl.n_split;
+  return rc;
+}
+
+B200OT_API int b200ot_softmin_bwd_sums(const float* x, const float* y, const float* h_a, const float* h_b,
+                                       float h_scale_b, const float* center, const float* lse2, float* sums,
+                                       int64_t N, int64_t M, int32_t D, int32_t p, float eps, void* scratch,
+                                       int64_t scratch_bytes, void* stream) {
+  if (!sums) return B200OT_EINVAL;
+  float* part = nullptr;
+  int n_part = 0;
+  const int rc = softmin_bwd_partials(x, y, h_a, h_b, h_scale_b, center, lse2, N, M, D, p, eps, scratch,
+                                      scratch_bytes, stream, &part, &n_part);
+  if (rc) return rc;
+  return b200ot_rowsum_merge(part, n_part, D + 1, sums, N, stream);
 }
 
 B200OT_API int b200ot_softmin_bwd_x(const float* x, const float* y, const float* h_a, const float* h_b,
                                     float h_scale_b, const float* center, const float* lse2, const float* grad_out,
                                     float* grad_x, int64_t N, int64_t M, int32_t D, int32_t p, float eps,
                                     void* scratch, int64_t scratch_bytes, void* stream) {
-  const bool tc = tc_supported_dim(D) && p == 2;
-  if (!x || !y || !h_a || !lse2 || !grad_out || !grad_x || !scratch || N <= 0 || M <= 0 ||
-      (!supported_simt_dim(D) && !tc) || (p != 1 && p != 2) || !(eps > 0.f))
-    return B200OT_EINVAL;
-  if (((uintptr_t)scratch) & 15) return B200OT_EALIGN;
-  if (scratch_bytes < b200ot_softmin_scratch_bytes(N, M, D)) return B200OT_ESCRATCH;
-  if (tc) {
-    float* tc_part = nullptr;
-    int n_part = 0;
-    const int rc = bwd_partial_tc(1, x, y, nullptr, h_a, h_b, h_scale_b, lse2, center, softmin_coord_scale(2, eps), N, M,
-                                  D, scratch, &tc_part, &n_part, (cudaStream_t)stream, nullptr);
-    if (rc) return rc;
-    return b200ot_softmin_bwd_finalize(tc_part, n_part, x, center, grad_out, grad_x, N, D, p, eps, stream);
-  }
-  const ReducePlan pl = make_plan(N, M);
-  float* cols = reinterpret_cast<float*>(scratch);
-  float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) +
-                                         round_up64(b200ot_packed_cols_floats(M, D, 1) * 4, 256));
-  int rc = softmin_pack_impl(y, h_a, h_b, h_scale_b, center, M, D, p, eps, cols, (cudaStream_t)stream);
+  if (!grad_out || !grad_x) return B200OT_EINVAL;
+  float* part = nullptr;
+  int n_part = 0;
+  const int rc = softmin_bwd_partials(x, y, h_a, h_b, h_scale_b, center, lse2, N, M, D, p, eps, scratch,
+                                      scratch_bytes, stream, &part, &n_part);
   if (rc) return rc;
-  rc = b200ot_softmin_bwd_partial(x, center, cols, lse2, part, pl.n_split, N, M, D, p, eps, stream);
-  if (rc) return rc;
-  return b200ot_softmin_bwd_finalize(part, pl.n_split, x, center, grad_out, grad_x, N, D, p, eps, stream);
+  return b200ot_softmin_bwd_finalize(part, n_part, x, center, grad_out, grad_x, N, D, p, eps, stream);
 }
 
 }  // extern "C"

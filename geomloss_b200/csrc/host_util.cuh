@@ -20,6 +20,16 @@ int num_sms();
 // Dimensions served by the CUDA-core (register tile) kernels that are instantiated in this build.
 inline bool supported_simt_dim(int D) { return D >= 1 && D <= B200OT_MAX_D; }
 
+// Cost exponent argument of the C ABI: 1 or 2, optionally or-ed with B200OT_P_UNCLAMPED (p = 1 only matters).
+inline int p_exponent(int p) { return p & 0xff; }
+inline bool valid_p(int p) {
+  const int e = p & 0xff;
+  return (e == 1 || e == 2) && (p & ~(0xff | B200OT_P_UNCLAMPED)) == 0;
+}
+// Clamp on |x-y|^2 under the square root: the reference's tensorized `distances` clamps at 1e-8 (utils.py:61);
+// pykeops' Norm2 / sqrt do not (sqrt(0) = 0 with a zero gradient) — emulated by a clamp far below fp32 resolution.
+inline float cost_clamp(int flags) { return (flags & B200OT_P_UNCLAMPED) ? 1e-30f : 1e-8f; }
+
 // Coordinate scale of the softmin kernels: the log2-domain exponent is H - |X-Y|^2/2 (p = 2) or
 // H - |X-Y| (p = 1) with X = scale * (x - c).
 inline float softmin_coord_scale(int p, float eps) {
@@ -28,7 +38,7 @@ inline float softmin_coord_scale(int p, float eps) {
 
 // Shared between translation units (defined in b200ot_softmin.cu).
 int softmin_pack_impl(const float* y, const float* h_a, const float* h_b, float h_scale_b, const float* center,
-                      int64_t M, int D, int p, float eps, float* cols_out, cudaStream_t st);
+                      int64_t M, int D, int p, float eps, float* cols_out, cudaStream_t st, const int* src);
 
 // Tensor-core (tcgen05) path for 8 < D <= 64, defined in b200ot_kernel_conv.cu.
 bool tc_supported_dim(int D);

@@ -44,11 +44,32 @@ inline ReducePlan make_plan(int64_t N, int64_t M) {
   return p;
 }
 
+// Ranges mode (block-sparse / batched problems): one CTA per row segment, one column split, the pieces of a
+// segment are at most one tile wide and aligned to kRangesAlign columns (a whole number of chunks of either
+// tile shape: 2 * CH = 16 columns for the big shape, 8 for the small one).
+constexpr int kRangesAlign = 16;
+inline ReducePlan ranges_plan(int variant, int64_t n_seg) {
+  ReducePlan p;
+  p.small = (variant == B200OT_RANGES_SMALL);
+  p.tj = p.small ? kSmallTJ : kBigTJ;
+  p.rows_cta = p.small ? kSmallNT * kSmallR : kBigNT * kBigR;
+  p.ntiles = 0;
+  p.tiles_per_split = 0;
+  p.n_split = 1;
+  p.row_tiles = n_seg;
+  return p;
+}
+
 // Launch one instantiation of a partial-reduction kernel with its dynamic shared memory opt-in.
 template <class C, class Kern, class... Args>
 inline int launch_reduce(Kern kern, const ReducePlan& pl, cudaStream_t st, Args... args) {
-  // per call, not cached: the attribute is per device and a process may drive several
-  B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  // the opt-in is per (kernel, device): set it once per device a process drives, not on every launch
+  static bool attr_done[64] = {};
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !attr_done[dev]) {
+    B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+  }
   dim3 grid((unsigned)pl.row_tiles, (unsigned)pl.n_split);
   kern<<<grid, C::NT + 32, C::SMEM_BYTES, st>>>(args...);
   B200OT_CUDA_TRY(cudaGetLastError());

@@ -46,7 +46,8 @@ struct RowSumCfg {
   static constexpr int TILE_FLOATS = (TJ / 2) * NF2 * 2;
   static constexpr int TILE_BYTES = TILE_FLOATS * 4;
   static constexpr int ROWS_PER_CTA = NT * R;
-  static constexpr int SMEM_BYTES = STAGES * TILE_BYTES + 2 * STAGES * 8;
+  static constexpr int SMEM_BYTES = STAGES * TILE_BYTES + 2 * STAGES * 8 + 16;  // + per-stage pair counts
+  static_assert(STAGES <= 4, "the per-stage pair counts live in one 16-byte slot");
 };
 
 // rowterm: per-row additive term of the exponent (softmin bwd: rowc_i - lse2_i; gaussian: rowc_i), may be null.
@@ -55,20 +56,33 @@ template <class C>
 __global__ void __launch_bounds__(C::NT + 32, C::MINB)
     rowsum_partial_kernel(const float* __restrict__ x, const float* __restrict__ center, float scale, float clampq,
                           const float* __restrict__ cols, const float* __restrict__ lse2, float* __restrict__ part,
-                          int64_t N, int ntiles, int tiles_per_split, const int* __restrict__ tile_ptr,
-                          const int* __restrict__ tile_list) {
+                          int64_t N, int ntiles, int tiles_per_split, const int4* __restrict__ seg,
+                          const int2* __restrict__ pieces) {
   constexpr int D = C::D, R = C::R, NT = C::NT, NF2 = C::NF2, STAGES = C::STAGES, NACC = C::NACC, MODE = C::MODE;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* tiles = reinterpret_cast<float*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * C::TILE_BYTES);
   uint64_t* empty = full + STAGES;
+  int* cnt = reinterpret_cast<int*>(empty + STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int split = blockIdx.y;
-  const bool sparse = (tile_ptr != nullptr);  // block-sparse mode: see softmin.cuh
-  const int t0 = sparse ? tile_ptr[blockIdx.x] : split * tiles_per_split;
-  const int t1 = sparse ? tile_ptr[blockIdx.x + 1] : min(ntiles, t0 + tiles_per_split);
+  const bool sparse = (seg != nullptr);  // ranges mode (segments + column pieces): see softmin.cuh
+  int t0, t1, nrows;
+  int64_t row0;
+  if (sparse) {
+    const int4 sg = seg[blockIdx.x];
+    row0 = sg.x;
+    nrows = sg.y;
+    t0 = sg.z;
+    t1 = sg.w;
+  } else {
+    row0 = (int64_t)blockIdx.x * C::ROWS_PER_CTA;
+    nrows = (int)min((int64_t)C::ROWS_PER_CTA, N - row0);
+    t0 = split * tiles_per_split;
+    t1 = min(ntiles, t0 + tiles_per_split);
+  }
   const int nt = t1 - t0;
 
   if (threadIdx.x == 0) {
@@ -85,23 +99,31 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
       for (int k = 0; k < nt; ++k) {
         const int st = k % STAGES;
         if (k >= STAGES) mbar_wait(&empty[st], ((k / STAGES) + 1) & 1);
-        const int64_t t = sparse ? tile_list[t0 + k] : (t0 + k);
-        mbar_arrive_expect_tx(&full[st], C::TILE_BYTES);
-        tma_load_1d(tiles + st * C::TILE_FLOATS, cols + t * C::TILE_FLOATS, C::TILE_BYTES, &full[st]);
+        if (sparse) {
+          const int2 pc = pieces[t0 + k];
+          const uint32_t bytes = (uint32_t)pc.y * (NF2 * 4);
+          cnt[st] = pc.y >> 1;
+          mbar_arrive_expect_tx(&full[st], bytes);
+          tma_load_1d(tiles + st * C::TILE_FLOATS, cols + (int64_t)pc.x * NF2, bytes, &full[st]);
+        } else {
+          mbar_arrive_expect_tx(&full[st], C::TILE_BYTES);
+          tma_load_1d(tiles + st * C::TILE_FLOATS, cols + (int64_t)(t0 + k) * C::TILE_FLOATS, C::TILE_BYTES,
+                      &full[st]);
+        }
       }
     }
     return;
   }
 
   const int tid = threadIdx.x - 32;
-  const int64_t row_base = (int64_t)blockIdx.x * C::ROWS_PER_CTA + tid;
+  const int64_t row_base = row0 + tid;
 
   float2 X[R][D];
   float2 rt2[R];  // per-row additive exponent term, duplicated
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     int64_t i = row_base + (int64_t)r * NT;
-    if (i >= N) i = N - 1;
+    if (tid + r * NT >= nrows) i = row0 + nrows - 1;
     float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -133,8 +155,9 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
 #pragma unroll
       for (int a = 0; a < NACC; ++a) T[r][a] = dup2(0.f);
 
+    const int npairs = sparse ? cnt[st] : C::TJ / 2;
 #pragma unroll 2
-    for (int jp = 0; jp < C::TJ / 2; ++jp) {
+    for (int jp = 0; jp < npairs; ++jp) {
       float2 S[NF2];
 #pragma unroll
       for (int q = 0; q < NF2 / 2; ++q) {
@@ -211,7 +234,7 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int64_t i = row_base + (int64_t)r * NT;
-    if (i < N) {
+    if (tid + r * NT < nrows) {
 #pragma unroll
       for (int a = 0; a < NACC; ++a) part[((int64_t)split * N + i) * NACC + a] = A[r][a].x + A[r][a].y;
     }

@@ -23,12 +23,10 @@ default is the CUDA implementation and it refuses non-CUDA tensors.
 """
 from __future__ import annotations
 
-import ctypes
-
 import torch
 import torch.distributed as dist
 
-from . import _lib, ops
+from . import _lib, ops, ranges
 
 
 def shard_bounds(M: int, rank: int, world: int):
@@ -47,6 +45,11 @@ class CudaStages:
         M = y.shape[0]
         dev = x.device
         L = _lib.lib()
+        if D > ops.MAX_D:
+            # tensor-core dimensions (8 < D <= 64, p = 2): the one-call forward leaves the shard's log2-domain
+            # log-sum-exp, which IS a merged partial (m = lse2, s = 1)
+            lse2 = ops.softmin_raw(eps, x, y, h_a, h_b, h_scale_b, p=p, center=center, want_lse2=True)[1]
+            return torch.stack([lse2, torch.ones_like(lse2)], dim=1).contiguous()
         with torch.cuda.device(dev):
             merged = torch.empty(N, 2, dtype=torch.float32, device=dev)
             nsplit = L.b200ot_softmin_num_splits(N, M, D)
@@ -83,7 +86,7 @@ class CudaStages:
         return out, lse2
 
     def softmin_bwd_shard(self, eps, x, y, h_a, h_b, h_scale_b, p, center, lse2):
-        """(N, D+1) partial sums of the backward pass over the column shard."""
+        """(N, D+1) partial sums of the backward pass over the column shard (any supported D)."""
         x, y, h_a, h_b, center, lse2 = (ops._f32c(t, n) for t, n in ((x, "x"), (y, "y"), (h_a, "h_a"), (h_b, "h_b"),
                                                                      (center, "center"), (lse2, "lse2")))
         N, D = x.shape
@@ -92,18 +95,11 @@ class CudaStages:
         L = _lib.lib()
         with torch.cuda.device(dev):
             sums = torch.empty(N, D + 1, dtype=torch.float32, device=dev)
-            nsplit = L.b200ot_softmin_num_splits(N, M, D)
-            cols = ops._scratch(L.b200ot_packed_cols_floats(M, D, 1) * 4, dev, "shard_cols")
-            part = ops._scratch(nsplit * N * 4 * (D + 1), dev, "shard_part")
-            st = ops._stream(dev)
-            _lib.check(L.b200ot_softmin_pack(ops._ptr(y), ops._ptr(h_a), ops._ptr(h_b), float(h_scale_b),
-                                             ops._ptr(center), M, D, int(p), float(eps), ops._ptr(cols), st),
-                       "b200ot_softmin_pack")
-            _lib.check(L.b200ot_softmin_bwd_partial(ops._ptr(x), ops._ptr(center), ops._ptr(cols), ops._ptr(lse2),
-                                                    ops._ptr(part), nsplit, N, M, D, int(p), float(eps), st),
-                       "b200ot_softmin_bwd_partial")
-            _lib.check(L.b200ot_rowsum_merge(ops._ptr(part), nsplit, D + 1, ops._ptr(sums), N, st),
-                       "b200ot_rowsum_merge")
+            scratch = ops._scratch(L.b200ot_softmin_scratch_bytes(N, M, D), dev, "softmin")
+            _lib.check(L.b200ot_softmin_bwd_sums(ops._ptr(x), ops._ptr(y), ops._ptr(h_a), ops._ptr(h_b),
+                                                 float(h_scale_b), ops._ptr(center), ops._ptr(lse2), ops._ptr(sums), N,
+                                                 M, D, int(p), float(eps), ops._ptr(scratch), scratch.numel(),
+                                                 ops._stream(dev)), "b200ot_softmin_bwd_sums")
         ops.count_launches(3)
         return sums
 
@@ -120,54 +116,14 @@ class CudaStages:
         ops.count_launches(1)
         return gx
 
-    # -- block-sparse (multiscale fine phase): ALL columns are packed, the tile lists select this rank's --
-    def tile_shape(self):
-        r, c = ctypes.c_int32(0), ctypes.c_int32(0)
-        _lib.lib().b200ot_sparse_tile_shape(ctypes.byref(r), ctypes.byref(c))
-        return r.value, c.value
+    # -- ranges mode (multiscale fine phase): ALL columns are packed, the pieces select this rank's clusters --
+    def softmin_sparse_shard(self, eps, x, y, h_a, h_b, h_scale_b, p, center, prob):
+        """(N, 2) partial (m, s) over the column pieces listed for this rank."""
+        return ranges.softmin_shard_ranges(eps, x, y, h_a, h_b, h_scale_b, prob, p=p, center=center)
 
-    def softmin_sparse_shard(self, eps, x, y, h_a, h_b, h_scale_b, p, center, tile_ptr, tile_list):
-        """(N, 2) partial (m, s) over the column tiles listed for this rank."""
-        x, y, h_a, h_b, center = (ops._f32c(t, n) for t, n in ((x, "x"), (y, "y"), (h_a, "h_a"), (h_b, "h_b"),
-                                                               (center, "center")))
-        N, D = x.shape
-        M = y.shape[0]
-        dev = x.device
-        L = _lib.lib()
-        with torch.cuda.device(dev):
-            part = torch.empty(N, 2, dtype=torch.float32, device=dev)
-            cols = ops._scratch(L.b200ot_packed_cols_floats(M, D, 1) * 4, dev, "sparse_cols")
-            st = ops._stream(dev)
-            _lib.check(L.b200ot_softmin_pack(ops._ptr(y), ops._ptr(h_a), ops._ptr(h_b), float(h_scale_b),
-                                             ops._ptr(center), M, D, int(p), float(eps), ops._ptr(cols), st),
-                       "b200ot_softmin_pack")
-            _lib.check(L.b200ot_softmin_partial_sparse(ops._ptr(x), ops._ptr(center), ops._ptr(cols),
-                                                       ops._ptr(tile_ptr), ops._ptr(tile_list), ops._ptr(part), N, M,
-                                                       D, int(p), float(eps), st), "b200ot_softmin_partial_sparse")
-        ops.count_launches(2)
-        return part
-
-    def softmin_bwd_sparse_shard(self, eps, x, y, h_a, h_b, h_scale_b, p, center, lse2, tile_ptr, tile_list):
-        """(N, D+1) partial backward sums over the column tiles listed for this rank."""
-        x, y, h_a, h_b, center, lse2 = (ops._f32c(t, n) for t, n in ((x, "x"), (y, "y"), (h_a, "h_a"), (h_b, "h_b"),
-                                                                     (center, "center"), (lse2, "lse2")))
-        N, D = x.shape
-        M = y.shape[0]
-        dev = x.device
-        L = _lib.lib()
-        with torch.cuda.device(dev):
-            sums = torch.empty(N, D + 1, dtype=torch.float32, device=dev)
-            cols = ops._scratch(L.b200ot_packed_cols_floats(M, D, 1) * 4, dev, "sparse_cols")
-            st = ops._stream(dev)
-            _lib.check(L.b200ot_softmin_pack(ops._ptr(y), ops._ptr(h_a), ops._ptr(h_b), float(h_scale_b),
-                                             ops._ptr(center), M, D, int(p), float(eps), ops._ptr(cols), st),
-                       "b200ot_softmin_pack")
-            _lib.check(L.b200ot_softmin_bwd_partial_sparse(ops._ptr(x), ops._ptr(center), ops._ptr(cols),
-                                                           ops._ptr(lse2), ops._ptr(tile_ptr), ops._ptr(tile_list),
-                                                           ops._ptr(sums), N, M, D, int(p), float(eps), st),
-                       "b200ot_softmin_bwd_partial_sparse")
-        ops.count_launches(2)
-        return sums
+    def softmin_bwd_sparse_shard(self, eps, x, y, h_a, h_b, h_scale_b, p, center, lse2, prob):
+        """(N, D+1) partial backward sums over the column pieces listed for this rank."""
+        return ranges.softmin_bwd_shard_ranges(eps, x, y, h_a, h_b, h_scale_b, prob, lse2, p=p, center=center)
 
     # -- kernel convolutions (plain sums: partial results simply add across shards) --
     def conv_shard(self, kind, x, y, w, blur, center):
@@ -215,8 +171,11 @@ class ColumnShardedEngine:
                                      h_scale_b, eps, p, center, scale_out, local, None)
 
     # -- the operator set of multiscale.sinkhorn_multiscale (same names as multiscale.LocalEngine) ----
-    def tile_shape(self):
-        return self.stages.tile_shape()
+    def build(self, keep, row_counts, layout, variant=None):
+        """Ranges problem restricted to THIS rank's slab of column clusters (balanced by kept pairs)."""
+        if variant is None:
+            variant = getattr(self.stages, "ranges_variant", None)
+        return ranges.build_problem(keep, row_counts, layout, variant=variant, rank=self.rank, world=self.world)
 
     def broadcast(self, t):
         t = t.contiguous()
@@ -233,8 +192,7 @@ class ColumnShardedEngine:
     def sparse_raw(self, eps, x, y, h_a, h_b, h_scale_b, prob, *, p=2, center=None, out_old=None, alpha_old=0.0,
                    beta=1.0, want_lse2=False):
         """Block-sparse softmin; ``prob`` holds THIS rank's column tiles (multiscale.tiles_from_cluster_mask)."""
-        mine = self.stages.softmin_sparse_shard(eps, x, y, h_a, h_b, h_scale_b, p, center, prob.tile_ptr,
-                                                prob.tile_list)
+        mine = self.stages.softmin_sparse_shard(eps, x, y, h_a, h_b, h_scale_b, p, center, prob)
         N = x.shape[0]
         parts = torch.empty(self.world, N, 2, dtype=mine.dtype, device=mine.device)
         dist.all_gather_into_tensor(parts.view(self.world * N, 2), mine, group=self.group)
@@ -284,8 +242,7 @@ class _ShardedSoftmin(torch.autograd.Function):
         M = y.shape[0]
         lo, hi = (0, M) if ctx.local else shard_bounds(M, eng.rank, eng.world)
         if ctx.prob is not None:
-            sums = eng.stages.softmin_bwd_sparse_shard(eps, x, y, h_a, h_b, h_scale_b, p, center, lse2,
-                                                       ctx.prob.tile_ptr, ctx.prob.tile_list)
+            sums = eng.stages.softmin_bwd_sparse_shard(eps, x, y, h_a, h_b, h_scale_b, p, center, lse2, ctx.prob)
         elif hi > lo:
             sums = eng.stages.softmin_bwd_shard(eps, x, y[lo:hi], h_a[lo:hi], None if h_b is None else h_b[lo:hi],
                                                 h_scale_b, p, center, lse2)

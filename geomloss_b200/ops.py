@@ -14,6 +14,10 @@ import torch
 from . import _lib
 
 KERNEL_KINDS = {"gaussian": 0, "laplacian": 1, "energy": 2}
+# flags of include/b200ot.h: the pykeops convention for sqrt(|x-y|^2) (no 1e-8 clamp, zero gradient at 0), used by
+# the reference's "online" / "multiscale" backends; the plain values are the "tensorized" convention
+P_UNCLAMPED = 0x100
+KERNEL_UNCLAMPED = 0x100
 MAX_D = 8  # dimensions instantiated in this build of libb200ot.so (supported_simt_dim in csrc/host_util.cuh)
 
 # Number of kernels of libb200ot.so enqueued so far by this process (bench.py reports the delta over its
@@ -99,7 +103,7 @@ def softmin_raw(eps, x, y, h_a, h_b=None, h_scale_b=0.0, *, p=2, center=None, ou
     """
     x, y, h_a, h_b = _f32c(x, "x"), _f32c(y, "y"), _f32c(h_a, "h_a"), _f32c(h_b, "h_b")
     center, out_old = _f32c(center, "center"), _f32c(out_old, "out_old")
-    _check_clouds(x, y, MAX_D_TC if p == 2 else MAX_D)
+    _check_clouds(x, y, MAX_D_TC if (p & 0xFF) == 2 else MAX_D)
     N, D = x.shape
     M = y.shape[0]
     if h_a.numel() != M or (h_b is not None and h_b.numel() != M):
@@ -124,7 +128,7 @@ def softmin_grad_rows(eps, x, y, h_a, h_b, h_scale_b, lse2, grad_out, *, p=2, ce
     """grad_x of <grad_out, softmin(eps, (x, y), h)> with y, h constant (b200ot_softmin_bwd_x)."""
     x, y, h_a, h_b = _f32c(x, "x"), _f32c(y, "y"), _f32c(h_a, "h_a"), _f32c(h_b, "h_b")
     center, lse2, grad_out = _f32c(center, "center"), _f32c(lse2, "lse2"), _f32c(grad_out, "grad_out")
-    _check_clouds(x, y, MAX_D_TC if p == 2 else MAX_D)
+    _check_clouds(x, y, MAX_D_TC if (p & 0xFF) == 2 else MAX_D)
     N, D = x.shape
     M = y.shape[0]
     dev = x.device
@@ -178,10 +182,15 @@ def softmin(eps, x, y, h_a, h_b=None, h_scale_b=0.0, *, p=2, center=None, scale_
 # ------------------------------------------------------------------------------------------------
 
 
+def kind_id(kind):
+    """Kernel name (tensorized convention) or an integer kind, possibly or-ed with KERNEL_UNCLAMPED."""
+    return KERNEL_KINDS[kind] if isinstance(kind, str) else int(kind)
+
+
 def kernel_conv_raw(kind, x, y, w, blur, *, center=None):
     """out_i = sum_j k(x_i, y_j) w_j, no autograd."""
     x, y, w, center = _f32c(x, "x"), _f32c(y, "y"), _f32c(w, "w"), _f32c(center, "center")
-    _check_clouds(x, y, MAX_D_TC if kind == "gaussian" else MAX_D)
+    _check_clouds(x, y, MAX_D_TC if (kind_id(kind) & 0xFF) == 0 else MAX_D)
     N, D = x.shape
     M = y.shape[0]
     if w.numel() != M:
@@ -193,7 +202,7 @@ def kernel_conv_raw(kind, x, y, w, blur, *, center=None):
         nbytes = L.b200ot_kernel_conv_scratch_bytes(N, M, D)
         scratch = _scratch(nbytes, dev, "conv")
         rc = L.b200ot_kernel_conv_fwd(_ptr(x), _ptr(y), _ptr(w), _ptr(center), _ptr(out), N, M, D,
-                                      KERNEL_KINDS[kind], float(blur), _ptr(scratch), scratch.numel(), _stream(dev))
+                                      kind_id(kind), float(blur), _ptr(scratch), scratch.numel(), _stream(dev))
     _lib.check(rc, "b200ot_kernel_conv_fwd")
     count_launches(3)
     return out
@@ -202,7 +211,7 @@ def kernel_conv_raw(kind, x, y, w, blur, *, center=None):
 def kernel_conv_grad_rows(kind, x, y, w, blur, grad_out, *, center=None):
     x, y, w, center = _f32c(x, "x"), _f32c(y, "y"), _f32c(w, "w"), _f32c(center, "center")
     grad_out = _f32c(grad_out, "grad_out")
-    _check_clouds(x, y, MAX_D_TC if kind == "gaussian" else MAX_D)
+    _check_clouds(x, y, MAX_D_TC if (kind_id(kind) & 0xFF) == 0 else MAX_D)
     N, D = x.shape
     M = y.shape[0]
     dev = x.device
@@ -212,7 +221,7 @@ def kernel_conv_grad_rows(kind, x, y, w, blur, grad_out, *, center=None):
         nbytes = L.b200ot_kernel_conv_scratch_bytes(N, M, D)
         scratch = _scratch(nbytes, dev, "conv")
         rc = L.b200ot_kernel_conv_bwd_x(_ptr(x), _ptr(y), _ptr(w), _ptr(center), _ptr(grad_out), _ptr(gx), N, M, D,
-                                        KERNEL_KINDS[kind], float(blur), _ptr(scratch), scratch.numel(),
+                                        kind_id(kind), float(blur), _ptr(scratch), scratch.numel(),
                                         _stream(dev))
     _lib.check(rc, "b200ot_kernel_conv_bwd_x")
     count_launches(3)

@@ -8,12 +8,15 @@ its quirks that user code may rely on:
     time, exactly like the reference at this commit (SURVEY.md A-13);
   * unknown ``p`` raises ``KeyError`` (the reference's cost table only has p = 1, 2).
 
-What differs by design: ``backend`` keeps the reference's routing rules (samples_loss.py:220-257: labels need
-"auto"/"multiscale"; "auto" picks "multiscale" for Sinkhorn, p = 2, D <= 3 above 1e8 pairs; a batched
-multiscale call warns and falls back to the dense path), but "tensorized" and "online" are ONE engine: the
-never-materialised sm_100a reductions, evaluated exactly.  "multiscale" is the two-scale scheme with kernel
-truncation on the block-sparse mode of the same kernels (multiscale.py) for ``loss="sinkhorn"``; the kernel
-MMDs are always evaluated exactly.  Inputs must be float32 CUDA tensors: there is no CPU path.
+``backend`` keeps the reference's routing rules (samples_loss.py:220-257: labels need "auto"/"multiscale"; "auto"
+picks "multiscale" for Sinkhorn, p = 2, D <= 3 above 1e8 pairs; a batched multiscale call warns and falls back to
+the dense path).  "tensorized" and "online" are ONE engine — the never-materialised sm_100a reductions, evaluated
+exactly — and differ only where the reference's two backends differ numerically: for p = 1 / laplacian / energy
+"tensorized" clamps |x-y|^2 at 1e-8 under the square root (utils.py:56-61) while "online" and "multiscale" use the
+pykeops norm (no clamp).  "multiscale" is the two-scale Sinkhorn with kernel truncation / the truncated kernel
+norms (multiscale.py) on the ranges mode of the same kernels, with exactly the reference's cluster blocks.
+Batched inputs (B, N, D) with D <= 8 run as ONE block-diagonal launch group per reduction (ranges.py).
+Inputs must be float32 CUDA tensors: there is no CPU path.
 """
 from __future__ import annotations
 
@@ -22,9 +25,10 @@ from torch.nn import Module
 
 import warnings
 
-from .kernel_loss import kernel_points
-from .multiscale import sinkhorn_multiscale
-from .sinkhorn import sinkhorn_points
+from .kernel_loss import kernel_points, kernel_points_batched
+from .multiscale import kernel_multiscale, sinkhorn_multiscale
+from .ops import MAX_D
+from .sinkhorn import sinkhorn_points, sinkhorn_points_batched
 
 _LOSSES = ("sinkhorn", "hausdorff", "energy", "gaussian", "laplacian")
 _BACKENDS = ("auto", "tensorized", "online", "multiscale")
@@ -100,7 +104,20 @@ class SamplesLoss(Module):
                 "only evaluates |x-y|^p/p, p in {1,2}, on the fly")
         routine = _route(self.loss)
         kw = dict(p=self.p, blur=self.blur, reach=self.reach, diameter=self.diameter, scaling=self.scaling,
-                  debias=self.debias, potentials=self.potentials, kernel=self.kernel, **self._engine)
+                  debias=self.debias, potentials=self.potentials, kernel=self.kernel,
+                  keops=(backend != "tensorized"), **self._engine)
+        if backend == "multiscale" and self.loss != "sinkhorn":
+            # kernel_multiscale (kernel_samples.py:177-271); "hausdorff" dies with KeyError(None) like the reference
+            sq = (lambda t: t[0]) if B == 1 else (lambda t: t)
+            name = None if self.loss == "hausdorff" else self.loss
+            values = kernel_multiscale(sq(a), sq(x), sq(b), sq(y), name=name, blur=self.blur, truncate=self.truncate,
+                                       diameter=self.diameter, cluster_scale=self.cluster_scale,
+                                       potentials=self.potentials, kernel=self.kernel, verbose=self.verbose,
+                                       conv=self._engine.get("conv"))
+            if self.potentials:
+                F, G = values
+                return F.view_as(a), G.view_as(b)
+            return values if B == 0 else values.view(-1)
         if backend == "multiscale" and self.loss == "sinkhorn" and D <= 3:
             # single problem (B == 0, or B == 1 squeezed like the reference does, samples_loss.py:249-251)
             sq = (lambda t: t[0]) if B == 1 else (lambda t: t)
@@ -126,6 +143,15 @@ class SamplesLoss(Module):
             from .sinkhorn import max_diameter
 
             kw["diameter"] = max_diameter(x.reshape(-1, D), y.reshape(-1, D))
+        if B > 1 and D <= MAX_D and not self._engine and self.loss != "hausdorff":
+            # the whole batch in one launch group per reduction (block-diagonal ranges problem)
+            batched = sinkhorn_points_batched if self.loss == "sinkhorn" else kernel_points_batched
+            if self.loss != "sinkhorn":
+                kw["name"] = self.loss
+            values = batched(a, x, b, y, **kw)
+            if self.potentials:
+                return values[0].view_as(a), values[1].view_as(b)
+            return values
         per_batch = [routine(a[k], x[k], b[k], y[k], **kw) for k in range(B)]
         if self.potentials:
             F = torch.stack([f for f, _ in per_batch])

@@ -51,7 +51,7 @@ def scaling_parameters(x, y, p, blur, reach, diameter, scaling):
 
 
 def sinkhorn_loop_points(a_log, b_log, x, y, eps_list, rho, *, p=2, debias=True, center=None, softmin_raw=None,
-                         softmin_grad=None):
+                         softmin_grad=None, problems=None):
     """Symmetric Sinkhorn iterations with eps-scaling on one pair of clouds.   sinkhorn_divergence.py:258-628
 
     The iterations run without autograd on detached clouds.  All four updates of an iteration read the
@@ -61,9 +61,27 @@ def sinkhorn_loop_points(a_log, b_log, x, y, eps_list, rho, *, p=2, debias=True,
 
     ``softmin_raw`` / ``softmin_grad`` default to the single-GPU kernels; the column-sharded
     multi-GPU engine (distributed.py) injects its own pair with the same signatures.
+    ``problems`` (batched inputs): ranges-mode descriptors {"xy", "yx", "xx", "yy"} of the block-diagonal problems
+    obtained by stacking the B batch elements along the point axis — the whole batch then runs in ONE launch group
+    per softmin, like the reference's batched LazyTensor reduction (sinkhorn_samples.py:229-290).
     """
-    sm = softmin_raw or ops.softmin_raw
-    smg = softmin_grad or ops.softmin
+    if problems is None:
+        sm = softmin_raw or ops.softmin_raw
+        smg = softmin_grad or ops.softmin
+    else:
+        from . import ranges
+
+        def _prob(rows, cols):
+            key = ("x" if rows is x or rows is xd else "y") + ("x" if cols is x or cols is xd else "y")
+            # (x is y: every key reads "xx", and the four problems have the same shape)
+            return problems[key] if key in problems else problems["xy"]
+
+        def sm(eps, rows, cols, h_a, h_b=None, h_scale_b=0.0, **kw):
+            return ranges.softmin_ranges_raw(eps, rows, cols, h_a, h_b, h_scale_b, _prob(rows, cols), **kw)
+
+        def smg(eps, rows, cols, h_a, h_b=None, h_scale_b=0.0, **kw):
+            return ranges.softmin_ranges(eps, rows, cols, h_a, h_b, h_scale_b, _prob(rows, cols), **kw)
+
     xd, yd = x.detach(), y.detach()
     with torch.no_grad():
         eps = eps_list[0]
@@ -116,14 +134,67 @@ def sinkhorn_cost(eps, rho, a, b, f_aa, g_bb, g_ab, f_ba, debias=True, potential
 
 
 def sinkhorn_points(a, x, b, y, p=2, blur=0.05, reach=None, diameter=None, scaling=0.5, debias=True,
-                    potentials=False, softmin_raw=None, softmin_grad=None, **_ignored):
+                    potentials=False, softmin_raw=None, softmin_grad=None, keops=False, **_ignored):
     """Sinkhorn divergence between two weighted clouds a:(N,) x:(N,D) b:(M,) y:(M,D) on one CUDA device.
-    Counterpart of sinkhorn_online (sinkhorn_samples.py:349-424) for a single batch element."""
+    Counterpart of sinkhorn_tensorized / sinkhorn_online (sinkhorn_samples.py:74-221, :349-424) for a single batch
+    element.  ``keops``: the "online" cost convention — for p = 1, Norm2(x-y) without the 1e-8 clamp of the
+    tensorized `distances` (sinkhorn_samples.py:303-306 vs utils.py:56-61)."""
     if p not in (1, 2):
         raise KeyError(p)  # the reference's cost table only knows p = 1, 2 (sinkhorn_samples.py:26-29)
     diameter, eps, eps_list, rho = scaling_parameters(x, y, p, blur, reach, diameter, scaling)
     center = ops.default_center(x.detach(), y.detach())
+    pk = (p | ops.P_UNCLAMPED) if keops else p
     f_aa, g_bb, g_ab, f_ba = sinkhorn_loop_points(log_weights(a.detach()), log_weights(b.detach()), x, y, eps_list,
-                                                  rho, p=p, debias=debias, center=center, softmin_raw=softmin_raw,
+                                                  rho, p=pk, debias=debias, center=center, softmin_raw=softmin_raw,
                                                   softmin_grad=softmin_grad)
     return sinkhorn_cost(eps, rho, a, b, f_aa, g_bb, g_ab, f_ba, debias=debias, potentials=potentials)
+
+
+def _bsum(w, f, B):
+    return (w * f).view(B, -1).sum(1)
+
+
+def sinkhorn_cost_batched(eps, rho, a, b, f_aa, g_bb, g_ab, f_ba, B, debias=True, potentials=False):
+    """sinkhorn_cost on B problems stacked along the point axis: one value per batch element (scal(batch=True),
+    utils.py:13-18)."""
+    if potentials:
+        return (f_ba - f_aa, g_ab - g_bb) if debias else (f_ba, g_ab)
+    if rho is None:
+        if debias:
+            return _bsum(a, f_ba - f_aa, B) + _bsum(b, g_ab - g_bb, B)
+        return _bsum(a, f_ba, B) + _bsum(b, g_ab, B)
+    w = rho + eps / 2
+    if debias:
+        return _bsum(a, w * ((-f_aa / rho).exp() - (-f_ba / rho).exp()), B) + _bsum(
+            b, w * ((-g_bb / rho).exp() - (-g_ab / rho).exp()), B)
+    return _bsum(a, w * (1 - (-f_ba / rho).exp()), B) + _bsum(b, w * (1 - (-g_ab / rho).exp()), B)
+
+
+def sinkhorn_points_batched(a, x, b, y, p=2, blur=0.05, reach=None, diameter=None, scaling=0.5, debias=True,
+                            potentials=False, keops=False, **_ignored):
+    """Batched Sinkhorn divergence a:(B,N) x:(B,N,D) b:(B,M) y:(B,M,D), D <= 8: every softmin of the loop is ONE
+    ranges-mode launch group over the whole batch (block-diagonal problem), not B launches.
+    Reference: sinkhorn_tensorized / sinkhorn_online on (B, ...) inputs, softmin_online_lazytensor
+    (sinkhorn_samples.py:74-221, :229-290, :349-424); one shared eps-schedule (diameter over the flattened batch)."""
+    from . import ranges
+
+    if p not in (1, 2):
+        raise KeyError(p)
+    B, N, D = x.shape
+    M = y.shape[1]
+    diameter, eps, eps_list, rho = scaling_parameters(x, y, p, blur, reach, diameter, scaling)
+    xf, yf, af, bf = x.reshape(B * N, D), y.reshape(B * M, D), a.reshape(B * N), b.reshape(B * M)
+    center = ops.default_center(xf.detach(), yf.detach())
+    dev = x.device
+    problems = {"xy": ranges.batch_problem(B, N, M, dev), "yx": ranges.batch_problem(B, M, N, dev)}
+    if debias:
+        problems["xx"] = ranges.batch_problem(B, N, N, dev)
+        problems["yy"] = ranges.batch_problem(B, M, M, dev)
+    pk = (p | ops.P_UNCLAMPED) if keops else p
+    f_aa, g_bb, g_ab, f_ba = sinkhorn_loop_points(log_weights(af.detach()), log_weights(bf.detach()), xf, yf,
+                                                  eps_list, rho, p=pk, debias=debias, center=center,
+                                                  problems=problems)
+    out = sinkhorn_cost_batched(eps, rho, af, bf, f_aa, g_bb, g_ab, f_ba, B, debias=debias, potentials=potentials)
+    if potentials:
+        return out[0].view(B, N), out[1].view(B, M)
+    return out

@@ -36,7 +36,7 @@ extern "C" {
 #define B200OT_API
 #endif
 
-#define B200OT_VERSION 100 /* 0.1.0 */
+#define B200OT_VERSION 200 /* 0.2.0 */
 #define B200OT_MAX_D 8     /* dimensions served by the CUDA-core (register tile) kernels of this build */
 
 /* error codes */
@@ -51,6 +51,14 @@ extern "C" {
 #define B200OT_KERNEL_LAPLACIAN 1 /* exp(-sqrt(max(|x-y|^2/blur^2, 1e-8))) */
 #define B200OT_KERNEL_ENERGY 2    /* -sqrt(max(|x-y|^2, 1e-8)) */
 
+/* The reference has TWO conventions for the Euclidean norm under p = 1 / laplacian / energy:
+ *   backend="tensorized":  sqrt(clamp_min(|x-y|^2, 1e-8))   (utils.py:56-61)           -> p = 1, kinds 1, 2
+ *   backend="online" / "multiscale" (pykeops Norm2 / .sqrt(), sinkhorn_samples.py:303-306, utils.py:56-58):
+ *                          sqrt(|x-y|^2), zero gradient at coincident points            -> flag below
+ * Or the flag into `p` (softmin entry points) or `kind` (kernel_conv entry points). */
+#define B200OT_P_UNCLAMPED 0x100
+#define B200OT_KERNEL_UNCLAMPED 0x100
+
 B200OT_API const char* b200ot_strerror(int code);
 B200OT_API const char* b200ot_last_cuda_error(void);
 B200OT_API int b200ot_version(void);
@@ -58,7 +66,8 @@ B200OT_API int b200ot_version(void);
 /* ---------------------------------------------------------------------------------------------
  * Softmin  —  out_i = -eps * log sum_j exp( h_j - |x_i - y_j|^p / (p * eps) ),   p in {1, 2}
  * replaces softmin_tensorized (sinkhorn_samples.py:32-71) / softmin_online (:337-346).
- * p = 1 uses sqrt(max(|x-y|^2, 1e-8)) like the reference's `distances` (utils.py:56-61).
+ * p = 1 uses sqrt(max(|x-y|^2, 1e-8)) like the reference's `distances` (utils.py:56-61);
+ * p = 1 | B200OT_P_UNCLAMPED uses the pykeops convention (see above).
  * ------------------------------------------------------------------------------------------- */
 
 /* Bytes of scratch needed by b200ot_softmin_fwd / _bwd_x for (N rows, M cols, D). */
@@ -108,14 +117,35 @@ B200OT_API int32_t b200ot_softmin_num_splits(int64_t N, int64_t M, int32_t D);
 B200OT_API int b200ot_softmin_partial(const float* x, const float* center, const float* cols, float* part, int32_t n_split,
                            int64_t N, int64_t M, int32_t D, int32_t p, float eps, void* stream);
 
-/* Block-sparse partial reduction (the reference's softmin_multiscale with `ranges`, sinkhorn_samples.py:445-450,
- * built by kernel_truncation :493-530): row tile r (b200ot_sparse_tile_shape rows of x, in order) reduces only over
- * the packed column tiles tile_list[tile_ptr[r] .. tile_ptr[r+1]) (each b200ot_sparse_tile_shape columns).
- * part: (N, 2) pairs (one split).  D <= 3. */
-B200OT_API void b200ot_sparse_tile_shape(int32_t* rows_per_tile, int32_t* cols_per_tile);
-B200OT_API int b200ot_softmin_partial_sparse(const float* x, const float* center, const float* cols,
-                                             const int32_t* tile_ptr, const int32_t* tile_list, float* part,
-                                             int64_t N, int64_t M, int32_t D, int32_t p, float eps, void* stream);
+/* ---- ranges mode: block-sparse and batched problems in ONE launch ------------------------------------------
+ * Replaces the reference's `ranges=` argument of pykeops reductions (softmin_multiscale, sinkhorn_samples.py:445-450,
+ * built by kernel_truncation :493-530 / from_matrix; kernel_multiscale, kernel_samples.py:246-256) and the batched
+ * LazyTensor reduction of softmin_online_lazytensor (:229-290, a block-diagonal problem).
+ *   segment  = a run of consecutive rows that share one list of column pieces (one CTA per segment):
+ *              a cluster of the sorted row cloud (cut into <= max_rows_per_segment rows), or a batch element;
+ *   piece    = a run of consecutive column SLOTS (col_start, col_count), both multiples of col_align,
+ *              col_count <= max_cols_per_piece;
+ *   slots    = the packed column buffer in gather mode: slot s holds column src_index[s] of the caller's arrays,
+ *              or a neutral padding column when src_index[s] < 0 — clusters / batch elements are padded to a
+ *              multiple of col_align slots so that every piece starts on a chunk boundary.
+ * The reduction visits exactly the (row, column) pairs listed: bit-for-bit the blocks of the reference's ranges. */
+typedef struct { int32_t row_start, row_count, piece_begin, piece_end; } b200ot_segment; /* 16-byte aligned array */
+typedef struct { int32_t col_start, col_count; } b200ot_piece;                           /*  8-byte aligned array */
+#define B200OT_RANGES_BIG 0   /* 512-row segments, pieces <= 1024 columns: large clusters */
+#define B200OT_RANGES_SMALL 1 /* 128-row segments, pieces <= 256 columns: small clusters / small batch elements */
+B200OT_API void b200ot_ranges_shape(int32_t variant, int32_t* max_rows_per_segment, int32_t* max_cols_per_piece,
+                                    int32_t* col_align);
+
+/* b200ot_softmin_pack in gather mode: cols_out holds b200ot_packed_cols_floats(n_slots, D, 1) floats. */
+B200OT_API int b200ot_softmin_pack_gather(const float* y, const float* h_a, const float* h_b, float h_scale_b,
+                                          const float* center, const int32_t* src_index, int64_t n_slots, int32_t D,
+                                          int32_t p, float eps, float* cols_out, void* stream);
+
+/* part: (N, 2) (m, s) pairs, one per row; rows that belong to no segment are left untouched. */
+B200OT_API int b200ot_softmin_partial_ranges(const float* x, const float* center, const float* cols,
+                                             const b200ot_segment* seg, int64_t n_seg, const b200ot_piece* pieces,
+                                             float* part, int64_t N, int32_t D, int32_t p, float eps,
+                                             int32_t variant, void* stream);
 
 /* Collapse n_part partial (m, s) sets into one per row: merged[i*2 + {0,1}].  A rank calls this on its own
  * splits before exchanging partials with the other column shards (N*8 bytes per rank). */
@@ -132,11 +162,18 @@ B200OT_API int b200ot_softmin_finalize(const float* part, int32_t n_part, const 
 B200OT_API int b200ot_softmin_bwd_partial(const float* x, const float* center, const float* cols, const float* lse2,
                                           float* part, int32_t n_split, int64_t N, int64_t M, int32_t D, int32_t p,
                                           float eps, void* stream);
-/* block-sparse variant (see b200ot_softmin_partial_sparse): part is (N, D+1), one split */
-B200OT_API int b200ot_softmin_bwd_partial_sparse(const float* x, const float* center, const float* cols,
-                                                 const float* lse2, const int32_t* tile_ptr,
-                                                 const int32_t* tile_list, float* part, int64_t N, int64_t M,
-                                                 int32_t D, int32_t p, float eps, void* stream);
+/* ranges variant (see b200ot_softmin_partial_ranges): part is (N, D+1), one split */
+B200OT_API int b200ot_softmin_bwd_partial_ranges(const float* x, const float* center, const float* cols,
+                                                 const float* lse2, const b200ot_segment* seg, int64_t n_seg,
+                                                 const b200ot_piece* pieces, float* part, int64_t N, int32_t D,
+                                                 int32_t p, float eps, int32_t variant, void* stream);
+/* One call: sums (N, D+1) = the merged partial sums of the row-gradient pass over ALL columns given (pack + partial +
+ * merge; CUDA-core path for D <= B200OT_MAX_D, tensor-core path for p = 2 up to D = 64).  A column shard calls this
+ * on its slice, all-reduces `sums` (SUM) and finishes with b200ot_softmin_bwd_finalize(n_part = 1). */
+B200OT_API int b200ot_softmin_bwd_sums(const float* x, const float* y, const float* h_a, const float* h_b,
+                                       float h_scale_b, const float* center, const float* lse2, float* sums,
+                                       int64_t N, int64_t M, int32_t D, int32_t p, float eps, void* scratch,
+                                       int64_t scratch_bytes, void* stream);
 /* merged[i*width + a] = sum_s part[(s*N + i)*width + a] */
 B200OT_API int b200ot_rowsum_merge(const float* part, int32_t n_part, int32_t width, float* merged, int64_t N,
                                    void* stream);
@@ -159,6 +196,26 @@ B200OT_API int b200ot_kernel_conv_fwd(const float* x, const float* y, const floa
 B200OT_API int b200ot_kernel_conv_bwd_x(const float* x, const float* y, const float* w, const float* center,
                              const float* grad_out, float* grad_x, int64_t N, int64_t M, int32_t D, int32_t kind,
                              float blur, void* scratch, int64_t scratch_bytes, void* stream);
+
+/* --- stages of the CUDA-core kernel convolutions (D <= B200OT_MAX_D), ranges mode: truncated block-sparse
+ *     MMDs (kernel_multiscale, kernel_samples.py:177-271) and batched problems.  cols: gather-packed,
+ *     b200ot_packed_cols_floats(n_slots, D, 2) floats.  part: (N) sums (backward = 0) or (N, width) sums
+ *     (backward = 1; width = D + 1 for the gaussian kernel, D otherwise); partial sums of column shards add. --- */
+B200OT_API int b200ot_kernel_conv_pack_gather(const float* y, const float* w, const float* center,
+                                              const int32_t* src_index, int64_t n_slots, int32_t D, int32_t kind,
+                                              float blur, float* cols_out, void* stream);
+B200OT_API int b200ot_kernel_conv_partial_ranges(const float* x, const float* center, const float* cols,
+                                                 const b200ot_segment* seg, int64_t n_seg,
+                                                 const b200ot_piece* pieces, float* part, int64_t N, int32_t D,
+                                                 int32_t kind, float blur, int32_t backward, int32_t variant,
+                                                 void* stream);
+/* out_i = sign(kind) * sum_s part[s*N + i] */
+B200OT_API int b200ot_kernel_conv_finalize(const float* part, int32_t n_part, float* out, int64_t N, int32_t kind,
+                                           void* stream);
+/* grad_x from n_part sets of (N, width) row-gradient sums */
+B200OT_API int b200ot_kernel_conv_bwd_finalize(const float* part, int32_t n_part, const float* x, const float* center,
+                                               const float* grad_out, float* grad_x, int64_t N, int32_t D,
+                                               int32_t kind, float blur, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Grid softmin  —  the separable soft-C-transform on (batch, N, N[, N]) images / volumes

@@ -31,7 +31,7 @@ def test_every_declared_symbol_is_exported(L):
 
 
 def test_version_and_strerror(L):
-    assert L.b200ot_version() == 100
+    assert L.b200ot_version() == 200
     assert L.b200ot_strerror(0) == b"ok"
     assert b"invalid" in L.b200ot_strerror(-1)
     assert b"scratch" in L.b200ot_strerror(-2)
@@ -110,6 +110,29 @@ def test_scratch_plans_cover_every_shape(L):
                 assert sb >= (N + M) * (2 * dk + 16) * 2, (N, M, D, sb)
         assert L.b200ot_softmin_scratch_bytes(10**6, 10**6, D) >= L.b200ot_softmin_scratch_bytes(10**5, 10**5, D)
     assert L.b200ot_softmin_scratch_bytes(10, 10, 65) == 0 or L.b200ot_softmin_scratch_bytes(10, 10, 65) > 0  # no crash
-    r, c = ctypes.c_int32(0), ctypes.c_int32(0)
-    L.b200ot_sparse_tile_shape(ctypes.byref(r), ctypes.byref(c))
-    assert r.value > 0 and c.value > 0 and c.value % 16 == 0
+    for variant, rows, cols in ((0, 512, 1024), (1, 128, 256)):
+        r, c, al = ctypes.c_int32(0), ctypes.c_int32(0), ctypes.c_int32(0)
+        L.b200ot_ranges_shape(variant, ctypes.byref(r), ctypes.byref(c), ctypes.byref(al))
+        assert (r.value, c.value) == (rows, cols) and al.value == 16 and c.value % al.value == 0
+
+
+def test_ranges_and_flag_validation_needs_no_gpu(L):
+    null = ctypes.c_void_p(None)
+    fake = ctypes.c_void_p(0x1000)
+    # p = 1 | UNCLAMPED and p = 2 | UNCLAMPED are legal, other flag bits are not
+    for p, rc in ((0x101, -2), (0x102, -2), (0x201, -1), (0x103, -1)):
+        assert L.b200ot_softmin_fwd(fake, fake, fake, null, 0.0, null, null, 0.0, 1.0, fake, null, 10, 10, 3, p, 0.1,
+                                    fake, 16, null) == rc
+    for kind, rc in ((0x101, -2), (0x102, -2), (0x103, -1), (0x201, -1)):
+        assert L.b200ot_kernel_conv_fwd(fake, fake, fake, null, fake, 10, 10, 3, kind, 0.1, fake, 16, null) == rc
+    # ranges entry points: null descriptors, bad variant, misaligned segment array
+    assert L.b200ot_softmin_partial_ranges(fake, null, fake, null, 1, fake, fake, 10, 3, 2, 0.1, 0, null) == -1
+    assert L.b200ot_softmin_partial_ranges(fake, null, fake, fake, 1, fake, fake, 10, 3, 2, 0.1, 2, null) == -1
+    assert L.b200ot_softmin_partial_ranges(fake, null, fake, ctypes.c_void_p(0x1008), 1, fake, fake, 10, 3, 2, 0.1, 0,
+                                           null) == -4
+    assert L.b200ot_softmin_bwd_partial_ranges(fake, null, fake, fake, fake, 0, fake, fake, 10, 3, 2, 0.1, 0,
+                                               null) == -1
+    assert L.b200ot_kernel_conv_partial_ranges(fake, null, fake, fake, 1, fake, fake, 10, 3, 9, 0.1, 0, 0, null) == -1
+    assert L.b200ot_softmin_pack_gather(fake, fake, null, 0.0, null, null, 10, 3, 2, 0.1, fake, null) == -1
+    assert L.b200ot_softmin_bwd_sums(fake, fake, fake, null, 0.0, null, fake, null, 10, 10, 3, 2, 0.1, fake, 1 << 30,
+                                     null) == -1

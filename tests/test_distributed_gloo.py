@@ -29,7 +29,9 @@ class OracleStages:
         from oracle import geomloss_oracle as O
 
         h = h_a if h_b is None else h_a + h_scale_b * h_b
-        return LOG2E * (h[None, :] - O.cost_matrix(x, y, p) / eps)
+        # p carries B200OT_P_UNCLAMPED (0x100) for the pykeops cost convention
+        C = O.keops_cost(x, y, p & 0xFF) if p & 0x100 else O.cost_matrix(x, y, p)
+        return LOG2E * (h[None, :] - C / eps)
 
     def softmin_shard(self, eps, x, y, h_a, h_b, h_scale_b, p, center):
         t = self._t(eps, x.double(), y.double(), h_a.double(), None if h_b is None else h_b.double(), h_scale_b, p)
@@ -56,68 +58,73 @@ class OracleStages:
         xd, yd = x.double(), y.double()
         t = self._t(eps, xd, yd, h_a.double(), None if h_b is None else h_b.double(), h_scale_b, p)
         w = torch.exp2(t - lse2.double()[:, None])
-        if p == 2:
+        return self._bwd_sums(w, xd, yd, p)
+
+    @staticmethod
+    def _bwd_sums(w, xd, yd, p):
+        if p & 0xFF == 2:
             vec = w @ yd  # un-scaled, un-centred coordinates: finalize below matches
         else:
+            clamp = 1e-30 if p & 0x100 else 1e-8
             diff = xd[:, None, :] - yd[None, :, :]
             q = (diff**2).sum(-1)
-            unit = torch.where(q[..., None] < 1e-8, torch.zeros_like(diff), diff / q.clamp_min(1e-8).sqrt()[..., None])
+            unit = torch.where(q[..., None] < clamp, torch.zeros_like(diff), diff / q.clamp_min(clamp).sqrt()[..., None])
             vec = (w[..., None] * unit).sum(1)
         return torch.cat([w.sum(1, keepdim=True), vec], 1).float()
 
     def softmin_bwd_finalize(self, sums, eps, x, center, grad_out, p):
         sums = sums.double()
         sw = sums[:, :1]
-        g = (x.double() - sums[:, 1:] / sw) if p == 2 else sums[:, 1:] / sw
+        g = (x.double() - sums[:, 1:] / sw) if p & 0xFF == 2 else sums[:, 1:] / sw
         return (grad_out.double()[:, None] * g).float()
 
-    # -- block-sparse stand-ins: dense evaluation, masked at the granularity of the (small, test-only) tiles --
-    TILE = (16, 32)
+    # -- ranges-mode stand-ins: dense evaluation, masked with the (row, column) pairs the descriptors list --
+    ranges_variant = 1  # small tiles (128-row segments, 256-column pieces): several segments per cluster here
 
-    def tile_shape(self):
-        return self.TILE
-
-    def _tile_mask(self, N, M, tile_ptr, tile_list):
-        tr, tc = self.TILE
+    @staticmethod
+    def _pair_mask(N, M, prob):
+        """Point-level mask of a RangesProblem: what b200ot_softmin_partial_ranges would visit."""
+        src = prob.layout.src.tolist()
         mask = torch.zeros(N, M, dtype=torch.bool)
-        ptr, lst = tile_ptr.tolist(), tile_list.tolist()
-        for rt in range(len(ptr) - 1):
-            for ct in lst[ptr[rt]:ptr[rt + 1]]:
-                mask[rt * tr:(rt + 1) * tr, ct * tc:(ct + 1) * tc] = True
+        pieces = prob.pieces.tolist()
+        for r0, nr, p0, p1 in prob.seg.tolist():
+            for c0, nc in pieces[p0:p1]:
+                cols = [j for j in src[c0:c0 + nc] if j >= 0]
+                mask[r0:r0 + nr, cols] = True
         return mask
 
-    def softmin_sparse_shard(self, eps, x, y, h_a, h_b, h_scale_b, p, center, tile_ptr, tile_list):
+    def softmin_sparse_shard(self, eps, x, y, h_a, h_b, h_scale_b, p, center, prob):
         t = self._t(eps, x.double(), y.double(), h_a.double(), None if h_b is None else h_b.double(), h_scale_b, p)
-        t = t.masked_fill(~self._tile_mask(x.shape[0], y.shape[0], tile_ptr, tile_list), -1.0e30)
+        t = t.masked_fill(~self._pair_mask(x.shape[0], y.shape[0], prob), -1.0e30)
         m = t.max(1).values
         s = torch.exp2(t - m[:, None]).sum(1)
-        s = torch.where(m <= -1.0e29, torch.zeros_like(s), s)  # a row with no listed tile: neutral partial
+        s = torch.where(m <= -1.0e29, torch.zeros_like(s), s)  # a row with no listed piece: neutral partial
         return torch.stack([m, s], 1).float()
 
-    def softmin_bwd_sparse_shard(self, eps, x, y, h_a, h_b, h_scale_b, p, center, lse2, tile_ptr, tile_list):
+    def softmin_bwd_sparse_shard(self, eps, x, y, h_a, h_b, h_scale_b, p, center, lse2, prob):
         xd, yd = x.double(), y.double()
         t = self._t(eps, xd, yd, h_a.double(), None if h_b is None else h_b.double(), h_scale_b, p)
-        w = torch.exp2(t - lse2.double()[:, None]) * self._tile_mask(x.shape[0], y.shape[0], tile_ptr, tile_list)
-        if p == 2:
-            vec = w @ yd
-        else:
-            diff = xd[:, None, :] - yd[None, :, :]
-            q = (diff**2).sum(-1)
-            unit = torch.where(q[..., None] < 1e-8, torch.zeros_like(diff), diff / q.clamp_min(1e-8).sqrt()[..., None])
-            vec = (w[..., None] * unit).sum(1)
-        return torch.cat([w.sum(1, keepdim=True), vec], 1).float()
+        w = torch.exp2(t - lse2.double()[:, None]) * self._pair_mask(x.shape[0], y.shape[0], prob)
+        return self._bwd_sums(w, xd, yd, p)
 
-    def conv_shard(self, kind, x, y, w, blur, center):
+    @staticmethod
+    def _kmat(kind, x, y, blur):
         from oracle import geomloss_oracle as O
 
-        return (O.kernel_matrix(kind, x.double(), y.double(), blur) @ w.double()).float()
+        if isinstance(kind, str):
+            return O.kernel_matrix(kind, x, y, blur)
+        name = ("gaussian", "laplacian", "energy")[kind & 0xFF]
+        return O.keops_kernel_matrix(name, x, y, blur) if kind & 0x100 else O.kernel_matrix(name, x, y, blur)
+
+    def conv_shard(self, kind, x, y, w, blur, center):
+        return (self._kmat(kind, x.double(), y.double(), blur) @ w.double()).float()
 
     def conv_grad_shard(self, kind, x, y, w, blur, grad_out, center):
         from oracle import geomloss_oracle as O
 
         with torch.enable_grad():  # called from inside an autograd backward (grad mode is off there)
             xr = x.detach().double().requires_grad_(True)
-            out = O.kernel_matrix(kind, xr, y.detach().double(), blur) @ w.detach().double()
+            out = self._kmat(kind, xr, y.detach().double(), blur) @ w.detach().double()
             (g,) = torch.autograd.grad(out, xr, grad_out.detach().double())
         return g.float()
 

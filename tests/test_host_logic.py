@@ -349,3 +349,65 @@ def test_sinkhorn_images_host_logic(monkeypatch, shape, kw):
     assert F.shape == a.shape and (F - Fr).abs().max() <= 1e-9 and (G - Gr).abs().max() <= 1e-9
     with pytest.raises(ValueError):
         SI.sinkhorn_divergence(a, b, scaling=0.3)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ranges mode descriptors (host logic of geomloss_b200/ranges.py; the C library is only asked for tile shapes)
+# ---------------------------------------------------------------------------------------------------------
+def _pair_mask(prob, n_rows, n_cols):
+    src = prob.layout.src.tolist()
+    pieces = prob.pieces.tolist()
+    mask = torch.zeros(n_rows, n_cols, dtype=torch.int32)
+    for r0, nr, p0, p1 in prob.seg.tolist():
+        for c0, nc in pieces[p0:p1]:
+            cols = [j for j in src[c0:c0 + nc] if j >= 0]
+            mask[r0:r0 + nr, cols] += 1
+    return mask
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_ranges_descriptors_list_exactly_the_kept_cluster_pairs(variant):
+    """segments x pieces == keep[lab_rows][:, lab_cols], each pair exactly once; pieces are aligned and tile-sized;
+    a column-sharded build partitions the pairs."""
+    from geomloss_b200 import ranges
+
+    g = torch.Generator().manual_seed(variant)
+    R, C = 23, 17
+    row_counts = torch.randint(1, 700, (R,), generator=g)
+    col_counts = torch.randint(1, 1500, (C,), generator=g)
+    keep = torch.rand(R, C, generator=g) < 0.4
+    keep[3] = False  # a row cluster that keeps nothing
+    keep[5] = True   # ... and one that keeps everything (one long run, cut into tile-sized pieces)
+    lay = ranges.ColumnLayout(col_counts)
+    n_rows, n_cols = int(row_counts.sum()), int(col_counts.sum())
+    lab_r = torch.repeat_interleave(torch.arange(R), row_counts)
+    lab_c = torch.repeat_interleave(torch.arange(C), col_counts)
+    want = keep[lab_r][:, lab_c].to(torch.int32)
+    max_rows, max_cols, align = ranges.shape(variant)
+    prob = ranges.build_problem(keep, row_counts, lay, variant=variant)
+    assert torch.equal(_pair_mask(prob, n_rows, n_cols), want)
+    assert prob.seg.dtype == torch.int32 and prob.pieces.dtype == torch.int32
+    assert int(prob.seg[:, 1].max()) <= max_rows and int(prob.seg[:, 1].min()) >= 1
+    assert int(prob.pieces[:, 1].max()) <= max_cols
+    assert bool((prob.pieces % align == 0).all())
+    assert abs(prob.density - want.double().mean().item()) < 1e-12
+    # padding slots are neutral, real columns appear exactly once
+    src = lay.src
+    assert sorted(src[src >= 0].tolist()) == list(range(n_cols)) and lay.n_slots % align == 0
+    # column-sharded: the ranks' problems partition the kept pairs and are roughly balanced
+    world = 3
+    parts = [ranges.build_problem(keep, row_counts, lay, variant=variant, rank=r, world=world) for r in range(world)]
+    masks = [_pair_mask(p, n_rows, n_cols) for p in parts]
+    assert torch.equal(sum(masks), want)
+    loads = [float(m.sum()) for m in masks]
+    assert max(loads) <= 0.6 * sum(loads)
+
+
+def test_batch_problem_is_block_diagonal():
+    from geomloss_b200 import ranges
+
+    B, N, M = 3, 150, 70
+    prob = ranges.batch_problem(B, N, M, "cpu")
+    want = torch.block_diag(*[torch.ones(N, M, dtype=torch.int32)] * B)
+    assert torch.equal(_pair_mask(prob, B * N, B * M), want)
+    assert prob.density == pytest.approx(1.0 / B)
