@@ -45,8 +45,10 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=1_000_000, help="points per cloud (N = M)")
     ap.add_argument("--blur", type=float, default=0.01)
-    ap.add_argument("--e2e-steps", type=int, default=2, help="full SamplesLoss calls timed end to end")
-    ap.add_argument("--e2e-scaling", type=float, default=0.5)
+    ap.add_argument("--e2e-steps", type=int, default=1, help="full SamplesLoss calls timed end to end")
+    ap.add_argument("--e2e-scaling", type=float, default=0.9,
+                    help="eps-scaling ratio of the end-to-end loss: .9 = BASELINE configs[1]'s '~50 iters' (51 eps values)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip BASELINE configs[2..4] (config.secondary)")
     ap.add_argument("--cpu-n", type=int, default=16000, help="cloud size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -114,10 +116,45 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # the reference arm: the reference's dense CPU algorithm (oracle port) on the host cores
 # ----------------------------------------------------------------------------------------------------
+class _RefOps:
+    """softmin_dense / cost_matrix served by the UNMODIFIED reference installed under oracle/_ref (oracle/make_ref.sh):
+    softmin_tensorized (sinkhorn_samples.py:32-71) and cost_routines[p] (:26-29)."""
+
+    kind = "reference"
+
+    def __init__(self, ss):
+        self.ss = ss
+
+    def cost_matrix(self, x, y, p):
+        return self.ss.cost_routines[p](x, y)
+
+    def softmin_dense(self, eps, C, h):
+        return self.ss.softmin_tensorized(eps, C, h)
+
+
+def reference_ops():
+    """(ops, kind): the real reference if oracle/_ref is present, else the oracle port."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if os.path.isdir(os.path.join(ref_dir, "geomloss")):
+        sys.path.insert(0, ref_dir)
+        try:
+            from geomloss._legacy import sinkhorn_samples as ss
+
+            if os.path.realpath(ss.__file__).startswith(os.path.realpath(ref_dir)):
+                return _RefOps(ss), "reference"
+        except Exception:  # pragma: no cover - fall through to the port
+            pass
+        finally:
+            sys.path.remove(ref_dir)
+    from oracle import geomloss_oracle as O
+
+    return O, "port"
+
+
 def dense_iteration_state(n, blur, seed=0):
     import torch
 
-    from oracle import geomloss_oracle as O
+    O, _ = reference_ops()
 
     g = torch.Generator().manual_seed(seed)
     x = torch.rand(n, 3, generator=g)
@@ -176,6 +213,7 @@ def run_reference(args):
     pairs = 4.0 * n * n
     value = pairs * args.steps / dt
     cores = torch.get_num_threads()
+    kind = reference_ops()[1]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -184,9 +222,10 @@ def run_reference(args):
                                "iteration (4 dense softmins on stored N x N cost matrices), bounded sample "
                                "N=M=%d of the N=M=1e6 problem (4 TB per cost matrix at full size)" % (args.blur, n),
                    "N": n, "M": n, "D": 3, "pairs_per_step": pairs},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"N=M={n}, {args.steps} dense Sinkhorn iterations, torch CPU {cores} threads, "
-                                   f"{cpu_model()}"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"N=M={n}, {args.steps} dense Sinkhorn iterations "
+                                   f"({'the unmodified reference (oracle/_ref): softmin_tensorized on cost_routines[2] matrices' if kind == 'reference' else 'oracle port of the tensorized path'}), "
+                                   f"torch CPU {cores} threads, {cpu_model()}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -306,7 +345,10 @@ def run_b200(args):
             yd = y_h.to(dev, non_blocking=True)
             return loss(xd, yd).item()  # .item(): device -> host read of the result
 
-        e2e_call()  # warm-up
+        warm = SamplesLoss("sinkhorn", p=2, blur=args.blur, scaling=0.5, diameter=3**0.5, backend="online")
+        if engine:
+            engine.attach(warm)
+        warm(x_h.to(dev, non_blocking=True), y_h.to(dev, non_blocking=True)).item()  # warm-up: the short ladder
         sync_all()
         t0 = time.perf_counter()
         vals = [e2e_call() for _ in range(args.e2e_steps)]
@@ -320,6 +362,12 @@ def run_b200(args):
                        f"backend='online')"
                        f"(x_host->cuda, y_host->cuda).item(): {n_eps} eps values, {4 * (n_eps + 2)} softmins",
                "s_per_call": dt.item() / args.e2e_steps, "loss_value": vals[-1]}
+
+    # ---- BASELINE configs[2], [3], [4]: own CUDA-event timings + in-run spot parity (config.secondary) ----
+    secondary = None
+    if not args.no_secondary:
+        secondary = secondary_configs(torch, dev, world, rank, engine, peaks_file=os.path.join(ROOT, "MEASURED_PEAKS.json"),
+                                      mufu_peak=ceil["mufu_ex2_per_s"])
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample (rank 0, N=1 only) ----
     cpu = None
@@ -356,14 +404,15 @@ def run_b200(args):
                 "parallelism": "single GPU" if world == 1 else f"columns of every softmin sharded x{world}, "
                                                                 "1 all_gather of (N,2) fp32 per softmin",
                 "finite": finite,
+                "secondary": secondary,
             },
             "e2e": e2e,
             "gpu_launches": gpu_launches,
             "clocks": clocks,
             "roofline": {
                 "bound": "sfu",
-                "kernel": "softmin_partial_kernel (1 MUFU.EX2 per pair; SURVEY.md 8(d): the path is exp-bound, "
-                          "not HBM-bound)",
+                "kernel": "softmin_partial_kernel (1 exponential per pair: 7 of 8 column pairs on MUFU.EX2, 1 of 8 on "
+                          "the FMA-pipe polynomial; SURVEY.md 8(d): the path is exp-bound, not HBM-bound)",
                 "achieved": k_rate / 1e9, "peak": mufu_peak / 1e9, "unit": "Gexp/s", "frac": k_rate / mufu_peak,
                 "peak_source": "MUFU.EX2 micro-benchmark (b200ot_ubench) run in this process after the timed region",
                 "kernel_ms": kern["ms_per_launch"], "kernel_share_of_step": kern["ms_per_launch"] * 4 / (total_ms / args.steps),
@@ -373,12 +422,189 @@ def run_b200(args):
                         "peak_gbs": hbm_peak, "frac": alg_bytes / (kern["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"},
                 "traffic": traffic,
+                "traffic_source": "profiles/softmin_partial_ncu_summary.json (dram__bytes_read.sum + dram__bytes_write.sum "
+                                  "of one ncu --set full capture of this kernel at this shape; not re-measured per run)",
             },
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+
+# ----------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2], [3], [4] — reported inside config.secondary of the same JSON line
+# ----------------------------------------------------------------------------------------------------
+def _ev_time(torch, dev, fn, reps=2, warm=1):
+    """Best CUDA-event time (s) of fn over `reps` runs after `warm` warm-ups, plus the last result."""
+    out = None
+    for _ in range(warm):
+        out = fn()
+    torch.cuda.synchronize(dev)
+    best = None
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t = e0.elapsed_time(e1) * 1e-3
+        best = t if best is None else min(best, t)
+    return best, out
+
+
+def secondary_configs(torch, dev, world, rank, engine, peaks_file, mufu_peak):
+    import math
+
+    import torch.distributed as dist
+
+    from geomloss_b200 import SamplesLoss, multiscale, ops, ranges, sinkhorn_divergence
+    from geomloss_b200.sinkhorn_images import softmin_grid
+
+    out = {}
+    peaks = json.load(open(peaks_file)) if os.path.exists(peaks_file) else {}
+    tensor_peak = peaks.get("bf16_tflops_sustained", 1450.0) * 1e12
+
+    if world == 1:
+        # ---- configs[2]: SamplesLoss('gaussian') N=M=1e6, D=64 (tensor-core path) ----
+        N, D = 1_000_000, 64
+        g = torch.Generator().manual_seed(0)
+        x = torch.rand(N, D, generator=g).to(dev)
+        y = torch.rand(N, D, generator=g).to(dev)
+        L = SamplesLoss("gaussian", blur=0.05, backend="online")
+        t_fwd, _ = _ev_time(torch, dev, lambda: L(x, y), reps=2)
+        xg = x.clone().requires_grad_(True)
+
+        def fwd_bwd():
+            v = L(xg, y)
+            torch.autograd.grad(v, xg)
+            return v
+
+        t_fb, _ = _ev_time(torch, dev, fwd_bwd, reps=2)
+        fwd_rate = 3.0 * N * N / t_fwd          # K_xx a, K_yy b, K_xy b
+        bwd_rate = 2.0 * N * N / (t_fb - t_fwd)  # row gradients of the xx and xy terms
+        # spot parity at blur = 2 (at the config's blur = .05 every off-diagonal kernel value underflows in [0,1]^64:
+        # SURVEY.md 8(d)); 128 sampled rows of K_xy @ b against fp64 brute force on the device
+        w = torch.full((N,), 1.0 / N, device=dev)
+        rows = torch.randint(0, N, (128,), generator=g).to(dev)
+        got = ops.kernel_conv_raw("gaussian", x, y, w, 2.0, center=ops.default_center(x, y))[rows].double()
+        xr = x[rows].double()
+        d2 = (xr * xr).sum(1)[:, None] - 2 * xr @ y.double().t() + (y.double() ** 2).sum(1)[None, :]
+        want = (torch.exp(-d2 / 8.0) @ w.double())
+        out["cfg3_gaussian_mmd_D64"] = {
+            "workload": "SamplesLoss('gaussian', blur=.05) N=M=1e6 D=64, uniform in [0,1]^64",
+            "s_fwd": t_fwd, "s_fwd_bwd": t_fb, "fwd_pairs_per_s": fwd_rate, "bwd_pairs_per_s": bwd_rate,
+            "sfu_frac_fwd": fwd_rate / mufu_peak, "sfu_frac_bwd": bwd_rate / mufu_peak,
+            "tensor_frac_fwd_algorithmic_128_flop_per_pair": fwd_rate * 128 / tensor_peak,
+            "tensor_frac_fwd_issued_416_flop_per_pair": fwd_rate * 416 / tensor_peak,
+            "tensor_peak_tflops": tensor_peak / 1e12,
+            "spot_parity": {"what": "128 sampled rows of K_xy @ b at blur=2 vs fp64 brute force",
+                            "max_rel_err": float(((got - want).abs() / want.abs()).max())},
+        }
+        del x, y, xg, d2
+        torch.cuda.empty_cache()
+
+        # ---- configs[4]: unbalanced Sinkhorn on a 256^3 volume (separable grid softmin) ----
+        n = 256
+        ax = torch.linspace(0, 1, n, device=dev)
+        X, Y, Z = torch.meshgrid(ax, ax, ax, indexing="ij")
+
+        def blobs(seed, mass):
+            gg = torch.Generator().manual_seed(seed)
+            f = torch.full((n, n, n), 1e-3, device=dev)
+            for _ in range(3):
+                c = 0.25 + 0.5 * torch.rand(3, generator=gg)
+                s = 0.05 + 0.1 * float(torch.rand(1, generator=gg))
+                f = f + torch.exp(-((X - c[0]) ** 2 + (Y - c[1]) ** 2 + (Z - c[2]) ** 2) / (2 * s * s))
+            return (f * (mass / f.sum()))[None, None].contiguous()
+
+        a, b = blobs(0, 1.0), blobs(1, 1.3)
+        h = torch.log(a)
+        pot = 0.01 * torch.randn(1, 1, n, n, n, generator=torch.Generator().manual_seed(2)).to(dev)
+        eps = (1.0 / n) ** 2
+        t_op, res = _ev_time(torch, dev, lambda: softmin_grid(eps, 2, h, pot, 1.0 / eps), reps=5)
+        t_div, val = _ev_time(torch, dev, lambda: sinkhorn_divergence(a, b, p=2, blur=1.0 / n, reach=0.3, scaling=0.5), reps=2)
+        # spot parity: 64 sampled output lines along the last axis, fp64 on the device, separable form
+        hh = (h + pot / eps)[0, 0].double()
+        xs = torch.arange(n, device=dev, dtype=torch.float64) / n / math.sqrt(2 * eps)
+        k = -(xs[:, None] - xs[None, :]) ** 2
+        i0 = torch.randint(0, n, (8,), generator=torch.Generator().manual_seed(3)).to(dev)
+        i1 = torch.randint(0, n, (8,), generator=torch.Generator().manual_seed(4)).to(dev)
+        t2 = torch.logsumexp(hh[:, :, None, :] + k[None, None, :, :], dim=-1)          # axis 2: (j0, j1, i2)
+        t1 = torch.logsumexp(t2[:, None, :, :] + k[i1][None, :, :, None], dim=2)        # axis 1 at i1: (j0, 8, i2)
+        t0 = torch.logsumexp(t1[None, :, :, :] + k[i0][:, :, None, None], dim=1)        # axis 0 at i0: (8, 8, i2)
+        want = -eps * t0
+        got = res[0, 0][i0][:, i1].double()
+        out["cfg5_grid_256"] = {
+            "workload": "sinkhorn_images.sinkhorn_divergence(a, b, p=2, blur=1/256, reach=.3, scaling=.5) on 256^3",
+            "softmin_grid_ms": t_op * 1e3, "softmin_grid_pairs_per_s": 3.0 * n**4 / t_op,
+            "sfu_frac": 3.0 * n**4 / t_op / mufu_peak,
+            "hbm_GBps_algorithmic": 3 * 8 * n**3 / t_op / 1e9, "divergence_ms": t_div * 1e3, "value": float(val[0]),
+            "spot_parity": {"what": "8 x 8 sampled output lines (all 256 entries) of one softmin_grid call vs fp64",
+                            "max_abs_err": float((got - want).abs().max()), "scale": float(want.abs().max())},
+        }
+        del a, b, h, pot, res, hh, t2, t1, t0, X, Y, Z
+        torch.cuda.empty_cache()
+
+    # ---- configs[3]: multiscale Sinkhorn (eps-scaling .5, truncate 5): N=M=1e6 at every --gpus, 1e7 at --gpus 8 ----
+    sizes = [1_000_000] + ([10_000_000] if world >= 8 else [])
+    ms = {}
+    for N in sizes:
+        g = torch.Generator().manual_seed(0)
+        x = torch.rand(N, 3, generator=g).to(dev)
+        y = torch.rand(N, 3, generator=g).to(dev)
+        L = SamplesLoss("sinkhorn", p=2, blur=0.01, scaling=0.5, truncate=5, backend="multiscale")
+        if engine:
+            engine.attach(L)
+        stats = {}
+        orig_build = ranges.build_problem
+
+        def spy(*a, **k):
+            pr = orig_build(*a, **k)
+            stats.setdefault("density", []).append(pr.density)
+            return pr
+
+        ranges.build_problem = spy
+        try:
+            t, v = _ev_time(torch, dev, lambda: L(x, y), reps=1, warm=1)
+        finally:
+            ranges.build_problem = orig_build
+        tt = torch.tensor([t], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms[f"N{N}"] = {"s_fwd": float(tt), "value": float(v),
+                       "kept_pair_fraction": (sum(stats["density"]) / len(stats["density"])) if stats.get("density") else None}
+        del x, y
+        torch.cuda.empty_cache()
+    if world == 1:
+        # operator-level spot parity of the ranges mode at full size: a geometric cluster mask, 64 sampled rows
+        N = 1_000_000
+        g = torch.Generator().manual_seed(1)
+        x, y = torch.rand(N, 3, generator=g).to(dev), torch.rand(N, 3, generator=g).to(dev)
+        w = torch.full((N,), 1.0 / N, device=dev)
+        cs = math.sqrt(3) / (math.sqrt(3) * 2000 ** (1 / 3))
+        (_, x_c), (_, x_s), lab_x, _, cnt_x = multiscale.clusterize(w, x, scale=cs)
+        (_, y_c), (_, y_s), lab_y, _, cnt_y = multiscale.clusterize(w, y, scale=cs)
+        keep = ((x_c[:, None, :] - y_c[None, :, :]) ** 2).sum(-1) < 0.2**2
+        prob = ranges.build_problem(keep, cnt_x, ranges.ColumnLayout(cnt_y))
+        h = torch.randn(N, generator=g).to(dev)
+        eps = 1e-3
+        t_op, (res, _) = _ev_time(torch, dev, lambda: ranges.softmin_ranges_raw(eps, x_s, y_s, h, None, 0.0, prob, p=2,
+                                                                              center=ops.default_center(x, y)), reps=3)
+        rows = torch.randint(0, N, (64,), generator=g).to(dev)
+        colmask = keep[lab_x[rows]][:, lab_y]
+        d2 = ((x_s[rows].double()[:, None, :] - y_s.double()[None, :, :]) ** 2).sum(-1) / 2
+        want = -eps * torch.logsumexp((h.double()[None, :] - d2 / eps).masked_fill(~colmask, -float("inf")), dim=1)
+        ms["ranges_operator_N1e6"] = {
+            "kept_pair_fraction": prob.density, "ms": t_op * 1e3, "pairs_per_s": prob.density * N * N / t_op,
+            "sfu_frac": prob.density * N * N / t_op / mufu_peak,
+            "spot_parity": {"what": "64 sampled rows of one ranges-mode softmin (cluster mask: centroids closer than .2) vs fp64 "
+                                    "brute force over the kept columns", "max_abs_err": float((res[rows].double() - want).abs().max()),
+                            "scale": float(want.abs().max())}}
+    ms["workload"] = "SamplesLoss('sinkhorn', p=2, blur=.01, scaling=.5, truncate=5, backend='multiscale') on uniform-in-cube clouds"
+    out["cfg4_multiscale"] = ms
+    return out
 
 
 def kernel_pass(L, ops, torch, dev, x, y, h_a, h_b, inv, center, eps, p, flush, reps, world, rank):
@@ -454,10 +680,12 @@ def cpu_baseline(args):
             if dt > 10.0 or it >= 50:
                 break
     cores = torch.get_num_threads()
-    return {"value": 4.0 * n * n * it / dt, "unit": UNIT, "cores": cores, "kind": "port",
+    kind = reference_ops()[1]
+    what = ("the unmodified reference's softmin_tensorized (oracle/_ref)" if kind == "reference"
+            else "oracle port of the reference's tensorized path")
+    return {"value": 4.0 * n * n * it / dt, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": f"{it} dense symmetric Sinkhorn iterations (4 softmins each) at N=M={n}, D=3, blur={args.blur}, "
-                      f"oracle port of the reference's tensorized path, torch CPU {cores} threads, {cpu_model()}, "
-                      f"{dt:.1f} s"}
+                      f"{what}, torch CPU {cores} threads, {cpu_model()}, {dt:.1f} s"}
 
 
 if __name__ == "__main__":
