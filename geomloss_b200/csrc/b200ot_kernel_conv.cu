@@ -327,7 +327,7 @@ extern "C" {
 B200OT_API int64_t b200ot_kernel_conv_scratch_bytes(int64_t N, int64_t M, int32_t D) {
   if (N <= 0 || M <= 0 || D <= 0) return 0;
   if (tc_supported_dim(D)) return tc_scratch_bytes(N, M, D);
-  const ReducePlan pl = make_plan(N, M);
+  const ReducePlan pl = make_plan(N, M, D);
   const int64_t cols = b200ot_packed_cols_floats(M, D, 2) * 4;
   const int64_t part = (int64_t)pl.n_split * N * 4 * (D + 1);
   return round_up64(cols, 256) + round_up64(part, 256);
@@ -396,7 +396,7 @@ B200OT_API int b200ot_kernel_conv_fwd(const float* x, const float* y, const floa
   if (((uintptr_t)scratch) & 15) return B200OT_EALIGN;
   if (scratch_bytes < b200ot_kernel_conv_scratch_bytes(N, M, D)) return B200OT_ESCRATCH;
   if (tc) return conv_fwd_tc(x, y, w, center, out, N, M, D, blur, scratch, (cudaStream_t)stream);
-  const ReducePlan pl = make_plan(N, M);
+  const ReducePlan pl = make_plan(N, M, D);
   const ConvScales cs = conv_scales(kind, blur);
   float* cols = reinterpret_cast<float*>(scratch);
   float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) +
@@ -433,7 +433,7 @@ B200OT_API int b200ot_kernel_conv_bwd_x(const float* x, const float* y, const fl
     B200OT_CUDA_TRY(cudaGetLastError());
     return B200OT_OK;
   }
-  const ReducePlan pl = make_plan(N, M);
+  const ReducePlan pl = make_plan(N, M, D);
   const ConvScales cs = conv_scales(kind, blur);
   float* cols = reinterpret_cast<float*>(scratch);
   float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) +

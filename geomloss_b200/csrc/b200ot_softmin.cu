@@ -146,13 +146,13 @@ B200OT_API int64_t b200ot_packed_cols_floats(int64_t M, int32_t D, int32_t extra
 B200OT_API int32_t b200ot_softmin_num_splits(int64_t N, int64_t M, int32_t D) {
   (void)D;
   if (N <= 0 || M <= 0) return 0;
-  return make_plan(N, M).n_split;
+  return make_plan(N, M, D).n_split;
 }
 
 B200OT_API int64_t b200ot_softmin_scratch_bytes(int64_t N, int64_t M, int32_t D) {
   if (N <= 0 || M <= 0 || D <= 0) return 0;
   if (tc_supported_dim(D)) return tc_scratch_bytes(N, M, D);
-  const ReducePlan pl = make_plan(N, M);
+  const ReducePlan pl = make_plan(N, M, D);
   const int64_t cols = b200ot_packed_cols_floats(M, D, 1) * 4;
   // forward partials are (m, s) pairs; the backward pass keeps D+1 sums per (split, row)
   const int64_t part = (int64_t)pl.n_split * N * 4 * (D + 1 > 2 ? D + 1 : 2);
@@ -174,7 +174,7 @@ B200OT_API int b200ot_softmin_partial(const float* x, const float* center, const
   if (!x || !cols || !part || N <= 0 || M <= 0 || !supported_simt_dim(D) || !valid_p(p) || !(eps > 0.f))
     return B200OT_EINVAL;
   if ((((uintptr_t)cols) & 15) || (((uintptr_t)part) & 7)) return B200OT_EALIGN;
-  const ReducePlan pl = make_plan(N, M);
+  const ReducePlan pl = make_plan(N, M, D);
   if (n_split != pl.n_split) return B200OT_EINVAL;
   return softmin_partial_impl(x, center, cols, part, pl, N, D, p, eps, (cudaStream_t)stream);
 }
@@ -252,7 +252,7 @@ B200OT_API int b200ot_softmin_fwd(const float* x, const float* y, const float* h
     if (rc) return rc;
     return b200ot_softmin_finalize(tc_part, n_part, out_old, alpha_old, beta, out, lse2_out, N, eps, stream);
   }
-  const ReducePlan pl = make_plan(N, M);
+  const ReducePlan pl = make_plan(N, M, D);
   float* cols = reinterpret_cast<float*>(scratch);
   float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) +
                                          round_up64(b200ot_packed_cols_floats(M, D, 1) * 4, 256));

@@ -106,7 +106,7 @@ B200OT_API int b200ot_softmin_bwd_partial(const float* x, const float* center, c
       !(eps > 0.f))
     return B200OT_EINVAL;
   if (((uintptr_t)cols) & 15) return B200OT_EALIGN;
-  const ReducePlan pl = make_plan(N, M);
+  const ReducePlan pl = make_plan(N, M, D);
   if (n_split != pl.n_split) return B200OT_EINVAL;
   const int pe = p_exponent(p);
   const float scale = softmin_coord_scale(pe, eps);
@@ -163,7 +163,7 @@ static int softmin_bwd_partials(const float* x, const float* y, const float* h_a
   if (tc)
     return bwd_partial_tc(1, x, y, nullptr, h_a, h_b, h_scale_b, lse2, center, softmin_coord_scale(2, eps), N, M, D,
                           scratch, part_out, n_part_out, (cudaStream_t)stream, nullptr);
-  const ReducePlan pl = make_plan(N, M);
+  const ReducePlan pl = make_plan(N, M, D);
   float* cols = reinterpret_cast<float*>(scratch);
   float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) +
                                          round_up64(b200ot_packed_cols_floats(M, D, 1) * 4, 256));

@@ -216,6 +216,7 @@ struct Problem {
 };
 
 static const char* g_filter = nullptr;
+static int g_nsplit = 0;  // > 0: override the number of column splits (wave-quantisation study)
 
 template <class C>
 static void run_variant(const char* name, Problem& P, int reps) {
@@ -229,6 +230,7 @@ static void run_variant(const char* name, Problem& P, int reps) {
   if (want > 64) want = 64;
   if (want > ntiles) want = ntiles;
   if (want < 1) want = 1;
+  if (g_nsplit > 0) want = g_nsplit < ntiles ? g_nsplit : ntiles;
   const int tps = (int)ceil_div64(ntiles, want);
   const int nsplit = (int)ceil_div64(ntiles, tps);
   const float scale = p == 2 ? sqrtf(kLog2e / P.eps) : kLog2e / P.eps;
@@ -247,7 +249,7 @@ static void run_variant(const char* name, Problem& P, int reps) {
   dim3 grid((unsigned)row_tiles, (unsigned)nsplit);
   auto launch = [&]() {
     kern<<<grid, C::NT + 32, C::SMEM_BYTES>>>(P.x, P.center, scale, clampq, P.cols, (float2*)P.part, P.N, ntiles,
-                                              tps, (const int*)nullptr, (const int*)nullptr);
+                                              tps, (const int4*)nullptr, (const int2*)nullptr);
   };
   const double ms = time_kernel(launch, reps);
   CK(b200ot_softmin_finalize(P.part, nsplit, nullptr, 0.f, 1.f, P.out, P.lse2, P.N, P.eps, nullptr) == 0
@@ -285,9 +287,9 @@ static void run_variant(const char* name, Problem& P, int reps) {
   const double pairs = (double)P.N * (double)P.M;
   printf(
       "{\"variant\": \"%s\", \"N\": %lld, \"M\": %lld, \"eps\": %g, \"ms\": %.3f, \"Tpairs_s\": %.3f, \"regs\": %d, "
-      "\"occ\": %d, \"grid\": [%u,%u], \"max_abs_err\": %.3e, \"max_rel_err\": %.3e}\n",
+      "\"occ\": %d, \"grid\": [%u,%u], \"waves\": %.2f, \"max_abs_err\": %.3e, \"max_rel_err\": %.3e}\n",
       name, (long long)P.N, (long long)P.M, P.eps, ms, pairs / (ms * 1e-3) * 1e-12, fa.numRegs, occ, grid.x, grid.y,
-      max_abs, max_rel);
+      (double)grid.x * grid.y / (148.0 * occ), max_abs, max_rel);
   fflush(stdout);
 }
 
@@ -297,6 +299,7 @@ int main(int argc, char** argv) {
   const float eps = argc > 3 ? (float)atof(argv[3]) : 1e-4f;
   const int reps = argc > 4 ? atoi(argv[4]) : 3;
   g_filter = argc > 5 ? argv[5] : nullptr;
+  g_nsplit = argc > 6 ? atoi(argv[6]) : 0;
 
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
@@ -373,7 +376,7 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&P.h, M * 4));
   CK(cudaMalloc(&P.center, 16 * 4));
   CK(cudaMalloc(&P.cols, b200ot_packed_cols_floats(M, D, 1) * 4 + 4096));
-  CK(cudaMalloc(&P.part, (size_t)64 * N * 8));
+  CK(cudaMalloc(&P.part, (size_t)64 * N * 8));  // up to 64 splits
   CK(cudaMalloc(&P.out, N * 4));
   CK(cudaMalloc(&P.lse2, N * 4));
   CK(cudaMemcpy(P.x, P.hx.data(), N * D * 4, cudaMemcpyHostToDevice));
