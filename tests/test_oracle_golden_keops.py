@@ -137,3 +137,16 @@ def test_images_barycenter_fp64(name):
     assert (gm is not None) == bool(g["measures_have_grad"])
     if gm is not None:
         np.testing.assert_allclose(gm.numpy(), g["grad_measures_f64"], rtol=1e-8, atol=1e-10)
+
+
+# ------------------------------------------------------------------------ dimensions 16 .. 64 (tensorized reference)
+@pytest.mark.parametrize("name", golden_names("hd_"))
+def test_high_dimension_fixtures(name):
+    g = load_golden(name)
+    kw = golden_kwargs(g)
+    leaves = [T(g[k]).double().requires_grad_(True) for k in "axby"]
+    val = O.samples_loss(*leaves, **kw)
+    np.testing.assert_allclose(val.item(), g["value_f64"], rtol=1e-11)
+    ga, gx, gb, gy = torch.autograd.grad(val, leaves)
+    np.testing.assert_allclose(ga.numpy(), g["grad_a_f64"], rtol=1e-9, atol=1e-14)
+    np.testing.assert_allclose(gx.numpy(), g["grad_x_f64"], rtol=2e-6, atol=1e-7 * np.abs(g["grad_x_f64"]).max())
