@@ -277,18 +277,16 @@ def run_b200(args):
             "f_aa": sm(eps, x, x, a_log, p=p, center=center)[0], "g_bb": sm(eps, y, y, b_log, p=p, center=center)[0]}
     inv = 1.0 / eps
 
+    from geomloss_b200.sinkhorn import softmin_many
+
     def step(pt):
-        new = {
-            "f_ba": sm(eps, x, y, b_log, pt["g_ab"], inv, p=p, center=center, out_old=pt["f_ba"], alpha_old=0.5,
-                       beta=0.5)[0],
-            "g_ab": sm(eps, y, x, a_log, pt["f_ba"], inv, p=p, center=center, out_old=pt["g_ab"], alpha_old=0.5,
-                       beta=0.5)[0],
-            "f_aa": sm(eps, x, x, a_log, pt["f_aa"], inv, p=p, center=center, out_old=pt["f_aa"], alpha_old=0.5,
-                       beta=0.5)[0],
-            "g_bb": sm(eps, y, y, b_log, pt["g_bb"], inv, p=p, center=center, out_old=pt["g_bb"], alpha_old=0.5,
-                       beta=0.5)[0],
-        }
-        return new
+        # exactly the body of sinkhorn.sinkhorn_loop_points: four independent (Jacobi) fused updates
+        ukw = dict(p=p, center=center, alpha_old=0.5, beta=0.5)
+        res = softmin_many(sm, [((eps, x, y, b_log, pt["g_ab"], inv), dict(out_old=pt["f_ba"], **ukw)),
+                                ((eps, y, x, a_log, pt["f_ba"], inv), dict(out_old=pt["g_ab"], **ukw)),
+                                ((eps, x, x, a_log, pt["f_aa"], inv), dict(out_old=pt["f_aa"], **ukw)),
+                                ((eps, y, y, b_log, pt["g_bb"], inv), dict(out_old=pt["g_bb"], **ukw))])
+        return {"f_ba": res[0][0], "g_ab": res[1][0], "f_aa": res[2][0], "g_bb": res[3][0]}
 
     def sync_all():
         torch.cuda.synchronize(dev)

@@ -59,6 +59,10 @@ _SIGNATURES = {
     "b200ot_kernel_conv_finalize": (c_int32, [_P, c_int32, _P, c_int64, c_int32, _P]),
     "b200ot_kernel_conv_bwd_finalize": (c_int32, [_P, c_int32, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_float,
                                                   _P]),
+    "b200ot_sinkhorn_iteration_small": (c_int32, [_P] * 13 + [c_int64, c_int64, c_int64, c_int32, c_int32, c_float,
+                                                  c_float, c_float, _P]),
+    "b200ot_sinkhorn_final_bwd_small": (c_int32, [_P] * 15 + [c_int64, c_int64, c_int64, c_int32, c_int32, c_float,
+                                                  c_float, _P]),
     "b200ot_softmin_grid": (c_int32, [_P, _P, c_float, _P, c_float, c_float, _P, c_int64, c_int32, c_int32, c_int32,
                                       c_float, _P]),
     "b200ot_ubench": (c_int32, [c_int32, c_int32, c_int32, _P, ctypes.POINTER(c_int32), _P]),

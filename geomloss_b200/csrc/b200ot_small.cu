@@ -1,0 +1,392 @@
+// b200ot — small problems: ONE launch per symmetric Sinkhorn iteration (and one for the gradient of the final step).
+//
+// Reference semantics: the body of sinkhorn_loop (src/geomloss/_legacy/sinkhorn_divergence.py:468-493) — the four
+// simultaneous updates
+//     f_ba <- a0 f_ba + b0 softmin(eps, (x, y), b_log + g_ab/eps)      g_ab <- a0 g_ab + b0 softmin(eps, (y, x), a_log + f_ba/eps)
+//     f_aa <- a0 f_aa + b0 softmin(eps, (x, x), a_log + f_aa/eps)      g_bb <- a0 g_bb + b0 softmin(eps, (y, y), b_log + g_bb/eps)
+// all read the OLD potentials, so they are independent and run as the y-slices of one grid; batched inputs
+// (B, N, D) are the z-slices (the reference's batched tensorized / LazyTensor reductions, sinkhorn_samples.py:70-71,
+// :229-290).  This is the regime most users live in (N <= 5 000: doc/index.rst:34), where the tiled TMA kernels
+// are launch-bound: 3 launches per softmin, 12 per iteration.  Here an iteration is one launch: no column packing
+// (the cost is evaluated by explicit differences straight from the input arrays staged in shared memory), no
+// partial (m, s) buffers (a CTA owns 32 rows and ALL columns: its four warps split the columns and merge through
+// shared memory), the Sinkhorn prologue h = log_w + pot/eps and the damped / averaged epilogue fused in.
+//
+// Numerics: explicit differences (exact for coincident points, no expansion), log2 domain, online (max, sum) per
+// thread refreshed once per 8 columns, fp32 throughout, final log in fp32 on a sum normalised into [1, 4 * 8).
+#include <math.h>
+
+#include "b200ot.h"
+#include "common.cuh"
+#include "host_util.cuh"
+
+namespace b200ot {
+
+constexpr int kSmallRows = 32;   // rows per CTA (one per lane)
+constexpr int kSmallWarps = 4;   // warps per CTA: each reduces a quarter of every column tile
+constexpr int kSmallTile = 256;  // columns staged per step
+
+struct SmallProblemSet {
+  // per problem q in {0: xy -> f_ba, 1: yx -> g_ab, 2: xx -> f_aa, 3: yy -> g_bb}
+  const float* rows[4];
+  const float* cols[4];
+  const float* logw[4];   // log-weights of the column cloud
+  const float* pot[4];    // potential on the column cloud (nullable: h = logw)
+  const float* old[4];    // previous value of the output (nullable when alpha_old == 0)
+  float* out[4];
+  float* lse2[4];         // nullable
+  const float* lse2_in[4];   // backward: saved lse2 of the forward final step
+  const float* gout[4];      // backward: upstream gradient per row (nullable = zero)
+  int nrows[4], ncols[4];
+};
+
+template <int D, int P>
+__device__ __forceinline__ float pair_exponent_small(const float (&X)[D], const float* __restrict__ c, float H,
+                                                     float clampq) {
+  float q = 0.f;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const float df = X[d] - c[d];
+    q = fmaf(df, df, q);
+  }
+  if (P == 2) return fmaf(-0.5f, q, H);
+  return H - sqrt_approx(fmaxf(q, clampq));
+}
+
+// smem column tile layout: [kSmallTile][D + 1] floats, slot D = H (log2-domain additive term)
+template <int D, int P>
+__global__ void __launch_bounds__(kSmallWarps * 32)
+    sinkhorn_iteration_small_kernel(SmallProblemSet S, float scale, float inv_eps_log2e, float clampq,
+                                    float alpha_old, float beta_neg_eps_ln2) {
+  constexpr int W = D + 1;
+  __shared__ float tile[kSmallTile * W];
+  __shared__ float2 red[kSmallWarps][kSmallRows];
+  const int q = blockIdx.y;
+  const int b = blockIdx.z;
+  const int nrows = S.nrows[q], ncols = S.ncols[q];
+  const int row0 = blockIdx.x * kSmallRows;
+  if (row0 >= nrows) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* __restrict__ rows = S.rows[q] + (int64_t)b * nrows * D;
+  const float* __restrict__ cols = S.cols[q] + (int64_t)b * ncols * D;
+  const float* __restrict__ logw = S.logw[q] + (int64_t)b * ncols;
+  const float* __restrict__ pot = S.pot[q] ? S.pot[q] + (int64_t)b * ncols : nullptr;
+
+  const int i = min(row0 + lane, nrows - 1);
+  float X[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) X[d] = scale * rows[(int64_t)i * D + d];
+
+  float m = kNegBig, s = 0.f;
+  for (int j0 = 0; j0 < ncols; j0 += kSmallTile) {
+    const int nt = min(kSmallTile, ncols - j0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < kSmallTile; e += kSmallWarps * 32) {
+      float* dst = tile + e * W;
+      if (e < nt) {
+        const int j = j0 + e;
+#pragma unroll
+        for (int d = 0; d < D; ++d) dst[d] = scale * cols[(int64_t)j * D + d];
+        float h = logw[j] * kLog2e;
+        if (pot) h = fmaf(pot[j], inv_eps_log2e, h);
+        dst[D] = h;
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d) dst[d] = 0.f;
+        dst[D] = -INFINITY;
+      }
+    }
+    __syncthreads();
+    // warp w takes columns [w*64, w*64 + 64) of the tile, 8 at a time
+    const int c_begin = warp * (kSmallTile / kSmallWarps);
+    const int c_end = min(c_begin + kSmallTile / kSmallWarps, (nt + 7) & ~7);
+    for (int c0 = c_begin; c0 < c_end; c0 += 8) {
+      float t[8];
+      float cm = kNegBig;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float* cp = tile + (c0 + c) * W;
+        t[c] = pair_exponent_small<D, P>(X, cp, cp[D], clampq);
+        cm = fmaxf(cm, t[c]);
+      }
+      if (cm > m) {
+        s *= ex2_approx(m - cm);
+        m = cm;
+      }
+      float cs = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) cs += ex2_approx(t[c] - m);
+      s += cs;
+    }
+  }
+  red[warp][lane] = make_float2(m, s);
+  __syncthreads();
+  if (warp == 0 && row0 + lane < nrows) {
+    float mm = red[0][lane].x;
+#pragma unroll
+    for (int w = 1; w < kSmallWarps; ++w) mm = fmaxf(mm, red[w][lane].x);
+    float ss = 0.f;
+#pragma unroll
+    for (int w = 0; w < kSmallWarps; ++w) ss += red[w][lane].y * ex2_approx(red[w][lane].x - mm);
+    int e = 0;
+    const float fr = frexpf(ss, &e);
+    const float lse2 = ss > 0.f ? (mm + (float)e) + log2f(fr) : -INFINITY;
+    const int64_t o = (int64_t)b * nrows + row0 + lane;
+    if (S.lse2[q]) S.lse2[q][o] = lse2;
+    float v = beta_neg_eps_ln2 * lse2;
+    if (S.old[q]) v = fmaf(alpha_old, S.old[q][o], v);
+    S.out[q][o] = v;
+  }
+}
+
+// Gradient of the final (gradient-carrying) step w.r.t. the ROW clouds:
+//   grad_rows[i] = sum over the problems that share this row cloud of  go_q[i] * sum_j w_ij dC(x_i, y_j)/dx_i,
+//   w_ij = 2^(t_ij - lse2_i).   blockIdx.y = 0: rows x (problems xy and xx), 1: rows y (problems yx and yy).
+template <int D, int P>
+__global__ void __launch_bounds__(kSmallWarps * 32)
+    sinkhorn_final_bwd_small_kernel(SmallProblemSet S, float scale, float inv_eps_log2e, float clampq,
+                                    float out_scale, float* __restrict__ grad_x, float* __restrict__ grad_y,
+                                    int n_terms) {
+  constexpr int W = D + 1;
+  __shared__ float tile[kSmallTile * W];
+  __shared__ float red[kSmallWarps][kSmallRows][D];
+  __shared__ float redw[kSmallWarps][kSmallRows];
+  const int side = blockIdx.y;  // 0: x rows, 1: y rows
+  const int b = blockIdx.z;
+  const int nrows = S.nrows[side];
+  const int row0 = blockIdx.x * kSmallRows;
+  if (row0 >= nrows) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* __restrict__ rows = S.rows[side] + (int64_t)b * nrows * D;
+  const int i = min(row0 + lane, nrows - 1);
+  float X[D], G[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    X[d] = scale * rows[(int64_t)i * D + d];
+    G[d] = 0.f;
+  }
+  for (int term = 0; term < n_terms; ++term) {
+    const int q = side + 2 * term;  // 0/1: cross terms, 2/3: self terms
+    const float* go_p = S.gout[q];
+    if (go_p == nullptr) continue;
+    const int ncols = S.ncols[q];
+    const float* __restrict__ cols = S.cols[q] + (int64_t)b * ncols * D;
+    const float* __restrict__ logw = S.logw[q] + (int64_t)b * ncols;
+    const float* __restrict__ pot = S.pot[q] ? S.pot[q] + (int64_t)b * ncols : nullptr;
+    const float lse2 = S.lse2_in[q][(int64_t)b * nrows + i];
+    const float go = go_p[(int64_t)b * nrows + i];
+    float A[D];
+    float sw = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) A[d] = 0.f;
+    for (int j0 = 0; j0 < ncols; j0 += kSmallTile) {
+      const int nt = min(kSmallTile, ncols - j0);
+      __syncthreads();
+      for (int e = threadIdx.x; e < kSmallTile; e += kSmallWarps * 32) {
+        float* dst = tile + e * W;
+        if (e < nt) {
+          const int j = j0 + e;
+#pragma unroll
+          for (int d = 0; d < D; ++d) dst[d] = scale * cols[(int64_t)j * D + d];
+          float h = logw[j] * kLog2e;
+          if (pot) h = fmaf(pot[j], inv_eps_log2e, h);
+          dst[D] = h;
+        } else {
+#pragma unroll
+          for (int d = 0; d < D; ++d) dst[d] = 0.f;
+          dst[D] = -INFINITY;
+        }
+      }
+      __syncthreads();
+      const int c_begin = warp * (kSmallTile / kSmallWarps);
+      const int c_end = min(c_begin + kSmallTile / kSmallWarps, nt);
+      for (int c = c_begin; c < c_end; ++c) {
+        const float* cp = tile + c * W;
+        float df[D];
+        float qq = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          df[d] = X[d] - cp[d];
+          qq = fmaf(df[d], df[d], qq);
+        }
+        float w;
+        if (P == 2) {
+          w = ex2_approx(fmaf(-0.5f, qq, cp[D]) - lse2);
+#pragma unroll
+          for (int d = 0; d < D; ++d) A[d] = fmaf(w, df[d], A[d]);  // dC/dx = x - y  (scaled units)
+        } else {
+          const bool inside = qq < clampq;  // zero gradient inside the clamp (or at coincident points)
+          const float qc = fmaxf(qq, clampq);
+          const float rinv = rsqrt_approx(qc);
+          w = ex2_approx(cp[D] - qc * rinv - lse2);
+          const float wr = inside ? 0.f : w * rinv;
+#pragma unroll
+          for (int d = 0; d < D; ++d) A[d] = fmaf(wr, df[d], A[d]);  // unit vector
+        }
+        sw += w;
+      }
+    }
+    // merge the four warps' partial sums of this term, then add  go * A / sw  into the row gradient
+    __syncthreads();
+#pragma unroll
+    for (int d = 0; d < D; ++d) red[warp][lane][d] = A[d];
+    redw[warp][lane] = sw;
+    __syncthreads();
+    if (warp == 0) {
+      float tw = 0.f;
+#pragma unroll
+      for (int w = 0; w < kSmallWarps; ++w) tw += redw[w][lane];
+      const float inv = tw > 0.f ? go / tw : 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < kSmallWarps; ++w) a += red[w][lane][d];
+        G[d] = fmaf(inv, a, G[d]);
+      }
+    }
+  }
+  if (warp == 0 && row0 + lane < nrows) {
+    float* g = (side == 0 ? grad_x : grad_y) + ((int64_t)b * nrows + row0 + lane) * D;
+    // p = 2: A is in scaled units (X - Y = scale (x - y)): dC/dx = (x - y) = A / scale;  p = 1: unit vectors
+    const float k = out_scale * (P == 2 ? 1.0f / scale : 1.0f);
+#pragma unroll
+    for (int d = 0; d < D; ++d) g[d] = k * G[d];
+  }
+}
+
+template <int D>
+static int launch_iter(int pe, const SmallProblemSet& S, dim3 grid, float scale, float inv_eps_log2e, float clampq,
+                       float alpha_old, float beta_neg_eps_ln2, cudaStream_t st) {
+  if (pe == 2)
+    sinkhorn_iteration_small_kernel<D, 2><<<grid, kSmallWarps * 32, 0, st>>>(S, scale, inv_eps_log2e, clampq,
+                                                                             alpha_old, beta_neg_eps_ln2);
+  else
+    sinkhorn_iteration_small_kernel<D, 1><<<grid, kSmallWarps * 32, 0, st>>>(S, scale, inv_eps_log2e, clampq,
+                                                                             alpha_old, beta_neg_eps_ln2);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  return B200OT_OK;
+}
+
+template <int D>
+static int launch_bwd(int pe, const SmallProblemSet& S, dim3 grid, float scale, float inv_eps_log2e, float clampq,
+                      float out_scale, float* gx, float* gy, int n_terms, cudaStream_t st) {
+  if (pe == 2)
+    sinkhorn_final_bwd_small_kernel<D, 2><<<grid, kSmallWarps * 32, 0, st>>>(S, scale, inv_eps_log2e, clampq,
+                                                                             out_scale, gx, gy, n_terms);
+  else
+    sinkhorn_final_bwd_small_kernel<D, 1><<<grid, kSmallWarps * 32, 0, st>>>(S, scale, inv_eps_log2e, clampq,
+                                                                             out_scale, gx, gy, n_terms);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  return B200OT_OK;
+}
+
+#define B200OT_DISPATCH_D(D, CALL)            \
+  switch (D) {                                \
+    case 1: return CALL(1);                   \
+    case 2: return CALL(2);                   \
+    case 3: return CALL(3);                   \
+    case 4: return CALL(4);                   \
+    case 5: return CALL(5);                   \
+    case 6: return CALL(6);                   \
+    case 7: return CALL(7);                   \
+    case 8: return CALL(8);                   \
+    default: return B200OT_EINVAL;            \
+  }
+
+static void fill_problems(SmallProblemSet& S, const float* x, const float* y, const float* a_log, const float* b_log,
+                          const float* f_ba, const float* g_ab, const float* f_aa, const float* g_bb, int N, int M) {
+  const float* rows[4] = {x, y, x, y};
+  const float* cols[4] = {y, x, x, y};
+  const float* logw[4] = {b_log, a_log, a_log, b_log};
+  const float* pot[4] = {g_ab, f_ba, f_aa, g_bb};
+  const int nr[4] = {N, M, N, M}, nc[4] = {M, N, N, M};
+  for (int q = 0; q < 4; ++q) {
+    S.rows[q] = rows[q];
+    S.cols[q] = cols[q];
+    S.logw[q] = logw[q];
+    S.pot[q] = pot[q];
+    S.nrows[q] = nr[q];
+    S.ncols[q] = nc[q];
+    S.old[q] = nullptr;
+    S.out[q] = nullptr;
+    S.lse2[q] = nullptr;
+    S.lse2_in[q] = nullptr;
+    S.gout[q] = nullptr;
+  }
+}
+
+}  // namespace b200ot
+
+using namespace b200ot;
+
+extern "C" {
+
+B200OT_API int b200ot_sinkhorn_iteration_small(const float* x, const float* y, const float* a_log, const float* b_log,
+                                               const float* f_ba, const float* g_ab, const float* f_aa,
+                                               const float* g_bb, float* f_ba_out, float* g_ab_out, float* f_aa_out,
+                                               float* g_bb_out, float* lse2_out, int64_t B, int64_t N, int64_t M,
+                                               int32_t D, int32_t p, float eps, float alpha_old, float beta,
+                                               void* stream) {
+  if (!x || !y || !a_log || !b_log || !f_ba_out || !g_ab_out || B <= 0 || N <= 0 || M <= 0 || B > 65535 ||
+      N > B200OT_SMALL_MAX_POINTS || M > B200OT_SMALL_MAX_POINTS || !supported_simt_dim(D) || !valid_p(p) ||
+      !(eps > 0.f) || ((f_aa_out == nullptr) != (g_bb_out == nullptr)))
+    return B200OT_EINVAL;
+  // old potentials: all present (an iteration) or all absent (the initialisation, h = log-weights, alpha_old = 0)
+  const bool has_old = f_ba && g_ab;
+  if (!has_old && (f_ba || g_ab || f_aa || g_bb || alpha_old != 0.f)) return B200OT_EINVAL;
+  const bool debias = f_aa_out != nullptr;
+  if (has_old && debias && (!f_aa || !g_bb)) return B200OT_EINVAL;
+  SmallProblemSet S;
+  fill_problems(S, x, y, a_log, b_log, f_ba, g_ab, f_aa, g_bb, (int)N, (int)M);
+  const float* old[4] = {f_ba, g_ab, f_aa, g_bb};
+  float* out[4] = {f_ba_out, g_ab_out, f_aa_out, g_bb_out};
+  for (int q = 0; q < 4; ++q) {
+    S.old[q] = (alpha_old != 0.f) ? old[q] : nullptr;
+    S.out[q] = out[q];
+    const int64_t off[4] = {0, B * N, B * (N + M), B * (2 * N + M)};
+    S.lse2[q] = lse2_out ? lse2_out + off[q] : nullptr;
+  }
+  const int pe = p_exponent(p);
+  const float scale = softmin_coord_scale(pe, eps);
+  const float clampq = scale * scale * cost_clamp(p);
+  const int64_t tiles = ceil_div64(N > M ? N : M, kSmallRows);
+  dim3 grid((unsigned)tiles, debias ? 4u : 2u, (unsigned)B);
+  const float bneg = -beta * eps * kLn2;
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(DD) launch_iter<DD>(pe, S, grid, scale, kLog2e / eps, clampq, alpha_old, bneg, st)
+  B200OT_DISPATCH_D(D, CALL)
+#undef CALL
+}
+
+B200OT_API int b200ot_sinkhorn_final_bwd_small(const float* x, const float* y, const float* a_log, const float* b_log,
+                                               const float* f_ba, const float* g_ab, const float* f_aa,
+                                               const float* g_bb, const float* lse2, const float* go_f_ba,
+                                               const float* go_g_ab, const float* go_f_aa, const float* go_g_bb,
+                                               float* grad_x, float* grad_y, int64_t B, int64_t N, int64_t M,
+                                               int32_t D, int32_t p, float eps, float scale_out, void* stream) {
+  if (!x || !y || !a_log || !b_log || !lse2 || !grad_x || !grad_y || B <= 0 || N <= 0 || M <= 0 || B > 65535 ||
+      N > B200OT_SMALL_MAX_POINTS || M > B200OT_SMALL_MAX_POINTS || !supported_simt_dim(D) || !valid_p(p) ||
+      !(eps > 0.f))
+    return B200OT_EINVAL;
+  SmallProblemSet S;
+  fill_problems(S, x, y, a_log, b_log, f_ba, g_ab, f_aa, g_bb, (int)N, (int)M);
+  const float* go[4] = {go_f_ba, go_g_ab, go_f_aa, go_g_bb};
+  const int64_t off[4] = {0, B * N, B * (N + M), B * (2 * N + M)};
+  for (int q = 0; q < 4; ++q) {
+    S.gout[q] = go[q];
+    S.lse2_in[q] = lse2 + off[q];
+  }
+  const int n_terms = (go_f_aa || go_g_bb) ? 2 : 1;
+  const int pe = p_exponent(p);
+  const float scale = softmin_coord_scale(pe, eps);
+  const float clampq = scale * scale * cost_clamp(p);
+  const int64_t tiles = ceil_div64(N > M ? N : M, kSmallRows);
+  dim3 grid((unsigned)tiles, 2u, (unsigned)B);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(DD) launch_bwd<DD>(pe, S, grid, scale, kLog2e / eps, clampq, scale_out, grad_x, grad_y, n_terms, st)
+  B200OT_DISPATCH_D(D, CALL)
+#undef CALL
+}
+
+}  // extern "C"

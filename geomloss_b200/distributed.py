@@ -165,6 +165,36 @@ class ColumnShardedEngine:
         self.collectives += 1
         return self.stages.softmin_finalize(parts, eps, out_old, alpha_old, beta, want_lse2)
 
+    def softmin_raw_many(self, calls):
+        """The independent softmins of one Jacobi iteration, ``calls = [(args, kwargs), ...]`` of ``softmin_raw``:
+        every shard reduction is enqueued first, each followed by an ASYNCHRONOUS all_gather of its (N, 2) partials,
+        and the merges come last — so the exchange of softmin k travels over NVLink while the partial-reduction
+        kernel of softmin k+1 runs (the collectives of an iteration are off the critical path except the last)."""
+        pending = []
+        for args, kw in calls:
+            kw = dict(kw)
+            eps, x, y, h_a = args[:4]
+            h_b = args[4] if len(args) > 4 else kw.pop("h_b", None)
+            h_scale_b = args[5] if len(args) > 5 else kw.pop("h_scale_b", 0.0)
+            p, center = kw.pop("p", 2), kw.pop("center", None)
+            M, N = y.shape[0], x.shape[0]
+            lo, hi = shard_bounds(M, self.rank, self.world)
+            if hi > lo:
+                mine = self.stages.softmin_shard(eps, x, y[lo:hi], h_a[lo:hi], None if h_b is None else h_b[lo:hi],
+                                                 h_scale_b, p, center)
+            else:
+                mine = self.stages.empty_shard(N, x.device)
+            parts = torch.empty(self.world, N, 2, dtype=mine.dtype, device=mine.device)
+            work = dist.all_gather_into_tensor(parts.view(self.world * N, 2), mine, group=self.group, async_op=True)
+            self.collectives += 1
+            pending.append((work, parts, mine, eps, kw))
+        out = []
+        for work, parts, _mine, eps, kw in pending:
+            work.wait()  # stream-level wait: the host does not block
+            out.append(self.stages.softmin_finalize(parts, eps, kw.get("out_old"), kw.get("alpha_old", 0.0),
+                                                    kw.get("beta", 1.0), kw.get("want_lse2", False)))
+        return out
+
     # -- forward + backward (the final, gradient-carrying Sinkhorn step) --------------------------
     def softmin(self, eps, x, y, h_a, h_b=None, h_scale_b=0.0, *, p=2, center=None, scale_out=1.0, local=False):
         return _ShardedSoftmin.apply(self, x, y.detach(), h_a.detach(), None if h_b is None else h_b.detach(),

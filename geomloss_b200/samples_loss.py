@@ -28,6 +28,7 @@ import warnings
 from .kernel_loss import kernel_points, kernel_points_batched
 from .multiscale import kernel_multiscale, sinkhorn_multiscale
 from .ops import MAX_D
+from . import sinkhorn_small
 from .sinkhorn import sinkhorn_points, sinkhorn_points_batched
 
 _LOSSES = ("sinkhorn", "hausdorff", "energy", "gaussian", "laplacian")
@@ -131,6 +132,14 @@ class SamplesLoss(Module):
                 return F.view_as(a), G.view_as(b)
             return values if B == 0 else values.view(-1)
 
+        if self.loss == "sinkhorn" and not self._engine and sinkhorn_small.eligible(N, M, D):
+            # small clouds (batched or not): one launch per Sinkhorn iteration (csrc/b200ot_small.cu)
+            lift = (lambda t: t.unsqueeze(0)) if B == 0 else (lambda t: t)
+            values = sinkhorn_small.sinkhorn_small(lift(a), lift(x), lift(b), lift(y), **kw)
+            if self.potentials:
+                F, G = values
+                return (F.view(1, -1), G.view(1, -1)) if B == 0 else (F.view_as(a), G.view_as(b))
+            return values[0] if B == 0 else values
         if B == 0:
             values = routine(a, x, b, y, **kw)
             if self.potentials:

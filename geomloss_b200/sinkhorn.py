@@ -50,6 +50,16 @@ def scaling_parameters(x, y, p, blur, reach, diameter, scaling):
     return diameter, blur**p, epsilon_schedule(p, diameter, blur, scaling), rho
 
 
+def softmin_many(sm, calls):
+    """Run the independent softmins ``calls = [(args, kwargs), ...]`` of one Jacobi iteration through ``sm``; an engine
+    that can overlap their collectives (distributed.ColumnShardedEngine.softmin_raw_many) gets them all at once."""
+    owner = getattr(sm, "__self__", None)
+    many = getattr(owner, "softmin_raw_many", None) if owner is not None else None
+    if many is not None:
+        return many(calls)
+    return [sm(*args, **kw) for args, kw in calls]
+
+
 def sinkhorn_loop_points(a_log, b_log, x, y, eps_list, rho, *, p=2, debias=True, center=None, softmin_raw=None,
                          softmin_grad=None, problems=None):
     """Symmetric Sinkhorn iterations with eps-scaling on one pair of clouds.   sinkhorn_divergence.py:258-628
@@ -94,17 +104,16 @@ def sinkhorn_loop_points(a_log, b_log, x, y, eps_list, rho, *, p=2, debias=True,
         for eps in eps_list:
             lam = damping(eps, rho)
             inv = 1.0 / eps
-            ft_ba = sm(eps, xd, yd, b_log, g_ab, inv, p=p, center=center, out_old=f_ba, alpha_old=0.5,
-                       beta=0.5 * lam)[0]
-            gt_ab = sm(eps, yd, xd, a_log, f_ba, inv, p=p, center=center, out_old=g_ab, alpha_old=0.5,
-                       beta=0.5 * lam)[0]
+            ukw = dict(p=p, center=center, alpha_old=0.5, beta=0.5 * lam)
+            calls = [((eps, xd, yd, b_log, g_ab, inv), dict(out_old=f_ba, **ukw)),
+                     ((eps, yd, xd, a_log, f_ba, inv), dict(out_old=g_ab, **ukw))]
             if debias:
-                ft_aa = sm(eps, xd, xd, a_log, f_aa, inv, p=p, center=center, out_old=f_aa, alpha_old=0.5,
-                           beta=0.5 * lam)[0]
-                gt_bb = sm(eps, yd, yd, b_log, g_bb, inv, p=p, center=center, out_old=g_bb, alpha_old=0.5,
-                           beta=0.5 * lam)[0]
-                f_aa, g_bb = ft_aa, gt_bb
-            f_ba, g_ab = ft_ba, gt_ab
+                calls += [((eps, xd, xd, a_log, f_aa, inv), dict(out_old=f_aa, **ukw)),
+                          ((eps, yd, yd, b_log, g_bb, inv), dict(out_old=g_bb, **ukw))]
+            res = softmin_many(sm, calls)  # all four read the OLD potentials (Jacobi): independent
+            f_ba, g_ab = res[0][0], res[1][0]
+            if debias:
+                f_aa, g_bb = res[2][0], res[3][0]
     # final extrapolation: eps / lam are the last values of the schedule (reference: leaked loop variables)
     inv = 1.0 / eps
     new_f_ba = smg(eps, x, yd, b_log, g_ab, inv, p=p, center=center, scale_out=lam)

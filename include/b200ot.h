@@ -218,6 +218,37 @@ B200OT_API int b200ot_kernel_conv_bwd_finalize(const float* part, int32_t n_part
                                                int32_t kind, float blur, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Small problems: one launch per symmetric Sinkhorn iteration
+ * replaces the four softmin calls of the loop body of sinkhorn_loop (sinkhorn_divergence.py:468-493) — and of its
+ * initialisation (:461-465) and final gradient-carrying step (:612-623) — for B stacked problems
+ * x:(B,N,D) y:(B,M,D) a_log:(B,N) b_log:(B,M) with N, M <= B200OT_SMALL_MAX_POINTS, D <= B200OT_MAX_D:
+ *     f_ba_out <- alpha_old f_ba + beta softmin(eps, (x, y), b_log + g_ab/eps)      (B,N)
+ *     g_ab_out <- alpha_old g_ab + beta softmin(eps, (y, x), a_log + f_ba/eps)      (B,M)
+ *     f_aa_out <- alpha_old f_aa + beta softmin(eps, (x, x), a_log + f_aa/eps)      (B,N)   (debiasing; nullable pair)
+ *     g_bb_out <- alpha_old g_bb + beta softmin(eps, (y, y), b_log + g_bb/eps)      (B,M)
+ * all four reading the OLD potentials (f_ba .. g_bb all null: h = log-weights, the initialisation; alpha_old = 0).
+ * Outputs must not alias inputs.  lse2_out (nullable): B*(2N+2M) floats [f_ba | g_ab | f_aa | g_bb], the log2-domain
+ * log-sum-exp of every row, consumed by b200ot_sinkhorn_final_bwd_small:
+ *     grad_x <- scale_out * ( go_f_ba[i] d softmin_xy / d x_i + go_f_aa[i] d softmin_xx / d x_i )     (B,N,D)
+ *     grad_y <- scale_out * ( go_g_ab[j] d softmin_yx / d y_j + go_g_bb[j] d softmin_yy / d y_j )     (B,M,D)
+ * with columns and potentials held constant (the reference's autograd contract); f_ba .. g_bb are the potentials
+ * that entered the final step; go_* nullable (zero upstream gradient).
+ * ------------------------------------------------------------------------------------------- */
+#define B200OT_SMALL_MAX_POINTS 65536
+B200OT_API int b200ot_sinkhorn_iteration_small(const float* x, const float* y, const float* a_log, const float* b_log,
+                                               const float* f_ba, const float* g_ab, const float* f_aa,
+                                               const float* g_bb, float* f_ba_out, float* g_ab_out, float* f_aa_out,
+                                               float* g_bb_out, float* lse2_out, int64_t B, int64_t N, int64_t M,
+                                               int32_t D, int32_t p, float eps, float alpha_old, float beta,
+                                               void* stream);
+B200OT_API int b200ot_sinkhorn_final_bwd_small(const float* x, const float* y, const float* a_log, const float* b_log,
+                                               const float* f_ba, const float* g_ab, const float* f_aa,
+                                               const float* g_bb, const float* lse2, const float* go_f_ba,
+                                               const float* go_g_ab, const float* go_f_aa, const float* go_g_bb,
+                                               float* grad_x, float* grad_y, int64_t B, int64_t N, int64_t M,
+                                               int32_t D, int32_t p, float eps, float scale_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Grid softmin  —  the separable soft-C-transform on (batch, N, N[, N]) images / volumes
  * replaces softmin_grid (src/geomloss/_legacy/utils.py:190-279), the operator of the image Sinkhorn loop
  * (src/geomloss/_legacy/sinkhorn_images.py:26-202):

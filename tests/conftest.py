@@ -49,3 +49,17 @@ def golden_kwargs(g):
             v = v.item()
             out[k[3:]] = None if v == "None" else v
     return out
+
+
+@pytest.fixture(params=["small-kernels", "tiled-kernels"])
+def sinkhorn_path(request):
+    """Small Sinkhorn problems are served by the one-launch-per-iteration kernels (csrc/b200ot_small.cu); the golden
+    cases are all small, so every test that takes this fixture runs twice: as routed by default, and with that path
+    disabled so that the tiled TMA kernels (the ones that run at N = 1e6) are checked on the same fixtures."""
+    from geomloss_b200 import sinkhorn_small
+
+    keep = sinkhorn_small.SMALL_MAX
+    if request.param == "tiled-kernels":
+        sinkhorn_small.SMALL_MAX = 0
+    yield request.param
+    sinkhorn_small.SMALL_MAX = keep

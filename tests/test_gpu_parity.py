@@ -243,7 +243,7 @@ def test_kernel_conv_gradients_vs_autograd(kind):
 # ------------------------------------------------------------------------------------------------
 # SamplesLoss vs the reference's golden outputs
 # ------------------------------------------------------------------------------------------------
-def test_cfg1_sinkhorn_n1000():
+def test_cfg1_sinkhorn_n1000(sinkhorn_path):
     """BASELINE.json configs[0]: N=M=1000, D=3, blur=.05 — value, potentials, all four gradients."""
     from geomloss_b200 import SamplesLoss
 
@@ -277,7 +277,7 @@ def test_cfg1_sinkhorn_n1000():
 
 
 @pytest.mark.parametrize("name", golden_names("sinkhorn_case"))
-def test_sinkhorn_cases(name):
+def test_sinkhorn_cases(name, sinkhorn_path):
     from geomloss_b200 import SamplesLoss, ops
 
     g = load_golden(name)
@@ -306,7 +306,7 @@ def dim_supported(d):
     return d <= 8
 
 
-def test_sinkhorn_batched():
+def test_sinkhorn_batched(sinkhorn_path):
     from geomloss_b200 import SamplesLoss
 
     g = load_golden("sinkhorn_batched")

@@ -44,7 +44,7 @@ def _assert_grads(grads, g, keys):
 
 
 @pytest.mark.parametrize("name", golden_names("ms_sinkhorn_") + golden_names("online_sinkhorn_"))
-def test_sinkhorn_keops_backends(name):
+def test_sinkhorn_keops_backends(name, sinkhorn_path):
     from geomloss_b200 import SamplesLoss
 
     g = load_golden(name)
@@ -129,7 +129,7 @@ def test_high_dimension_vs_reference(name):
         assert err <= tol * np.abs(r).max() + 1e-9, (key, err, np.abs(r).max())
 
 
-def test_batched_equals_per_element_loop():
+def test_batched_equals_per_element_loop(sinkhorn_path):
     """One block-diagonal launch group per softmin == B independent problems (same eps-schedule)."""
     from geomloss_b200 import SamplesLoss
 

@@ -70,7 +70,7 @@ CASES = [
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("backend,kw,d", CASES)
-def test_samples_loss_vs_live_reference(ref, backend, kw, d):
+def test_samples_loss_vs_live_reference(ref, backend, kw, d, sinkhorn_path):
     from geomloss_b200 import SamplesLoss
 
     a, x, b, y = _clouds(sum(map(ord, backend + kw["loss"])) + d, 1700, 1500, d)
