@@ -283,7 +283,7 @@ int softmin_partial_tc(const float* x, const float* y, const float* h_a, const f
   B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   dim3 grid((unsigned)(p.a_tiles_pad / kTcRT), (unsigned)p.n_split);
   kern<<<grid, TcConvCfg::THREADS, (size_t)p.smem, st>>>(a_imgs, b_imgs, part, N, p.kp, (int)p.b_tiles,
-                                                        p.tiles_per_split, p.nstage, D);
+                                                        p.tiles_per_split, p.nstage, D, 0);
   B200OT_CUDA_TRY(cudaGetLastError());
   *part_out = part;
   *n_part_out = p.n_split * (kTcEpi / 4);
@@ -292,6 +292,7 @@ int softmin_partial_tc(const float* x, const float* y, const float* h_a, const f
 
 static int conv_fwd_tc(const float* x, const float* y, const float* w, const float* center, float* out, int64_t N,
                        int64_t M, int D, float blur, void* scratch, cudaStream_t st) {
+  const int self_mode = (x == y && N == M) ? 1 : 0;  // K_xx / K_yy: the diagonal exponent is exactly 0 (tcconv.cuh)
   const TcPlan p = make_tc_plan(N, M, D);
   if (p.nstage < 1) return B200OT_EINVAL;
   unsigned char* base = reinterpret_cast<unsigned char*>(scratch);
@@ -310,7 +311,7 @@ static int conv_fwd_tc(const float* x, const float* y, const float* w, const flo
   B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   dim3 grid((unsigned)(p.a_tiles_pad / kTcRT), (unsigned)p.n_split);
   kern<<<grid, TcConvCfg::THREADS, (size_t)p.smem, st>>>(a_imgs, b_imgs, part, N, p.kp, (int)p.b_tiles,
-                                                        p.tiles_per_split, p.nstage, D);
+                                                        p.tiles_per_split, p.nstage, D, self_mode);
   B200OT_CUDA_TRY(cudaGetLastError());
   conv_fwd_finalize_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, st>>>(part, p.n_split * (kTcEpi / 4), 1.f, out,
                                                                        N);

@@ -172,7 +172,7 @@ template <class C, int MODE>
 __global__ void __launch_bounds__(C::THREADS, 1)
     tc_reduce_kernel(const unsigned char* __restrict__ a_imgs, const unsigned char* __restrict__ b_imgs,
                      float* __restrict__ part, int64_t N, int kp, int ntiles_b, int tiles_per_split, int NSTAGE,
-                     int D) {
+                     int D, int self_mode) {
   constexpr int BN = C::BN, NEPI = C::NEPI, RT = kTcRT;
   static_assert(MODE == 0 || MODE == 1, "row gradients live in tcbwd.cuh");
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -303,6 +303,20 @@ __global__ void __launch_bounds__(C::THREADS, 1)
           float v[32];
           tmem_ld32(lane_base + r * BN + half * CW + c0, v);
           if constexpr (MODE == 0) {
+            if (self_mode) {
+              // rows and columns are the SAME cloud (the K_xx / K_yy terms of an MMD): the exponent of the pair
+              // (i, i) is -|X_i - X_i|^2/2 = 0 exactly, but the expansion X.X - |X|^2/2 - |X|^2/2 cancels three
+              // O(|x/blur|^2) numbers in fp32 (5e-3 at blur = .05, D = 64 — BASELINE configs[2], where the diagonal
+              // IS the loss).  Warp-uniform test, taken on one column tile in N/128.
+              const int64_t col0 = (int64_t)(t0 + k) * BN + half * CW + c0;
+              const int64_t row_lo = (int64_t)(row_tile0 + r) * kTcM + quarter * 32;
+              if (col0 < row_lo + 32 && row_lo < col0 + 32) {
+                const int diag = (int)(row_lo + lane - col0);
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                  if (c == diag) v[c] = 0.f;
+              }
+            }
             const float4* w4 = reinterpret_cast<const float4*>(wts + half * CW + c0);
 #pragma unroll
             for (int c = 0; c < 32; c += 4) {
