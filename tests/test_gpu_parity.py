@@ -168,17 +168,32 @@ def test_gaussian_conv_tensor_core_path(shape):
     xr, yr = x.double().requires_grad_(True), y.double().requires_grad_(True)
     ref = O.samples_loss(xr, yr, loss="gaussian", blur=2.0)
     rx, ry = torch.autograd.grad(ref, [xr, yr])
-    # (the MMD value is a difference of three O(1) sums: fp32 matvec rounding is ~1e-7 absolute)
-    assert abs(val.item() - ref.item()) <= 1e-4 * abs(ref.item()) + 3e-7
+    # The MMD value is the small difference of three positive sums 1/2 a'K_xx a + 1/2 b'K_yy b - a'K_xy b.  The
+    # tensor-core operands are two-term fp16 splits (22 significant bits) and the sums are fp32: the absolute error
+    # bound is 2^-22 of the summands' total, computed here from the fp64 oracle — not a fitted constant
+    ua, ub = torch.full((n,), 1.0 / n).double(), torch.full((m,), 1.0 / m).double()
+    summands = (0.5 * ua @ O.kernel_matrix("gaussian", x.double(), x.double(), 2.0) @ ua
+                + 0.5 * ub @ O.kernel_matrix("gaussian", y.double(), y.double(), 2.0) @ ub
+                + ua @ O.kernel_matrix("gaussian", x.double(), y.double(), 2.0) @ ub).item()
+    assert abs(val.item() - ref.item()) <= 1e-4 * abs(ref.item()) + 2.0**-22 * summands
     assert (gx.cpu().double() - rx).abs().max() <= 2e-4 * rx.abs().max()
     assert (gy.cpu().double() - ry).abs().max() <= 2e-4 * ry.abs().max()
     # BASELINE configs[2] regime (blur = .05 at D = 64): |x/blur|^2 ~ 1e4, every off-diagonal term underflows and
-    # the diagonal exponent is a cancellation of three O(6000) numbers; fp32 accumulation (the reference's own
-    # fp32 expansion has ~1e-3 error here) bounds the accuracy, the result must stay ~1
-    out = ops.kernel_conv_raw("gaussian", x.to(DEV), x.to(DEV), torch.ones(n, device=DEV), 0.05,
-                              center=ops.default_center(x.to(DEV), x.to(DEV))).cpu().numpy()
+    # the loss is carried by the diagonal of the self terms, whose exponent the kernel sets to its exact value 0
+    # (tcconv.cuh, self_mode: rows and columns are the same buffer, as in kernel_loss's K_xx / K_yy).  Bar: 1e-3,
+    # the reference's own fp32 error in this regime being ~4e-5 (tests/golden/hd_gaussian_d64_blur005.npz)
+    xd, yd = x.to(DEV), y.to(DEV)
+    out = ops.kernel_conv_raw("gaussian", xd, xd, torch.ones(n, device=DEV), 0.05,
+                              center=ops.default_center(xd, xd)).cpu().numpy()
     ref = O.kernel_conv_points("gaussian", x.double(), x.double(), torch.ones(n).double(), 0.05).numpy()
-    np.testing.assert_allclose(out, ref, rtol=2e-2)
+    np.testing.assert_allclose(out, ref, rtol=1e-3)
+    cross = ops.kernel_conv_raw("gaussian", xd, yd, torch.ones(m, device=DEV), 0.05,
+                                center=ops.default_center(xd, yd)).cpu().numpy()
+    refc = O.kernel_conv_points("gaussian", x.double(), y.double(), torch.ones(m).double(), 0.05).numpy()
+    np.testing.assert_allclose(cross, refc, rtol=1e-3, atol=1e-30)
+    val = SamplesLoss("gaussian", blur=0.05)(xd, yd).item()
+    ref = O.samples_loss(x.double(), y.double(), loss="gaussian", blur=0.05).item()
+    assert abs(val - ref) <= 1e-3 * abs(ref), (val, ref)
 
 
 @pytest.mark.parametrize("shape", [(200, 300, 16), (131, 67, 40), (1500, 2300, 64)])
