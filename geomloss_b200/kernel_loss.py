@@ -45,7 +45,7 @@ def kernel_points(a, x, b, y, name=None, blur=0.05, potentials=False, kernel=Non
     if potentials:
         a_y = conv(name, y, x, a, blur, center=center)
         return a_x - b_x, b_y - a_y
-    return 0.5 * torch.dot(dg(a), a_x) + 0.5 * torch.dot(dg(b), b_y) - torch.dot(a, b_x)
+    return 0.5 * (dg(a) * a_x).sum() + 0.5 * (dg(b) * b_y).sum() - (a * b_x).sum()
 
 
 def kernel_points_batched(a, x, b, y, name=None, blur=0.05, potentials=False, kernel=None, keops=False, **_ignored):

@@ -125,6 +125,11 @@ def sinkhorn_loop_points(a_log, b_log, x, y, eps_list, rho, *, p=2, debias=True,
     return None, None, new_g_ab, new_f_ba
 
 
+def _dot(w, f):
+    """<w, f> as an elementwise product + sum (a plain reduction kernel: no cuBLAS on the value path)."""
+    return (w * f).sum()
+
+
 def sinkhorn_cost(eps, rho, a, b, f_aa, g_bb, g_ab, f_ba, debias=True, potentials=False):
     """Value of the divergence (or the dual potentials) from the four potentials, unbatched vectors.
     sinkhorn_divergence.py:171-250.  The unbalanced weight is (rho + eps/2) in both passes — the
@@ -133,13 +138,13 @@ def sinkhorn_cost(eps, rho, a, b, f_aa, g_bb, g_ab, f_ba, debias=True, potential
         return (f_ba - f_aa, g_ab - g_bb) if debias else (f_ba, g_ab)
     if rho is None:
         if debias:
-            return torch.dot(a, f_ba - f_aa) + torch.dot(b, g_ab - g_bb)
-        return torch.dot(a, f_ba) + torch.dot(b, g_ab)
+            return _dot(a, f_ba - f_aa) + _dot(b, g_ab - g_bb)
+        return _dot(a, f_ba) + _dot(b, g_ab)
     w = rho + eps / 2
     if debias:
-        return torch.dot(a, w * ((-f_aa / rho).exp() - (-f_ba / rho).exp())) + torch.dot(
+        return _dot(a, w * ((-f_aa / rho).exp() - (-f_ba / rho).exp())) + _dot(
             b, w * ((-g_bb / rho).exp() - (-g_ab / rho).exp()))
-    return torch.dot(a, w * (1 - (-f_ba / rho).exp())) + torch.dot(b, w * (1 - (-g_ab / rho).exp()))
+    return _dot(a, w * (1 - (-f_ba / rho).exp())) + _dot(b, w * (1 - (-g_ab / rho).exp()))
 
 
 def sinkhorn_points(a, x, b, y, p=2, blur=0.05, reach=None, diameter=None, scaling=0.5, debias=True,

@@ -762,3 +762,85 @@ def test_images_barycenter_gradients(backward_iterations):
     else:
         # measures enter the extra iterations only through constants computed without autograd (as in the reference)
         assert (r_i is None or float(r_i.abs().max()) == 0.0) and (g_i is None or float(g_i.abs().max()) == 0.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# mid / full size against an INDEPENDENT fp64 evaluation on the device (plain torch ops, row-chunked)
+# ------------------------------------------------------------------------------------------------
+def _chunked_fp64_softmin(p, rows=4096):
+    """softmin(eps, (x, y), h) for the oracle's sinkhorn_loop: plain torch fp64 on the device, row-chunked so that it
+    reaches N = M = 1e5 (8 GB of temporaries would be needed otherwise).  Independent of libb200ot.so."""
+
+    def softmin(eps, C, h):
+        x, y = C  # (1, N, D), (1, M, D)
+        out = torch.empty(1, x.shape[1], dtype=torch.float64, device=x.device)
+        yy = (y[0] * y[0]).sum(-1)
+        for s in range(0, x.shape[1], rows):
+            xs = x[0, s:s + rows]
+            d2 = ((xs * xs).sum(-1)[:, None] - 2.0 * xs @ y[0].t() + yy[None, :]).clamp_min(0.0)
+            cost = d2 / 2 if p == 2 else d2.clamp_min(1e-8).sqrt()
+            out[0, s:s + rows] = -eps * torch.logsumexp(h.reshape(1, -1) - cost / eps, dim=1)
+        return out
+
+    return softmin
+
+
+def test_full_sinkhorn_loop_n1e5_vs_chunked_fp64():
+    """the WHOLE eps-scaling loop (10 temperatures, 48 softmins, tiled TMA kernels) at
+    N = M = 1e5 against the oracle's sinkhorn_loop driven by a chunked fp64 softmin — value, potentials and the
+    gradient w.r.t. x."""
+    from geomloss_b200 import SamplesLoss
+    from oracle import geomloss_oracle as O
+
+    g = torch.Generator().manual_seed(7)
+    n = m = 100_000
+    x = torch.rand(n, 3, generator=g)
+    y = torch.rand(m, 3, generator=g) * 0.9 + 0.1
+    kw = dict(p=2, blur=0.02, scaling=0.5)
+    xd, yd = x.to(DEV), y.to(DEV)
+    xg = xd.clone().requires_grad_(True)
+    val = SamplesLoss("sinkhorn", backend="online", **kw)(xg, yd)
+    (gx,) = torch.autograd.grad(val, xg)
+    F, G = SamplesLoss("sinkhorn", backend="online", potentials=True, **kw)(xd, yd)
+
+    x64, y64 = xd.double()[None], yd.double()[None]
+    x64r = x64.clone().requires_grad_(True)
+    a = torch.full((1, n), 1.0 / n, dtype=torch.float64, device=DEV)
+    b = torch.full((1, m), 1.0 / m, dtype=torch.float64, device=DEV)
+    diameter, eps, eps_list, rho = O.scaling_parameters(x64, y64, 2, kw["blur"], None, None, kw["scaling"])
+    sm = _chunked_fp64_softmin(2)
+    f_aa, g_bb, g_ab, f_ba = O.sinkhorn_loop(sm, O.log_weights(a), O.log_weights(b), (x64r, x64.detach()),
+                                             (y64, y64.detach()), (x64r, y64.detach()), (y64, x64.detach()), eps_list,
+                                             rho, debias=True)
+    ref = O.sinkhorn_value(eps, rho, a, b, f_aa, g_bb, g_ab, f_ba)[0]
+    (rgx,) = torch.autograd.grad(ref, x64r)
+    assert abs(val.item() - ref.item()) <= 1e-4 * abs(ref.item()), (val.item(), ref.item())
+    assert (F[0].double() - (f_ba - f_aa)[0].detach()).abs().max().item() < 1e-5
+    assert (G[0].double() - (g_ab - g_bb)[0].detach()).abs().max().item() < 1e-5
+    assert (gx.double() - rgx[0]).abs().max().item() <= 5e-4 * rgx.abs().max().item()
+
+
+def test_grid_softmin_256_cubed_sampled_lines():
+    """The 3-D separable grid kernel at BASELINE configs[4]'s side (256: the transposed last-axis path and the
+    8-outputs-per-thread tiling at full width) on 8 x 8 sampled output lines vs a separable fp64 evaluation."""
+    from geomloss_b200.sinkhorn_images import softmin_grid
+
+    n = 256
+    g = torch.Generator().manual_seed(11)
+    h = (torch.randn(1, 1, n, n, n, generator=g) * 2.0).to(DEV)
+    h[0, 0, :5] = -10000.0  # an empty slab (log_dens floor)
+    for p, eps in ((2, (1.0 / n) ** 2), (2, 0.01), (1, 2.0 / n)):
+        out = softmin_grid(eps, p, h)
+        hh = h[0, 0].double()
+        xs = torch.arange(n, device=DEV, dtype=torch.float64) / n
+        xs = xs / np.sqrt(2 * eps) if p == 2 else xs / eps
+        d = xs[:, None] - xs[None, :]
+        k = -(d**2) if p == 2 else -d.abs()
+        i0 = torch.randint(0, n, (8,), generator=g).to(DEV)
+        i1 = torch.randint(0, n, (8,), generator=g).to(DEV)
+        t2 = torch.logsumexp(hh[:, :, None, :] + k[None, None, :, :], dim=-1)
+        t1 = torch.logsumexp(t2[:, None, :, :] + k[i1][None, :, :, None], dim=2)
+        t0 = torch.logsumexp(t1[None, :, :, :] + k[i0][:, :, None, None], dim=1)
+        want = -eps * t0
+        got = out[0, 0][i0][:, i1].double()
+        assert (got - want).abs().max().item() < 3e-6 * max(1.0, want.abs().max().item()), (p, eps)
