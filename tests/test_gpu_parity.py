@@ -771,16 +771,24 @@ def _chunked_fp64_softmin(p, rows=4096):
     """softmin(eps, (x, y), h) for the oracle's sinkhorn_loop: plain torch fp64 on the device, row-chunked so that it
     reaches N = M = 1e5 (8 GB of temporaries would be needed otherwise).  Independent of libb200ot.so."""
 
+    from torch.utils.checkpoint import checkpoint
+
     def softmin(eps, C, h):
         x, y = C  # (1, N, D), (1, M, D)
-        out = torch.empty(1, x.shape[1], dtype=torch.float64, device=x.device)
         yy = (y[0] * y[0]).sum(-1)
-        for s in range(0, x.shape[1], rows):
-            xs = x[0, s:s + rows]
+
+        def block(xs):
             d2 = ((xs * xs).sum(-1)[:, None] - 2.0 * xs @ y[0].t() + yy[None, :]).clamp_min(0.0)
             cost = d2 / 2 if p == 2 else d2.clamp_min(1e-8).sqrt()
-            out[0, s:s + rows] = -eps * torch.logsumexp(h.reshape(1, -1) - cost / eps, dim=1)
-        return out
+            return -eps * torch.logsumexp(h.reshape(1, -1) - cost / eps, dim=1)
+
+        out = []
+        for s in range(0, x.shape[1], rows):
+            xs = x[0, s:s + rows]
+            # (the gradient-carrying final step: recompute each block in backward instead of keeping its
+            #  rows x M fp64 temporaries — 25 blocks of 3 GB each at N = M = 1e5)
+            out.append(checkpoint(block, xs, use_reentrant=False) if xs.requires_grad else block(xs))
+        return torch.cat(out)[None]
 
     return softmin
 
