@@ -63,6 +63,8 @@ _SIGNATURES = {
                                                   c_float, c_float, _P]),
     "b200ot_sinkhorn_final_bwd_small": (c_int32, [_P] * 15 + [c_int64, c_int64, c_int64, c_int32, c_int32, c_float,
                                                   c_float, _P]),
+    "b200ot_kernel_mmd_small": (c_int32, [_P] * 8 + [c_int64, c_int64, c_int64, c_int32, c_int32, c_float, _P]),
+    "b200ot_kernel_mmd_bwd_small": (c_int32, [_P] * 7 + [c_int64, c_int64, c_int64, c_int32, c_int32, c_float, _P]),
     "b200ot_softmin_grid": (c_int32, [_P, _P, c_float, _P, c_float, c_float, _P, c_int64, c_int32, c_int32, c_int32,
                                       c_float, _P]),
     "b200ot_ubench": (c_int32, [c_int32, c_int32, c_int32, _P, ctypes.POINTER(c_int32), _P]),

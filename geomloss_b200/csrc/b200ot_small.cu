@@ -316,6 +316,222 @@ static void fill_problems(SmallProblemSet& S, const float* x, const float* y, co
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Kernel norms on small clouds: the three (four) matvecs of kernel_loss (kernel_samples.py:116-137) in ONE launch,
+// their four row gradients in one more.
+//   forward   q = 0: a_x = K(x, x) a     1: b_y = K(y, y) b     2: b_x = K(x, y) b     3: a_y = K(y, x) a
+//   backward  side 0 (rows x): gx_i = c_i ( sum_j a_j d1 k(x_i, x_j) - sum_j b_j d1 k(x_i, y_j) ),  c_i = go a_i
+//             side 1 (rows y): gy_j = c_j ( sum_i b_i d1 k(y_j, y_i) - sum_i a_i d1 k(y_j, x_i) ),  c_j = go b_j
+// which is the gradient of  1/2 <dg(a), K_xx a> + 1/2 <dg(b), K_yy b> - <a, K_xy b>  with the reference's DoubleGrad /
+// detach pattern (kernel_samples.py:43-54, :116-146).
+// ---------------------------------------------------------------------------------------------------------------
+struct SmallConvSet {
+  const float* rows[4];
+  const float* cols[4];
+  const float* w[4];
+  float* out[4];
+  int nrows[4], ncols[4];
+};
+
+// KIND 0 gaussian: X = x sqrt(log2e)/blur, k = 2^(-|X-Y|^2/2);  1 laplacian: X = x log2e/blur, k = 2^(-|X-Y|);
+// 2 energy: X = x, k = -|X-Y|
+template <int D, int KIND>
+__global__ void __launch_bounds__(kSmallWarps * 32)
+    kernel_mmd_small_kernel(SmallConvSet S, float scale, float clampq) {
+  constexpr int W = D + 1;
+  __shared__ float tile[kSmallTile * W];
+  __shared__ float red[kSmallWarps][kSmallRows];
+  const int q = blockIdx.y, b = blockIdx.z;
+  const int nrows = S.nrows[q], ncols = S.ncols[q];
+  const int row0 = blockIdx.x * kSmallRows;
+  if (row0 >= nrows) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* __restrict__ rows = S.rows[q] + (int64_t)b * nrows * D;
+  const float* __restrict__ cols = S.cols[q] + (int64_t)b * ncols * D;
+  const float* __restrict__ wts = S.w[q] + (int64_t)b * ncols;
+  const int i = min(row0 + lane, nrows - 1);
+  float X[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) X[d] = scale * rows[(int64_t)i * D + d];
+  float acc = 0.f;
+  for (int j0 = 0; j0 < ncols; j0 += kSmallTile) {
+    const int nt = min(kSmallTile, ncols - j0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < kSmallTile; e += kSmallWarps * 32) {
+      float* dst = tile + e * W;
+      const bool live = e < nt;
+#pragma unroll
+      for (int d = 0; d < D; ++d) dst[d] = live ? scale * cols[(int64_t)(j0 + e) * D + d] : 0.f;
+      dst[D] = live ? wts[j0 + e] : 0.f;
+    }
+    __syncthreads();
+    const int c_begin = warp * (kSmallTile / kSmallWarps);
+    const int c_end = min(c_begin + kSmallTile / kSmallWarps, nt);
+#pragma unroll 4
+    for (int c = c_begin; c < c_end; ++c) {
+      const float* cp = tile + c * W;
+      float qq = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float df = X[d] - cp[d];
+        qq = fmaf(df, df, qq);
+      }
+      float k;
+      if (KIND == 0) {
+        k = ex2_approx(-0.5f * qq);
+      } else {
+        const float dist = sqrt_approx(fmaxf(qq, clampq));
+        k = (KIND == 1) ? ex2_approx(-dist) : -dist;
+      }
+      acc = fmaf(k, cp[D], acc);
+    }
+  }
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && row0 + lane < nrows) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kSmallWarps; ++w) t += red[w][lane];
+    S.out[q][(int64_t)b * nrows + row0 + lane] = t;
+  }
+}
+
+struct SmallConvBwd {
+  const float* x;
+  const float* y;
+  const float* a;
+  const float* b;
+  const float* go;  // (B,) upstream gradient of the value
+  float* gx;
+  float* gy;
+  int N, M;
+};
+
+template <int D, int KIND>
+__global__ void __launch_bounds__(kSmallWarps * 32)
+    kernel_mmd_bwd_small_kernel(SmallConvBwd S, float scale, float clampq, float coef) {
+  constexpr int W = D + 1;
+  __shared__ float tile[kSmallTile * W];
+  __shared__ float red[kSmallWarps][kSmallRows][D];
+  const int side = blockIdx.y, b = blockIdx.z;
+  const int nrows = side == 0 ? S.N : S.M;
+  const int row0 = blockIdx.x * kSmallRows;
+  if (row0 >= nrows) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* __restrict__ rows = (side == 0 ? S.x : S.y) + (int64_t)b * nrows * D;
+  const float* __restrict__ roww = (side == 0 ? S.a : S.b) + (int64_t)b * nrows;
+  const int i = min(row0 + lane, nrows - 1);
+  float X[D], A[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    X[d] = scale * rows[(int64_t)i * D + d];
+    A[d] = 0.f;
+  }
+  for (int term = 0; term < 2; ++term) {
+    // term 0: the self term (same cloud, +), term 1: the cross term (other cloud, -)
+    const bool other = (term == 1);
+    const int ncols = (side == 0) != other ? S.N : S.M;
+    const float* __restrict__ cols = ((side == 0) != other ? S.x : S.y) + (int64_t)b * ncols * D;
+    const float* __restrict__ wts = ((side == 0) != other ? S.a : S.b) + (int64_t)b * ncols;
+    const float sign = other ? -1.f : 1.f;
+    for (int j0 = 0; j0 < ncols; j0 += kSmallTile) {
+      const int nt = min(kSmallTile, ncols - j0);
+      __syncthreads();
+      for (int e = threadIdx.x; e < kSmallTile; e += kSmallWarps * 32) {
+        float* dst = tile + e * W;
+        const bool live = e < nt;
+#pragma unroll
+        for (int d = 0; d < D; ++d) dst[d] = live ? scale * cols[(int64_t)(j0 + e) * D + d] : 0.f;
+        dst[D] = live ? sign * wts[j0 + e] : 0.f;
+      }
+      __syncthreads();
+      const int c_begin = warp * (kSmallTile / kSmallWarps);
+      const int c_end = min(c_begin + kSmallTile / kSmallWarps, nt);
+#pragma unroll 2
+      for (int c = c_begin; c < c_end; ++c) {
+        const float* cp = tile + c * W;
+        float df[D];
+        float qq = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          df[d] = X[d] - cp[d];
+          qq = fmaf(df[d], df[d], qq);
+        }
+        float g;  // d1 k(x, y) = g * (X - Y) up to the constant `coef`
+        if (KIND == 0) {
+          g = ex2_approx(-0.5f * qq);
+        } else {
+          const bool inside = qq < clampq;
+          const float qc = fmaxf(qq, clampq);
+          const float rinv = rsqrt_approx(qc);
+          g = (KIND == 1) ? ex2_approx(-qc * rinv) * rinv : rinv;
+          if (inside) g = 0.f;
+        }
+        g *= cp[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) A[d] = fmaf(g, df[d], A[d]);
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int d = 0; d < D; ++d) red[warp][lane][d] = A[d];
+  __syncthreads();
+  if (warp == 0 && row0 + lane < nrows) {
+    const float c = coef * S.go[b] * roww[row0 + lane];
+    float* g = (side == 0 ? S.gx : S.gy) + ((int64_t)b * nrows + row0 + lane) * D;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kSmallWarps; ++w) t += red[w][lane][d];
+      g[d] = c * t;
+    }
+  }
+}
+
+template <int D>
+static int launch_mmd(int kind, const SmallConvSet& S, dim3 grid, float scale, float clampq, cudaStream_t st) {
+  if (kind == B200OT_KERNEL_GAUSSIAN)
+    kernel_mmd_small_kernel<D, 0><<<grid, kSmallWarps * 32, 0, st>>>(S, scale, clampq);
+  else if (kind == B200OT_KERNEL_LAPLACIAN)
+    kernel_mmd_small_kernel<D, 1><<<grid, kSmallWarps * 32, 0, st>>>(S, scale, clampq);
+  else
+    kernel_mmd_small_kernel<D, 2><<<grid, kSmallWarps * 32, 0, st>>>(S, scale, clampq);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  return B200OT_OK;
+}
+
+template <int D>
+static int launch_mmd_bwd(int kind, const SmallConvBwd& S, dim3 grid, float scale, float clampq, float coef,
+                          cudaStream_t st) {
+  if (kind == B200OT_KERNEL_GAUSSIAN)
+    kernel_mmd_bwd_small_kernel<D, 0><<<grid, kSmallWarps * 32, 0, st>>>(S, scale, clampq, coef);
+  else if (kind == B200OT_KERNEL_LAPLACIAN)
+    kernel_mmd_bwd_small_kernel<D, 1><<<grid, kSmallWarps * 32, 0, st>>>(S, scale, clampq, coef);
+  else
+    kernel_mmd_bwd_small_kernel<D, 2><<<grid, kSmallWarps * 32, 0, st>>>(S, scale, clampq, coef);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  return B200OT_OK;
+}
+
+// coordinate scale and clamp (scaled units) of a kernel kind — same conventions as b200ot_kernel_conv.cu
+static void mmd_scales(int kind_flags, float blur, float* scale, float* clampq) {
+  const int kind = kind_flags & 0xff;
+  const float clamp = cost_clamp(kind_flags);
+  if (kind == B200OT_KERNEL_GAUSSIAN) {
+    *scale = sqrtf(kLog2e) / blur;
+    *clampq = 0.f;
+  } else if (kind == B200OT_KERNEL_LAPLACIAN) {
+    *scale = kLog2e / blur;
+    *clampq = kLog2e * kLog2e * clamp;
+  } else {
+    *scale = 1.f;
+    *clampq = clamp;
+  }
+}
+
 }  // namespace b200ot
 
 using namespace b200ot;
@@ -385,6 +601,68 @@ B200OT_API int b200ot_sinkhorn_final_bwd_small(const float* x, const float* y, c
   dim3 grid((unsigned)tiles, 2u, (unsigned)B);
   cudaStream_t st = (cudaStream_t)stream;
 #define CALL(DD) launch_bwd<DD>(pe, S, grid, scale, kLog2e / eps, clampq, scale_out, grad_x, grad_y, n_terms, st)
+  B200OT_DISPATCH_D(D, CALL)
+#undef CALL
+}
+
+B200OT_API int b200ot_kernel_mmd_small(const float* x, const float* y, const float* a, const float* b, float* a_x,
+                                       float* b_y, float* b_x, float* a_y, int64_t B, int64_t N, int64_t M, int32_t D,
+                                       int32_t kind, float blur, void* stream) {
+  const int kb = kind & 0xff;
+  if (!x || !y || !a || !b || !a_x || !b_y || !b_x || B <= 0 || N <= 0 || M <= 0 || B > 65535 ||
+      N > B200OT_SMALL_MAX_POINTS || M > B200OT_SMALL_MAX_POINTS || !supported_simt_dim(D) || kb < 0 || kb > 2 ||
+      (kind & ~(0xff | B200OT_KERNEL_UNCLAMPED)) != 0 || (kb != B200OT_KERNEL_ENERGY && !(blur > 0.f)))
+    return B200OT_EINVAL;
+  SmallConvSet S;
+  const float* rows[4] = {x, y, x, y};
+  const float* cols[4] = {x, y, y, x};
+  const float* w[4] = {a, b, b, a};
+  float* out[4] = {a_x, b_y, b_x, a_y};
+  const int nr[4] = {(int)N, (int)M, (int)N, (int)M}, nc[4] = {(int)N, (int)M, (int)M, (int)N};
+  for (int q = 0; q < 4; ++q) {
+    S.rows[q] = rows[q];
+    S.cols[q] = cols[q];
+    S.w[q] = w[q];
+    S.out[q] = out[q];
+    S.nrows[q] = nr[q];
+    S.ncols[q] = nc[q];
+  }
+  float scale, clampq;
+  mmd_scales(kind, blur, &scale, &clampq);
+  dim3 grid((unsigned)ceil_div64(N > M ? N : M, kSmallRows), a_y ? 4u : 3u, (unsigned)B);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(DD) launch_mmd<DD>(kb, S, grid, scale, clampq, st)
+  B200OT_DISPATCH_D(D, CALL)
+#undef CALL
+}
+
+B200OT_API int b200ot_kernel_mmd_bwd_small(const float* x, const float* y, const float* a, const float* b,
+                                           const float* grad_value, float* grad_x, float* grad_y, int64_t B, int64_t N,
+                                           int64_t M, int32_t D, int32_t kind, float blur, void* stream) {
+  const int kb = kind & 0xff;
+  if (!x || !y || !a || !b || !grad_value || !grad_x || !grad_y || B <= 0 || N <= 0 || M <= 0 || B > 65535 ||
+      N > B200OT_SMALL_MAX_POINTS || M > B200OT_SMALL_MAX_POINTS || !supported_simt_dim(D) || kb < 0 || kb > 2 ||
+      (kind & ~(0xff | B200OT_KERNEL_UNCLAMPED)) != 0 || (kb != B200OT_KERNEL_ENERGY && !(blur > 0.f)))
+    return B200OT_EINVAL;
+  SmallConvBwd S;
+  S.x = x;
+  S.y = y;
+  S.a = a;
+  S.b = b;
+  S.go = grad_value;
+  S.gx = grad_x;
+  S.gy = grad_y;
+  S.N = (int)N;
+  S.M = (int)M;
+  float scale, clampq;
+  mmd_scales(kind, blur, &scale, &clampq);
+  // d1 k(x, y): gaussian -k (x - y)/blur^2 = -(k (X - Y)) / (scale blur^2); laplacian -k (x - y)/(blur |x - y|)
+  // = -(k (X - Y)/|X - Y|) / blur; energy -(x - y)/|x - y|
+  const float coef = kb == B200OT_KERNEL_GAUSSIAN ? -1.0f / (scale * blur * blur)
+                                                  : (kb == B200OT_KERNEL_LAPLACIAN ? -1.0f / blur : -1.0f);
+  dim3 grid((unsigned)ceil_div64(N > M ? N : M, kSmallRows), 2u, (unsigned)B);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(DD) launch_mmd_bwd<DD>(kb, S, grid, scale, clampq, coef, st)
   B200OT_DISPATCH_D(D, CALL)
 #undef CALL
 }

@@ -28,7 +28,7 @@ import warnings
 from .kernel_loss import kernel_points, kernel_points_batched
 from .multiscale import kernel_multiscale, sinkhorn_multiscale
 from .ops import MAX_D
-from . import sinkhorn_small
+from . import kernel_small, sinkhorn_small
 from .sinkhorn import sinkhorn_points, sinkhorn_points_batched
 
 _LOSSES = ("sinkhorn", "hausdorff", "energy", "gaussian", "laplacian")
@@ -136,6 +136,16 @@ class SamplesLoss(Module):
             # small clouds (batched or not): one launch per Sinkhorn iteration (csrc/b200ot_small.cu)
             lift = (lambda t: t.unsqueeze(0)) if B == 0 else (lambda t: t)
             values = sinkhorn_small.sinkhorn_small(lift(a), lift(x), lift(b), lift(y), **kw)
+            if self.potentials:
+                F, G = values
+                return (F.view(1, -1), G.view(1, -1)) if B == 0 else (F.view_as(a), G.view_as(b))
+            return values[0] if B == 0 else values
+        if (self.loss in ("gaussian", "laplacian", "energy") and not self._engine and self.kernel is None
+                and not self.potentials and sinkhorn_small.eligible(N, M, D)):
+            # small clouds: the matvecs of kernel_loss in one launch, the cloud gradients in one more
+            lift = (lambda t: t.unsqueeze(0)) if B == 0 else (lambda t: t)
+            values = kernel_small.kernel_small(lift(a), lift(x), lift(b), lift(y), name=self.loss, blur=self.blur,
+                                               potentials=self.potentials, keops=kw["keops"])
             if self.potentials:
                 F, G = values
                 return (F.view(1, -1), G.view(1, -1)) if B == 0 else (F.view_as(a), G.view_as(b))

@@ -248,6 +248,17 @@ B200OT_API int b200ot_sinkhorn_final_bwd_small(const float* x, const float* y, c
                                                float* grad_x, float* grad_y, int64_t B, int64_t N, int64_t M,
                                                int32_t D, int32_t p, float eps, float scale_out, void* stream);
 
+/* Kernel norms on small clouds (same size limits): the matvecs of kernel_loss (kernel_samples.py:116-137) in one launch,
+ *     a_x = K(x,x) a   b_y = K(y,y) b   b_x = K(x,y) b   a_y = K(y,x) a  (a_y nullable: only needed for potentials / d/db)
+ * and the gradient of  value = 1/2 <a, a_x> + 1/2 <b, b_y> - <a, b_x>  w.r.t. both clouds, with the reference's
+ * DoubleGrad / detach pattern (kernel_samples.py:43-54, :116-146), scaled by grad_value[batch], in one more. */
+B200OT_API int b200ot_kernel_mmd_small(const float* x, const float* y, const float* a, const float* b, float* a_x,
+                                       float* b_y, float* b_x, float* a_y, int64_t B, int64_t N, int64_t M, int32_t D,
+                                       int32_t kind, float blur, void* stream);
+B200OT_API int b200ot_kernel_mmd_bwd_small(const float* x, const float* y, const float* a, const float* b,
+                                           const float* grad_value, float* grad_x, float* grad_y, int64_t B, int64_t N,
+                                           int64_t M, int32_t D, int32_t kind, float blur, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Grid softmin  —  the separable soft-C-transform on (batch, N, N[, N]) images / volumes
  * replaces softmin_grid (src/geomloss/_legacy/utils.py:190-279), the operator of the image Sinkhorn loop

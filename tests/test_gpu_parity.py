@@ -341,7 +341,7 @@ def test_sinkhorn_batched(sinkhorn_path):
 
 @pytest.mark.parametrize("name", golden_names("kernel_gaussian") + golden_names("kernel_laplacian")
                          + golden_names("kernel_energy"))
-def test_kernel_losses(name):
+def test_kernel_losses(name, sinkhorn_path):
     from geomloss_b200 import SamplesLoss
 
     g = load_golden(name)

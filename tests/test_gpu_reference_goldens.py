@@ -70,7 +70,7 @@ def test_sinkhorn_keops_backends(name, sinkhorn_path):
 
 @pytest.mark.parametrize("name", golden_names("ms_kernel_") + ["online_gaussian_batched", "online_laplacian_batched",
                                                               "online_energy"])
-def test_kernel_keops_backends(name):
+def test_kernel_keops_backends(name, sinkhorn_path):
     from geomloss_b200 import SamplesLoss
 
     g = load_golden(name)
