@@ -60,9 +60,12 @@ _SIGNATURES = {
     "b200ot_kernel_conv_bwd_finalize": (c_int32, [_P, c_int32, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_float,
                                                   _P]),
     "b200ot_sinkhorn_iteration_small": (c_int32, [_P] * 13 + [c_int64, c_int64, c_int64, c_int32, c_int32, c_float,
-                                                  c_float, c_float, _P]),
+                                                  c_float, c_float, c_int32, _P]),
+    "b200ot_sinkhorn_loop_small": (c_int32, [_P, _P, _P, _P, c_int32, ctypes.POINTER(ctypes.c_double), c_int32,
+                                             ctypes.c_double, c_int32, _P, _P, ctypes.POINTER(c_int32), c_int64,
+                                             c_int64, c_int64, c_int32, c_int32, _P]),
     "b200ot_sinkhorn_final_bwd_small": (c_int32, [_P] * 15 + [c_int64, c_int64, c_int64, c_int32, c_int32, c_float,
-                                                  c_float, _P]),
+                                                  c_float, c_int32, _P]),
     "b200ot_kernel_mmd_small": (c_int32, [_P] * 8 + [c_int64, c_int64, c_int64, c_int32, c_int32, c_float, _P]),
     "b200ot_kernel_mmd_bwd_small": (c_int32, [_P] * 7 + [c_int64, c_int64, c_int64, c_int32, c_int32, c_float, _P]),
     "b200ot_softmin_grid": (c_int32, [_P, _P, c_float, _P, c_float, c_float, _P, c_int64, c_int32, c_int32, c_int32,

@@ -9,6 +9,7 @@
 #include "pack.cuh"
 #include "plan.cuh"
 #include "rowsum.cuh"
+#include "rowsum_launch.cuh"
 #include "tcbwd.cuh"
 #include "tcconv.cuh"
 
@@ -107,13 +108,13 @@ static int launch_rowsum(const ReducePlan& pl, cudaStream_t st, const float* x, 
                          const int2* pieces = nullptr) {
   if (pl.small) {
     using C = RowSumCfg<MODE, D, kSmallR, kSmallNT, kSmallTJ, 3, 4>;
-    return launch_reduce<C>(rowsum_partial_kernel<C>, pl, st, x, center, scale, clampq, cols,
+    return launch_rowsum_kernel<C>(pl, st, x, center, scale, clampq, cols,
                             (const float*)nullptr, part, N, pl.ntiles, pl.tiles_per_split, seg, pieces);
   }
   // D >= 5: one row per thread (same 512 rows per CTA) keeps the 2 x (D+1) accumulator pairs in registers
   using C = std::conditional_t<(D <= 4), RowSumCfg<MODE, D, kBigR, kBigNT, kBigTJ, 3, 2>,
                                RowSumCfg<MODE, D, 1, kBigR * kBigNT, kBigTJ, 3, 1>>;
-  return launch_reduce<C>(rowsum_partial_kernel<C>, pl, st, x, center, scale, clampq, cols, (const float*)nullptr,
+  return launch_rowsum_kernel<C>(pl, st, x, center, scale, clampq, cols, (const float*)nullptr,
                           part, N, pl.ntiles, pl.tiles_per_split, seg, pieces);
 }
 

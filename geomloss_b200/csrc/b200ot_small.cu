@@ -40,6 +40,14 @@ struct SmallProblemSet {
   int nrows[4], ncols[4];
 };
 
+// log2-domain log-weight of a column: from a natural-log weight (w_linear = 0), or from the weight itself with the
+// reference's floor log_weights(a)[a <= 0] = -100000 (sinkhorn_divergence.py:61-65) — saves the host four tiny
+// elementwise launches per cloud
+__device__ __forceinline__ float column_log2_weight(float w, int w_linear) {
+  if (!w_linear) return w * kLog2e;
+  return w > 0.f ? log2f(w) : -100000.0f * kLog2e;
+}
+
 template <int D, int P>
 __device__ __forceinline__ float pair_exponent_small(const float (&X)[D], const float* __restrict__ c, float H,
                                                      float clampq) {
@@ -57,7 +65,7 @@ __device__ __forceinline__ float pair_exponent_small(const float (&X)[D], const 
 template <int D, int P>
 __global__ void __launch_bounds__(kSmallWarps * 32)
     sinkhorn_iteration_small_kernel(SmallProblemSet S, float scale, float inv_eps_log2e, float clampq,
-                                    float alpha_old, float beta_neg_eps_ln2) {
+                                    float alpha_old, float beta_neg_eps_ln2, int w_linear) {
   constexpr int W = D + 1;
   __shared__ float tile[kSmallTile * W];
   __shared__ float2 red[kSmallWarps][kSmallRows];
@@ -87,7 +95,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
         const int j = j0 + e;
 #pragma unroll
         for (int d = 0; d < D; ++d) dst[d] = scale * cols[(int64_t)j * D + d];
-        float h = logw[j] * kLog2e;
+        float h = column_log2_weight(logw[j], w_linear);
         if (pot) h = fmaf(pot[j], inv_eps_log2e, h);
         dst[D] = h;
       } else {
@@ -146,7 +154,7 @@ template <int D, int P>
 __global__ void __launch_bounds__(kSmallWarps * 32)
     sinkhorn_final_bwd_small_kernel(SmallProblemSet S, float scale, float inv_eps_log2e, float clampq,
                                     float out_scale, float* __restrict__ grad_x, float* __restrict__ grad_y,
-                                    int n_terms) {
+                                    int n_terms, int w_linear) {
   constexpr int W = D + 1;
   __shared__ float tile[kSmallTile * W];
   __shared__ float red[kSmallWarps][kSmallRows][D];
@@ -188,7 +196,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
           const int j = j0 + e;
 #pragma unroll
           for (int d = 0; d < D; ++d) dst[d] = scale * cols[(int64_t)j * D + d];
-          float h = logw[j] * kLog2e;
+          float h = column_log2_weight(logw[j], w_linear);
           if (pot) h = fmaf(pot[j], inv_eps_log2e, h);
           dst[D] = h;
         } else {
@@ -257,26 +265,26 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
 
 template <int D>
 static int launch_iter(int pe, const SmallProblemSet& S, dim3 grid, float scale, float inv_eps_log2e, float clampq,
-                       float alpha_old, float beta_neg_eps_ln2, cudaStream_t st) {
+                       float alpha_old, float beta_neg_eps_ln2, int w_linear, cudaStream_t st) {
   if (pe == 2)
     sinkhorn_iteration_small_kernel<D, 2><<<grid, kSmallWarps * 32, 0, st>>>(S, scale, inv_eps_log2e, clampq,
-                                                                             alpha_old, beta_neg_eps_ln2);
+                                                                             alpha_old, beta_neg_eps_ln2, w_linear);
   else
     sinkhorn_iteration_small_kernel<D, 1><<<grid, kSmallWarps * 32, 0, st>>>(S, scale, inv_eps_log2e, clampq,
-                                                                             alpha_old, beta_neg_eps_ln2);
+                                                                             alpha_old, beta_neg_eps_ln2, w_linear);
   B200OT_CUDA_TRY(cudaGetLastError());
   return B200OT_OK;
 }
 
 template <int D>
 static int launch_bwd(int pe, const SmallProblemSet& S, dim3 grid, float scale, float inv_eps_log2e, float clampq,
-                      float out_scale, float* gx, float* gy, int n_terms, cudaStream_t st) {
+                      float out_scale, float* gx, float* gy, int n_terms, int w_linear, cudaStream_t st) {
   if (pe == 2)
     sinkhorn_final_bwd_small_kernel<D, 2><<<grid, kSmallWarps * 32, 0, st>>>(S, scale, inv_eps_log2e, clampq,
-                                                                             out_scale, gx, gy, n_terms);
+                                                                             out_scale, gx, gy, n_terms, w_linear);
   else
     sinkhorn_final_bwd_small_kernel<D, 1><<<grid, kSmallWarps * 32, 0, st>>>(S, scale, inv_eps_log2e, clampq,
-                                                                             out_scale, gx, gy, n_terms);
+                                                                             out_scale, gx, gy, n_terms, w_linear);
   B200OT_CUDA_TRY(cudaGetLastError());
   return B200OT_OK;
 }
@@ -543,7 +551,7 @@ B200OT_API int b200ot_sinkhorn_iteration_small(const float* x, const float* y, c
                                                const float* g_bb, float* f_ba_out, float* g_ab_out, float* f_aa_out,
                                                float* g_bb_out, float* lse2_out, int64_t B, int64_t N, int64_t M,
                                                int32_t D, int32_t p, float eps, float alpha_old, float beta,
-                                               void* stream) {
+                                               int32_t weights_linear, void* stream) {
   if (!x || !y || !a_log || !b_log || !f_ba_out || !g_ab_out || B <= 0 || N <= 0 || M <= 0 || B > 65535 ||
       N > B200OT_SMALL_MAX_POINTS || M > B200OT_SMALL_MAX_POINTS || !supported_simt_dim(D) || !valid_p(p) ||
       !(eps > 0.f) || ((f_aa_out == nullptr) != (g_bb_out == nullptr)))
@@ -570,7 +578,7 @@ B200OT_API int b200ot_sinkhorn_iteration_small(const float* x, const float* y, c
   dim3 grid((unsigned)tiles, debias ? 4u : 2u, (unsigned)B);
   const float bneg = -beta * eps * kLn2;
   cudaStream_t st = (cudaStream_t)stream;
-#define CALL(DD) launch_iter<DD>(pe, S, grid, scale, kLog2e / eps, clampq, alpha_old, bneg, st)
+#define CALL(DD) launch_iter<DD>(pe, S, grid, scale, kLog2e / eps, clampq, alpha_old, bneg, weights_linear, st)
   B200OT_DISPATCH_D(D, CALL)
 #undef CALL
 }
@@ -580,7 +588,8 @@ B200OT_API int b200ot_sinkhorn_final_bwd_small(const float* x, const float* y, c
                                                const float* g_bb, const float* lse2, const float* go_f_ba,
                                                const float* go_g_ab, const float* go_f_aa, const float* go_g_bb,
                                                float* grad_x, float* grad_y, int64_t B, int64_t N, int64_t M,
-                                               int32_t D, int32_t p, float eps, float scale_out, void* stream) {
+                                               int32_t D, int32_t p, float eps, float scale_out,
+                                               int32_t weights_linear, void* stream) {
   if (!x || !y || !a_log || !b_log || !lse2 || !grad_x || !grad_y || B <= 0 || N <= 0 || M <= 0 || B > 65535 ||
       N > B200OT_SMALL_MAX_POINTS || M > B200OT_SMALL_MAX_POINTS || !supported_simt_dim(D) || !valid_p(p) ||
       !(eps > 0.f))
@@ -600,9 +609,47 @@ B200OT_API int b200ot_sinkhorn_final_bwd_small(const float* x, const float* y, c
   const int64_t tiles = ceil_div64(N > M ? N : M, kSmallRows);
   dim3 grid((unsigned)tiles, 2u, (unsigned)B);
   cudaStream_t st = (cudaStream_t)stream;
-#define CALL(DD) launch_bwd<DD>(pe, S, grid, scale, kLog2e / eps, clampq, scale_out, grad_x, grad_y, n_terms, st)
+#define CALL(DD) \
+  launch_bwd<DD>(pe, S, grid, scale, kLog2e / eps, clampq, scale_out, grad_x, grad_y, n_terms, weights_linear, st)
   B200OT_DISPATCH_D(D, CALL)
 #undef CALL
+}
+
+B200OT_API int b200ot_sinkhorn_loop_small(const float* x, const float* y, const float* a, const float* b,
+                                          int32_t weights_linear, const double* eps_list, int32_t n_eps, double rho,
+                                          int32_t debias, float* pots_a, float* pots_b, int32_t* result_in_a,
+                                          int64_t B, int64_t N, int64_t M, int32_t D, int32_t p, void* stream) {
+  if (!eps_list || n_eps <= 0 || !pots_a || !pots_b || !result_in_a || pots_a == pots_b) return B200OT_EINVAL;
+  auto view = [&](float* base, float** f_ba, float** g_ab, float** f_aa, float** g_bb) {
+    *f_ba = base;
+    *g_ab = base + B * N;
+    *f_aa = debias ? base + B * (N + M) : nullptr;
+    *g_bb = debias ? base + B * (2 * N + M) : nullptr;
+  };
+  auto damp = [&](double eps) { return rho > 0.0 ? 1.0 / (1.0 + eps / rho) : 1.0; };
+  float *c0, *c1, *c2, *c3, *n0, *n1, *n2, *n3;
+  float* cur = pots_a;
+  float* nxt = pots_b;
+  view(cur, &c0, &c1, &c2, &c3);
+  // initialisation at the first temperature (sinkhorn_divergence.py:461-465): h = log-weights only
+  int rc = b200ot_sinkhorn_iteration_small(x, y, a, b, nullptr, nullptr, nullptr, nullptr, c0, c1, c2, c3, nullptr, B, N, M,
+                                           D, p, (float)eps_list[0], 0.f, (float)damp(eps_list[0]), weights_linear,
+                                           stream);
+  if (rc) return rc;
+  // eps-scaling descent (:468-493): symmetric, averaged updates
+  for (int i = 0; i < n_eps; ++i) {
+    const double eps = eps_list[i];
+    view(cur, &c0, &c1, &c2, &c3);
+    view(nxt, &n0, &n1, &n2, &n3);
+    rc = b200ot_sinkhorn_iteration_small(x, y, a, b, c0, c1, c2, c3, n0, n1, n2, n3, nullptr, B, N, M, D, p, (float)eps,
+                                         0.5f, (float)(0.5 * damp(eps)), weights_linear, stream);
+    if (rc) return rc;
+    float* t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+  *result_in_a = (cur == pots_a) ? 1 : 0;
+  return B200OT_OK;
 }
 
 B200OT_API int b200ot_kernel_mmd_small(const float* x, const float* y, const float* a, const float* b, float* a_x,

@@ -79,7 +79,10 @@ template <class C>
 static int launch_partial(const float* x, const float* center, float scale, float clampq, const float* cols,
                           float* part, const ReducePlan& pl, int64_t N, cudaStream_t st, const int4* seg,
                           const int2* pieces) {
-  return launch_reduce<C>(softmin_partial_kernel<C>, pl, st, x, center, scale, clampq, cols,
+  if (seg != nullptr)
+    return launch_reduce<C>(softmin_partial_kernel<C, true>, pl, st, x, center, scale, clampq, cols,
+                            reinterpret_cast<float2*>(part), N, pl.ntiles, pl.tiles_per_split, seg, pieces);
+  return launch_reduce<C>(softmin_partial_kernel<C, false>, pl, st, x, center, scale, clampq, cols,
                           reinterpret_cast<float2*>(part), N, pl.ntiles, pl.tiles_per_split, seg, pieces);
 }
 

@@ -9,6 +9,7 @@
 #include "host_util.cuh"
 #include "plan.cuh"
 #include "rowsum.cuh"
+#include "rowsum_launch.cuh"
 
 #include <type_traits>
 
@@ -56,13 +57,13 @@ static int launch_rowsum(const ReducePlan& pl, cudaStream_t st, const float* x, 
                          const int4* tile_ptr = nullptr, const int2* tile_list = nullptr) {
   if (pl.small) {
     using C = RowSumCfg<MODE, D, kSmallR, kSmallNT, kSmallTJ, 3, 4>;
-    return launch_reduce<C>(rowsum_partial_kernel<C>, pl, st, x, center, scale, clampq, cols, lse2, part, N,
+    return launch_rowsum_kernel<C>(pl, st, x, center, scale, clampq, cols, lse2, part, N,
                             pl.ntiles, pl.tiles_per_split, tile_ptr, tile_list);
   }
   // D >= 5: one row per thread (same 512 rows per CTA) keeps the 2 x (D+1) accumulator pairs in registers
   using C = std::conditional_t<(D <= 4), RowSumCfg<MODE, D, kBigR, kBigNT, kBigTJ, 3, 2>,
                                RowSumCfg<MODE, D, 1, kBigR * kBigNT, kBigTJ, 3, 1>>;
-  return launch_reduce<C>(rowsum_partial_kernel<C>, pl, st, x, center, scale, clampq, cols, lse2, part, N, pl.ntiles,
+  return launch_rowsum_kernel<C>(pl, st, x, center, scale, clampq, cols, lse2, part, N, pl.ntiles,
                           pl.tiles_per_split, tile_ptr, tile_list);
 }
 

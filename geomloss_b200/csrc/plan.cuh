@@ -12,6 +12,7 @@ namespace b200ot {
 constexpr int kBigNT = 256, kBigR = 2, kBigTJ = 1024;
 constexpr int kSmallNT = 128, kSmallR = 1, kSmallTJ = 256;
 constexpr int kPackPad = 1024;  // packed column buffers are padded to this many columns
+constexpr int kPlanWaves = 16;  // waves (of 2 CTAs/SM) a launch is cut into when the problem is large enough
 
 struct ReducePlan {
   int tj;        // columns per tile
@@ -26,13 +27,14 @@ struct ReducePlan {
 // Pure function of (N, M, D) and the SM count, so that the scratch-size query, the pack stage and the
 // reduction stage of the C ABI always agree.
 //
-// Column splits.  All CTAs of a launch cost the same (rows x tiles of one split), so they run in near lock-step
-// waves of `resident` = SMs x CTAs/SM; a grid that is not a whole number of waves pays a full unit for its last
-// partial wave (round 1: 5 862 CTAs over 444 slots = 13.2 waves, up to 5.7 % of the kernel).  The plan therefore
-// (i) cuts the columns into enough splits for ~40 waves, which bounds that loss by ~1/40 even in the worst case,
-// and (ii) among the neighbouring split counts takes the one whose last wave is fullest.  A split keeps >= 8
-// tiles, so the per-CTA prologue (row loads, barrier init, TMA ring fill: a few us) stays < 1 % of its ~0.5 ms.
+// Column splits: as FEW as fill the machine for ~16 waves of 2 CTAs/SM.  Measured on B200 at N = 1e6, D = 3
+// (profiles/r02_explore_nsplit.jsonl): the kernel time is flat in the number of splits for M = 1e6 (3 .. 12 splits:
+// 247.8 .. 249.4 ms, i.e. the 13.2-wave grid of round 1 loses nothing measurable to its partial last wave — CTAs
+// drift out of lock-step within a few waves) and GROWS with it on a 125 000-column shard (4 / 8 / 12 / 16 splits:
+// 32.6 / 34.1 / 35.4 / 36.9 ms): every extra CTA costs its prologue and a cold TMA ring, which is what the 8-GPU
+// shard kernel of round 1 was paying.  A 40-wave plan sized for the wave-quantisation model was tried and reverted.
 inline ReducePlan make_plan(int64_t N, int64_t M, int D = 3) {
+  (void)D;
   ReducePlan p;
   const int big_rows = kBigNT * kBigR;
   p.small = (N < 8 * (int64_t)big_rows) || (M < 4 * kBigTJ);
@@ -40,33 +42,12 @@ inline ReducePlan make_plan(int64_t N, int64_t M, int D = 3) {
   p.rows_cta = p.small ? kSmallNT * kSmallR : big_rows;
   p.ntiles = (int)(round_up64(M, p.tj) / p.tj);
   p.row_tiles = ceil_div64(N, p.rows_cta);
-  const int cps = p.small ? 4 : (D <= 4 ? 3 : 2);  // CTAs/SM of the softmin instantiations (b200ot_softmin.cu)
-  const int64_t resident = (int64_t)num_sms() * cps;
-  int64_t cap = p.ntiles / 8;  // >= 8 tiles per split ...
-  if (cap < 1) cap = 1;
-  int64_t want = ceil_div64(40 * resident, p.row_tiles);
-  if (want > cap) want = cap;
-  // ... unless the problem is too small to fill the machine once: then parallelism comes first
-  int64_t fill = ceil_div64(resident, p.row_tiles);
-  if (fill > p.ntiles) fill = p.ntiles;
-  if (want < fill) want = fill;
+  const int64_t target_ctas = (int64_t)num_sms() * 2 * kPlanWaves;
+  int64_t want = ceil_div64(target_ctas, p.row_tiles);
   if (want < 1) want = 1;
   if (want > 64) want = 64;
-  cap = want + 6 < 64 ? want + 6 : 64;
-  if (cap > p.ntiles) cap = p.ntiles;
-  double best_eff = -1.0;
-  int best_tps = p.ntiles;
-  for (int64_t w = want; w <= want + 6 && w <= cap; ++w) {
-    const int tps = (int)ceil_div64(p.ntiles, w);
-    const int ns = (int)ceil_div64(p.ntiles, tps);
-    const double waves = (double)(p.row_tiles * ns) / (double)resident;
-    const double eff = waves / ceil(waves);
-    if (eff > best_eff + 1e-3) {
-      best_eff = eff;
-      best_tps = tps;
-    }
-  }
-  p.tiles_per_split = best_tps;
+  if (want > p.ntiles) want = p.ntiles;
+  p.tiles_per_split = (int)ceil_div64(p.ntiles, want);
   p.n_split = (int)ceil_div64(p.ntiles, p.tiles_per_split);
   return p;
 }

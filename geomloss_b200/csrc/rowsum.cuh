@@ -46,13 +46,12 @@ struct RowSumCfg {
   static constexpr int TILE_FLOATS = (TJ / 2) * NF2 * 2;
   static constexpr int TILE_BYTES = TILE_FLOATS * 4;
   static constexpr int ROWS_PER_CTA = NT * R;
-  static constexpr int SMEM_BYTES = STAGES * TILE_BYTES + 2 * STAGES * 8 + 16;  // + per-stage pair counts
-  static_assert(STAGES <= 4, "the per-stage pair counts live in one 16-byte slot");
+  static constexpr int SMEM_BYTES = STAGES * TILE_BYTES + 2 * STAGES * 8;
 };
 
 // rowterm: per-row additive term of the exponent (softmin bwd: rowc_i - lse2_i; gaussian: rowc_i), may be null.
 // If rowterm_is_lse2, the kernel forms  (DIRECT ? 0 : -|X|^2/2) - rowterm[i]  itself.
-template <class C>
+template <class C, bool RANGES>
 __global__ void __launch_bounds__(C::NT + 32, C::MINB)
     rowsum_partial_kernel(const float* __restrict__ x, const float* __restrict__ center, float scale, float clampq,
                           const float* __restrict__ cols, const float* __restrict__ lse2, float* __restrict__ part,
@@ -63,12 +62,11 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
   float* tiles = reinterpret_cast<float*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * C::TILE_BYTES);
   uint64_t* empty = full + STAGES;
-  int* cnt = reinterpret_cast<int*>(empty + STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int split = blockIdx.y;
-  const bool sparse = (seg != nullptr);  // ranges mode (segments + column pieces): see softmin.cuh
+  constexpr bool sparse = RANGES;  // ranges mode (segments + column pieces): see softmin.cuh
   int t0, t1, nrows;
   int64_t row0;
   if (sparse) {
@@ -79,7 +77,7 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
     t1 = sg.w;
   } else {
     row0 = (int64_t)blockIdx.x * C::ROWS_PER_CTA;
-    nrows = (int)min((int64_t)C::ROWS_PER_CTA, N - row0);
+    nrows = 0;  // (dense mode bounds its rows with N)
     t0 = split * tiles_per_split;
     t1 = min(ntiles, t0 + tiles_per_split);
   }
@@ -102,7 +100,6 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
         if (sparse) {
           const int2 pc = pieces[t0 + k];
           const uint32_t bytes = (uint32_t)pc.y * (NF2 * 4);
-          cnt[st] = pc.y >> 1;
           mbar_arrive_expect_tx(&full[st], bytes);
           tma_load_1d(tiles + st * C::TILE_FLOATS, cols + (int64_t)pc.x * NF2, bytes, &full[st]);
         } else {
@@ -123,7 +120,11 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     int64_t i = row_base + (int64_t)r * NT;
-    if (tid + r * NT >= nrows) i = row0 + nrows - 1;
+    if constexpr (sparse) {
+      if (tid + r * NT >= nrows) i = row0 + nrows - 1;
+    } else {
+      if (i >= N) i = N - 1;
+    }
     float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -143,8 +144,11 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
 #pragma unroll
     for (int a = 0; a < NACC; ++a) A[r][a] = dup2(0.f);
 
+  int np_next = (sparse && nt > 0) ? (pieces[t0].y >> 1) : C::TJ / 2;  // see softmin.cuh
   for (int k = 0; k < nt; ++k) {
     const int st = k % STAGES;
+    const int npairs = np_next;
+    if (sparse && k + 1 < nt) np_next = pieces[t0 + k + 1].y >> 1;
     mbar_wait(&full[st], (k / STAGES) & 1);
     const float4* tp = reinterpret_cast<const float4*>(tiles + st * C::TILE_FLOATS);
 
@@ -155,7 +159,6 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
 #pragma unroll
       for (int a = 0; a < NACC; ++a) T[r][a] = dup2(0.f);
 
-    const int npairs = sparse ? cnt[st] : C::TJ / 2;
 #pragma unroll 2
     for (int jp = 0; jp < npairs; ++jp) {
       float2 S[NF2];
@@ -234,7 +237,8 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int64_t i = row_base + (int64_t)r * NT;
-    if (tid + r * NT < nrows) {
+    const bool live = sparse ? (tid + r * NT < nrows) : (i < N);
+    if (live) {
 #pragma unroll
       for (int a = 0; a < NACC; ++a) part[((int64_t)split * N + i) * NACC + a] = A[r][a].x + A[r][a].y;
     }

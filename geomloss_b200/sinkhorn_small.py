@@ -10,10 +10,12 @@ The reference's own benchmark protocol at N = 1 000 (blur = .05: 8 temperatures)
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib, ops
-from .sinkhorn import damping, log_weights, scaling_parameters, sinkhorn_cost_batched
+from .sinkhorn import damping, scaling_parameters, sinkhorn_cost_batched
 
 # largest cloud served by the one-launch-per-iteration kernels; beyond, the tiled TMA kernels win
 # (measured crossover: profiles/r02_small_n.md)
@@ -24,45 +26,64 @@ def eligible(N, M, D):
     return max(N, M) <= SMALL_MAX and D <= ops.MAX_D
 
 
-def _iteration(x, y, a_log, b_log, pots, outs, eps, alpha_old, beta, p, lse2=None):
-    """pots: (f_ba, g_ab, f_aa, g_bb) or None (initialisation); outs: 4 tensors (f_aa / g_bb None without debias)."""
+def _views(buf, B, N, M, debias):
+    f_ba = buf[: B * N].view(B, N)
+    g_ab = buf[B * N: B * (N + M)].view(B, M)
+    if not debias:
+        return f_ba, g_ab, None, None
+    return f_ba, g_ab, buf[B * (N + M): B * (2 * N + M)].view(B, N), buf[B * (2 * N + M):].view(B, M)
+
+
+def _descent(x, y, a, b, eps_list, rho, p, debias):
+    """Initialisation + every eps-scaling step in ONE C call (n_eps + 1 launches enqueued back to back); weights are
+    passed as they are, their logarithm (with the reference's -100000 floor) is taken inside the kernel."""
     B, N, D = x.shape
     M = y.shape[1]
+    dev = x.device
+    bufs = torch.empty(2, B * (2 * N + 2 * M), dtype=torch.float32, device=dev)
+    eps_arr = (ctypes.c_double * len(eps_list))(*[float(e) for e in eps_list])
+    which = ctypes.c_int32(0)
     L = _lib.lib()
     P = ops._ptr
-    f_ba, g_ab, f_aa, g_bb = pots if pots is not None else (None, None, None, None)
-    with torch.cuda.device(x.device):
-        rc = L.b200ot_sinkhorn_iteration_small(P(x), P(y), P(a_log), P(b_log), P(f_ba), P(g_ab), P(f_aa), P(g_bb),
-                                               P(outs[0]), P(outs[1]), P(outs[2]), P(outs[3]), P(lse2), B, N, M, D,
-                                               int(p), float(eps), float(alpha_old), float(beta),
-                                               ops._stream(x.device))
-    _lib.check(rc, "b200ot_sinkhorn_iteration_small")
-    ops.count_launches(1)
+    with torch.cuda.device(dev):
+        rc = L.b200ot_sinkhorn_loop_small(P(x), P(y), P(a), P(b), 1, eps_arr, len(eps_list),
+                                          -1.0 if rho is None else float(rho), 1 if debias else 0, P(bufs[0]),
+                                          P(bufs[1]), ctypes.byref(which), B, N, M, D, int(p), ops._stream(dev))
+    _lib.check(rc, "b200ot_sinkhorn_loop_small")
+    ops.count_launches(len(eps_list) + 1)
+    return _views(bufs[0] if which.value else bufs[1], B, N, M, debias)
 
 
 class _FinalStep(torch.autograd.Function):
     """The last, non-averaged update (sinkhorn_divergence.py:612-623): potentials detached, gradient to x and y only."""
 
     @staticmethod
-    def forward(ctx, x, y, a_log, b_log, f_ba, g_ab, f_aa, g_bb, eps, lam, p, debias):
+    def forward(ctx, x, y, a, b, f_ba, g_ab, f_aa, g_bb, eps, lam, p, debias):
         B, N, D = x.shape
         M = y.shape[1]
         dev = x.device
-        new = [torch.empty(B, N, device=dev), torch.empty(B, M, device=dev),
-               torch.empty(B, N, device=dev) if debias else None, torch.empty(B, M, device=dev) if debias else None]
+        new = torch.empty(B * (2 * N + 2 * M), dtype=torch.float32, device=dev)
+        n_f_ba, n_g_ab, n_f_aa, n_g_bb = _views(new, B, N, M, debias)
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         lse2 = torch.empty(B * (2 * N + 2 * M), device=dev) if need else None
-        _iteration(x, y, a_log, b_log, (f_ba, g_ab, f_aa, g_bb), new, eps, 0.0, lam, p, lse2=lse2)
+        L = _lib.lib()
+        P = ops._ptr
+        with torch.cuda.device(dev):
+            rc = L.b200ot_sinkhorn_iteration_small(P(x), P(y), P(a), P(b), P(f_ba), P(g_ab), P(f_aa), P(g_bb),
+                                                   P(n_f_ba), P(n_g_ab), P(n_f_aa), P(n_g_bb), P(lse2), B, N, M, D,
+                                                   int(p), float(eps), 0.0, float(lam), 1, ops._stream(dev))
+        _lib.check(rc, "b200ot_sinkhorn_iteration_small")
+        ops.count_launches(1)
         if need:
-            ctx.save_for_backward(x, y, a_log, b_log, f_ba, g_ab, f_aa if debias else f_ba, g_bb if debias else g_ab, lse2)
+            ctx.save_for_backward(x, y, a, b, f_ba, g_ab, f_aa if debias else f_ba, g_bb if debias else g_ab, lse2)
             ctx.meta = (float(eps), float(lam), int(p), bool(debias))
         if debias:
-            return new[0], new[1], new[2], new[3]
-        return new[0], new[1]
+            return n_f_ba, n_g_ab, n_f_aa, n_g_bb
+        return n_f_ba, n_g_ab
 
     @staticmethod
     def backward(ctx, *gos):
-        x, y, a_log, b_log, f_ba, g_ab, f_aa, g_bb, lse2 = ctx.saved_tensors
+        x, y, a, b, f_ba, g_ab, f_aa, g_bb, lse2 = ctx.saved_tensors
         eps, lam, p, debias = ctx.meta
         B, N, D = x.shape
         M = y.shape[1]
@@ -71,10 +92,10 @@ class _FinalStep(torch.autograd.Function):
         L = _lib.lib()
         P = ops._ptr
         with torch.cuda.device(x.device):
-            rc = L.b200ot_sinkhorn_final_bwd_small(P(x), P(y), P(a_log), P(b_log), P(f_ba), P(g_ab),
+            rc = L.b200ot_sinkhorn_final_bwd_small(P(x), P(y), P(a), P(b), P(f_ba), P(g_ab),
                                                    P(f_aa) if debias else None, P(g_bb) if debias else None, P(lse2),
                                                    P(gos[0]), P(gos[1]), P(gos[2]), P(gos[3]), P(gx), P(gy), B, N, M,
-                                                   D, p, eps, lam, ops._stream(x.device))
+                                                   D, p, eps, lam, 1, ops._stream(x.device))
         _lib.check(rc, "b200ot_sinkhorn_final_bwd_small")
         ops.count_launches(1)
         return (gx, gy) + (None,) * 10
@@ -91,24 +112,12 @@ def sinkhorn_small(a, x, b, y, p=2, blur=0.05, reach=None, diameter=None, scalin
     M = y.shape[1]
     diameter, eps_final, eps_list, rho = scaling_parameters(x, y, p, blur, reach, diameter, scaling)
     pk = (p | ops.P_UNCLAMPED) if keops else p
-    a_log, b_log = log_weights(a.detach()), log_weights(b.detach())
-    xd, yd = x.detach(), y.detach()
-    dev = x.device
-
-    def fresh():
-        return [torch.empty(B, N, device=dev), torch.empty(B, M, device=dev),
-                torch.empty(B, N, device=dev) if debias else None, torch.empty(B, M, device=dev) if debias else None]
-
-    cur, nxt = fresh(), fresh()
+    ad, bd = a.detach(), b.detach()
     with torch.no_grad():
-        eps = eps_list[0]
-        _iteration(xd, yd, a_log, b_log, None, cur, eps, 0.0, damping(eps, rho), pk)
-        for eps in eps_list:
-            lam = damping(eps, rho)
-            _iteration(xd, yd, a_log, b_log, cur, nxt, eps, 0.5, 0.5 * lam, pk)
-            cur, nxt = nxt, cur
-    f_ba, g_ab, f_aa, g_bb = cur
-    outs = _FinalStep.apply(x, y, a_log, b_log, f_ba, g_ab, f_aa, g_bb, eps, lam, pk, debias)
+        f_ba, g_ab, f_aa, g_bb = _descent(x.detach(), y.detach(), ad, bd, eps_list, rho, pk, debias)
+    eps = eps_list[-1]
+    lam = damping(eps, rho)
+    outs = _FinalStep.apply(x, y, ad, bd, f_ba, g_ab, f_aa, g_bb, eps, lam, pk, debias)
     if debias:
         n_f_ba, n_g_ab, n_f_aa, n_g_bb = outs
     else:

@@ -227,6 +227,7 @@ B200OT_API int b200ot_kernel_conv_bwd_finalize(const float* part, int32_t n_part
  *     f_aa_out <- alpha_old f_aa + beta softmin(eps, (x, x), a_log + f_aa/eps)      (B,N)   (debiasing; nullable pair)
  *     g_bb_out <- alpha_old g_bb + beta softmin(eps, (y, y), b_log + g_bb/eps)      (B,M)
  * all four reading the OLD potentials (f_ba .. g_bb all null: h = log-weights, the initialisation; alpha_old = 0).
+ * a_log / b_log are natural-log weights, or the weights themselves when weights_linear = 1.
  * Outputs must not alias inputs.  lse2_out (nullable): B*(2N+2M) floats [f_ba | g_ab | f_aa | g_bb], the log2-domain
  * log-sum-exp of every row, consumed by b200ot_sinkhorn_final_bwd_small:
  *     grad_x <- scale_out * ( go_f_ba[i] d softmin_xy / d x_i + go_f_aa[i] d softmin_xx / d x_i )     (B,N,D)
@@ -240,13 +241,24 @@ B200OT_API int b200ot_sinkhorn_iteration_small(const float* x, const float* y, c
                                                const float* g_bb, float* f_ba_out, float* g_ab_out, float* f_aa_out,
                                                float* g_bb_out, float* lse2_out, int64_t B, int64_t N, int64_t M,
                                                int32_t D, int32_t p, float eps, float alpha_old, float beta,
-                                               void* stream);
+                                               int32_t weights_linear, void* stream);
+/* The whole descent in ONE host call: initialisation at eps_list[0] (potentials <- damped softmins of the log-weights)
+ * followed by one averaged symmetric update per temperature of eps_list (host array of n_eps doubles) — n_eps + 1
+ * launches enqueued back to back, no Python / FFI round trip between them.  rho <= 0: balanced (damping 1), else
+ * damping 1/(1 + eps/rho) per temperature (sinkhorn_divergence.py:56-58).  pots_a, pots_b: two scratch sets of
+ * B*(2N+2M) floats [f_ba | g_ab | f_aa | g_bb] used as ping-pong buffers; *result_in_a tells which one holds the final
+ * iterate.  weights_linear = 1: a, b are the weights themselves (log taken in the kernel, -100000 floor for a <= 0). */
+B200OT_API int b200ot_sinkhorn_loop_small(const float* x, const float* y, const float* a, const float* b,
+                                          int32_t weights_linear, const double* eps_list, int32_t n_eps, double rho,
+                                          int32_t debias, float* pots_a, float* pots_b, int32_t* result_in_a,
+                                          int64_t B, int64_t N, int64_t M, int32_t D, int32_t p, void* stream);
 B200OT_API int b200ot_sinkhorn_final_bwd_small(const float* x, const float* y, const float* a_log, const float* b_log,
                                                const float* f_ba, const float* g_ab, const float* f_aa,
                                                const float* g_bb, const float* lse2, const float* go_f_ba,
                                                const float* go_g_ab, const float* go_f_aa, const float* go_g_bb,
                                                float* grad_x, float* grad_y, int64_t B, int64_t N, int64_t M,
-                                               int32_t D, int32_t p, float eps, float scale_out, void* stream);
+                                               int32_t D, int32_t p, float eps, float scale_out,
+                                               int32_t weights_linear, void* stream);
 
 /* Kernel norms on small clouds (same size limits): the matvecs of kernel_loss (kernel_samples.py:116-137) in one launch,
  *     a_x = K(x,x) a   b_y = K(y,y) b   b_x = K(x,y) b   a_y = K(y,x) a  (a_y nullable: only needed for potentials / d/db)

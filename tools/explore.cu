@@ -240,7 +240,7 @@ static void run_variant(const char* name, Problem& P, int reps) {
                                                               scale, C::DIRECT ? 1 : 0, D, C::NF2, P.M, mpad,
                                                               P.cols);
   CK(cudaGetLastError());
-  auto kern = softmin_partial_kernel<C>;
+  auto kern = softmin_partial_kernel<C, false>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::NT + 32, C::SMEM_BYTES));
