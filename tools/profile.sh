@@ -3,7 +3,7 @@
 # exact bench command.  Outputs land in gpurun_out/; tools/ncu_summary.py turns them into profiles/*.
 set -u
 mkdir -p gpurun_out
-BENCH="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
+BENCH="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-secondary"
 # 1. every launch with its device time (cold-cache, serialised: compare SHARES, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
     $BENCH > gpurun_out/launches_bench.log 2>&1
