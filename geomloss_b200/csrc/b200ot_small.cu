@@ -40,6 +40,13 @@ struct SmallProblemSet {
   int nrows[4], ncols[4];
 };
 
+// Scaled coordinates are ROUNDED products (__fmul_rn is never contracted).  With a plain `scale * x` the compiler fuses
+// the row side into the difference, df = fma(x, scale, -Y), while the column side Y = round(scale * y) went through
+// shared memory: a point then sits at distance ~1e-6 (scaled) from ITSELF instead of 0.  Harmless for the values, fatal
+// for the p = 1 gradient in the unclamped (pykeops) convention, where only an exact zero distance has a zero gradient:
+// the self pair — the heaviest weight of the x <-> x problem — contributed a unit vector of rounding noise
+// (found on the B200 by tools/debug_p1.py: gradient off by O(1), value correct to 2e-7).
+//
 // log2-domain log-weight of a column: from a natural-log weight (w_linear = 0), or from the weight itself with the
 // reference's floor log_weights(a)[a <= 0] = -100000 (sinkhorn_divergence.py:61-65) — saves the host four tiny
 // elementwise launches per cloud
@@ -83,7 +90,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
   const int i = min(row0 + lane, nrows - 1);
   float X[D];
 #pragma unroll
-  for (int d = 0; d < D; ++d) X[d] = scale * rows[(int64_t)i * D + d];
+  for (int d = 0; d < D; ++d) X[d] = __fmul_rn(scale, rows[(int64_t)i * D + d]);  // (never contracted: see scaled_coord)
 
   float m = kNegBig, s = 0.f;
   for (int j0 = 0; j0 < ncols; j0 += kSmallTile) {
@@ -94,7 +101,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
       if (e < nt) {
         const int j = j0 + e;
 #pragma unroll
-        for (int d = 0; d < D; ++d) dst[d] = scale * cols[(int64_t)j * D + d];
+        for (int d = 0; d < D; ++d) dst[d] = __fmul_rn(scale, cols[(int64_t)j * D + d]);
         float h = column_log2_weight(logw[j], w_linear);
         if (pot) h = fmaf(pot[j], inv_eps_log2e, h);
         dst[D] = h;
@@ -170,7 +177,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
   float X[D], G[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    X[d] = scale * rows[(int64_t)i * D + d];
+    X[d] = __fmul_rn(scale, rows[(int64_t)i * D + d]);  // (never contracted: see scaled_coord)
     G[d] = 0.f;
   }
   for (int term = 0; term < n_terms; ++term) {
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
         if (e < nt) {
           const int j = j0 + e;
 #pragma unroll
-          for (int d = 0; d < D; ++d) dst[d] = scale * cols[(int64_t)j * D + d];
+          for (int d = 0; d < D; ++d) dst[d] = __fmul_rn(scale, cols[(int64_t)j * D + d]);
           float h = column_log2_weight(logw[j], w_linear);
           if (pot) h = fmaf(pot[j], inv_eps_log2e, h);
           dst[D] = h;
@@ -361,7 +368,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
   const int i = min(row0 + lane, nrows - 1);
   float X[D];
 #pragma unroll
-  for (int d = 0; d < D; ++d) X[d] = scale * rows[(int64_t)i * D + d];
+  for (int d = 0; d < D; ++d) X[d] = __fmul_rn(scale, rows[(int64_t)i * D + d]);  // (never contracted: see scaled_coord)
   float acc = 0.f;
   for (int j0 = 0; j0 < ncols; j0 += kSmallTile) {
     const int nt = min(kSmallTile, ncols - j0);
@@ -370,7 +377,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
       float* dst = tile + e * W;
       const bool live = e < nt;
 #pragma unroll
-      for (int d = 0; d < D; ++d) dst[d] = live ? scale * cols[(int64_t)(j0 + e) * D + d] : 0.f;
+      for (int d = 0; d < D; ++d) dst[d] = live ? __fmul_rn(scale, cols[(int64_t)(j0 + e) * D + d]) : 0.f;
       dst[D] = live ? wts[j0 + e] : 0.f;
     }
     __syncthreads();
@@ -433,7 +440,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
   float X[D], A[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    X[d] = scale * rows[(int64_t)i * D + d];
+    X[d] = __fmul_rn(scale, rows[(int64_t)i * D + d]);  // (never contracted: see scaled_coord)
     A[d] = 0.f;
   }
   for (int term = 0; term < 2; ++term) {
@@ -450,7 +457,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
         float* dst = tile + e * W;
         const bool live = e < nt;
 #pragma unroll
-        for (int d = 0; d < D; ++d) dst[d] = live ? scale * cols[(int64_t)(j0 + e) * D + d] : 0.f;
+        for (int d = 0; d < D; ++d) dst[d] = live ? __fmul_rn(scale, cols[(int64_t)(j0 + e) * D + d]) : 0.f;
         dst[D] = live ? sign * wts[j0 + e] : 0.f;
       }
       __syncthreads();
