@@ -71,12 +71,23 @@ inline ReducePlan ranges_plan(int variant, int64_t n_seg) {
 // Launch one instantiation of a partial-reduction kernel with its dynamic shared memory opt-in.
 template <class C, class Kern, class... Args>
 inline int launch_reduce(Kern kern, const ReducePlan& pl, cudaStream_t st, Args... args) {
-  // the opt-in is per (kernel, device): set it once per device a process drives, not on every launch
-  static bool attr_done[64] = {};
+  // the opt-in is per (kernel, device): set it once per device a process drives, not on every launch.  The cache is
+  // keyed by the kernel's address — the dense and the ranges instantiation of one Cfg share this function template
+  // instance (same pointer type), not the attribute.
+  static const void* done[64][4] = {};
   int dev = -1;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !attr_done[dev]) {
+  const void* key = reinterpret_cast<const void*>(kern);
+  bool known = false;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64)
+    for (int s = 0; s < 4; ++s) known = known || (done[dev][s] == key);
+  if (!known) {
     B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    if (dev >= 0 && dev < 64)
+      for (int s = 0; s < 4; ++s)
+        if (done[dev][s] == nullptr) {
+          done[dev][s] = key;
+          break;
+        }
   }
   dim3 grid((unsigned)pl.row_tiles, (unsigned)pl.n_split);
   kern<<<grid, C::NT + 32, C::SMEM_BYTES, st>>>(args...);

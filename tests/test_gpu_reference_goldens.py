@@ -229,3 +229,27 @@ def test_grid_softmin_largest_side():
         t = torch.logsumexp(h[0, 0].double()[:, None, :] + k[None, :, :], dim=-1)  # (row j, col i)
         ref = -eps * torch.logsumexp(t[None, :, :] + k[rows][:, :, None], dim=1)  # (rows, col i)
         assert (out[0, 0, rows].cpu().double() - ref).abs().max().item() < 3e-6 * max(1.0, ref.abs().max().item()), n
+
+
+def test_dense_and_ranges_instantiations_alternate():
+    """The dense and the ranges instantiation of ONE kernel configuration are different kernels: each needs its own
+    dynamic-shared-memory opt-in.  (Round 2 regression: the opt-in cache was keyed per configuration, the second kind
+    of launch in a process failed with cudaErrorInvalidValue — bench.py hit it, the test suite's order did not.)"""
+    from geomloss_b200 import ops, ranges
+
+    g = torch.Generator().manual_seed(5)
+    n, m = 4200, 4300
+    x, y, h = torch.rand(n, 3, generator=g).to(DEV), torch.rand(m, 3, generator=g).to(DEV), torch.randn(m, generator=g).to(DEV)
+    rows = torch.tensor([n // 2, n - n // 2], device=DEV)
+    lay = ranges.ColumnLayout(torch.tensor([m // 2, m - m // 2], device=DEV))
+    for variant in (ranges.BIG, ranges.SMALL):
+        prob = ranges.build_problem(None, rows, lay, variant=variant)
+        for _ in range(2):
+            dense, _ = ops.softmin_raw(0.05, x, y, h)
+            sparse, _ = ranges.softmin_ranges_raw(0.05, x, y, h, None, 0.0, prob)
+            # keep = all pairs: the two kernels compute the same softmin
+            assert (dense - sparse).abs().max().item() < 2e-6
+            xg = x.clone().requires_grad_(True)
+            (gd,) = torch.autograd.grad(ops.softmin(0.05, xg, y, h).sum(), xg)
+            (gs,) = torch.autograd.grad(ranges.softmin_ranges(0.05, xg, y, h, None, 0.0, prob).sum(), xg)
+            assert (gd - gs).abs().max().item() < 1e-5 * gd.abs().max().item()
