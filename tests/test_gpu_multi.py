@@ -52,6 +52,25 @@ def _worker(rank, world, port, results):
                             gx=(gx - gxs).abs().max().item() / gxs.abs().max().item(),
                             gy=(gy - gys).abs().max().item() / gys.abs().max().item(),
                             replicated=all(v == vals[0] for v in vals), collectives=eng.collectives)
+        # D = 16: shards go through the tensor-core entries (b200ot_softmin_fwd -> (lse2, 1) partials,
+        # b200ot_softmin_bwd_sums) — ADVICE r01: the staged CUDA-core calls reject D > 8
+        gh = torch.Generator().manual_seed(1)
+        xh, yh = torch.rand(3001, 16, generator=gh).to(dev), torch.rand(2503, 16, generator=gh).to(dev)
+        for tag, loss, kw in (("d16_sinkhorn", "sinkhorn", dict(p=2, blur=0.5, scaling=0.6)),
+                              ("d16_gaussian", "gaussian", dict(blur=1.5))):
+            xs, ys = xh.clone().requires_grad_(True), yh.clone().requires_grad_(True)
+            single = SamplesLoss(loss, **kw)(xs, ys)
+            gxs, gys = torch.autograd.grad(single, [xs, ys])
+            eng = ColumnShardedEngine()
+            xg, yg = xh.clone().requires_grad_(True), yh.clone().requires_grad_(True)
+            val = eng.attach(SamplesLoss(loss, **kw))(xg, yg)
+            gx, gy = torch.autograd.grad(val, [xg, yg])
+            vals = [None] * world
+            dist.all_gather_object(vals, (val.item(), gx.abs().sum().item()))
+            out[tag] = dict(val=val.item(), single=single.item(),
+                            gx=(gx - gxs).abs().max().item() / gxs.abs().max().item(),
+                            gy=(gy - gys).abs().max().item() / gys.abs().max().item(),
+                            replicated=all(v == vals[0] for v in vals), collectives=eng.collectives, tol=2e-5)
         # two-scale Sinkhorn (BASELINE configs[3]): coarse phase replicated, block-sparse fine phase sharded by column tiles
         gm = torch.Generator().manual_seed(3)
         xm = torch.rand(40000, 3, generator=gm).to(dev)
@@ -102,6 +121,6 @@ def test_column_sharded_nccl():
         assert abs(r["val"] - r["single"]) <= r.get("tol", 2e-6) * abs(r["single"]) + 1e-9, r
         # (truncated two-scale runs may keep slightly different tile sets: borderline cluster pairs flip with the
         #  last bits of the atomically accumulated centroids; their weight is ~exp(-truncate))
-        gtol = 1e-3 if tag == "ms_trunc" else 1e-4
+        gtol = 1e-3 if tag in ("ms_trunc", "d16_gaussian") else 1e-4
         assert r["gx"] < gtol and r["gy"] < gtol, r
         assert r["collectives"] > 0
