@@ -1,6 +1,8 @@
 // b200ot — work decomposition shared by every N x M reduction kernel (softmin, its backward,
 // kernel convolutions): which tile shape, how many column splits.
 #pragma once
+#include <stdlib.h>
+
 #include "host_util.cuh"
 
 namespace b200ot {
@@ -44,6 +46,13 @@ inline ReducePlan make_plan(int64_t N, int64_t M, int D = 3) {
   p.row_tiles = ceil_div64(N, p.rows_cta);
   const int64_t target_ctas = (int64_t)num_sms() * 2 * kPlanWaves;
   int64_t want = ceil_div64(target_ctas, p.row_tiles);
+  // test hook (tools/sanitize_smoke.py): force the number of column splits, e.g. 1 to make a small problem re-use
+  // the stages of its TMA ring many times under compute-sanitizer
+  static const int forced = [] {
+    const char* e = getenv("B200OT_FORCE_SPLITS");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced > 0) want = forced;
   if (want < 1) want = 1;
   if (want > 64) want = 64;
   if (want > p.ntiles) want = p.ntiles;

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], NT / 32);
+      mbar_init(&empty[s], NT);  // every consumer THREAD releases the stage itself (see below)
     }
     mbar_fence_init();
   }
@@ -309,8 +309,9 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) s2[r] = __fadd2_rn(s2[r], ts2[r]);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[st]);
+    // release: each thread arrives after ITS OWN last read of the stage (an elected lane behind a __syncwarp() is as
+    // correct, but compute-sanitizer's racecheck does not follow that hand-over and reports the refill as a WAR hazard)
+    mbar_arrive(&empty[st]);
   }
 
 #pragma unroll

@@ -30,6 +30,19 @@ def check(name, got, ref, tol=2e-5):
 
 
 which = set(sys.argv[1:]) or {"softmin", "ranges", "conv", "tc", "grid", "loss"}
+if "ring" in which:
+    # the dense kernels with MANY tiles per CTA (B200OT_FORCE_SPLITS=1 in the environment): every stage of the TMA ring
+    # is refilled a dozen times — the pattern the N = 1e6 runs live in
+    assert __import__("os").environ.get("B200OT_FORCE_SPLITS") == "1", "run with B200OT_FORCE_SPLITS=1"
+    x, y, h = torch.rand(4200, 3, generator=g), torch.rand(40000, 3, generator=g), torch.randn(40000, generator=g)
+    xg = x.to(DEV).requires_grad_(True)
+    out = ops.softmin(0.05, xg, y.to(DEV), h.to(DEV), p=2)
+    check("ring_softmin", out, ref_softmin(0.05, x, y, h, 2))
+    (gx,) = torch.autograd.grad(out.sum(), xg)
+    assert torch.isfinite(gx).all()
+    w = torch.rand(40000, generator=g)
+    conv = ops.kernel_conv("laplacian", xg, y.to(DEV), w.to(DEV), 0.3)
+    assert torch.isfinite(conv).all()
 if "softmin" in which:
     for tag, n, m, d, p in (("big", 4200, 4300, 3, 2), ("small", 300, 500, 2, 1), ("big_p1", 4100, 4100, 1, 1),
                             ("d8", 600, 700, 8, 2)):
