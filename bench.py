@@ -547,6 +547,34 @@ def secondary_configs(torch, dev, world, rank, engine, peaks_file, mufu_peak):
         del a, b, h, pot, res, hh, t2, t1, t0, X, Y, Z
         torch.cuda.empty_cache()
 
+    if world == 1:
+        # ---- small / batched clouds (the regime most users live in): B=64 x N=M=500 and one N=M=1000 problem,
+        #      reference benchmark protocol = forward + backward, wall clock over 20 calls after a warm-up ----
+        small = {}
+        g = torch.Generator().manual_seed(0)
+        for tag, shape in (("B64_N500", (64, 500, 3)), ("N1000", (1000, 3))):
+            xs = torch.rand(*shape, generator=g).to(dev).requires_grad_(True)
+            ys = torch.rand(*shape, generator=g).to(dev)
+            for loss_name, kw in (("sinkhorn", dict(p=2, blur=0.05, diameter=1.8)), ("gaussian", dict(blur=0.1))):
+                Ls = SamplesLoss(loss_name, **kw)
+
+                def call():
+                    v = Ls(xs, ys).sum()
+                    torch.autograd.grad(v, xs)
+                    return v
+
+                call()
+                torch.cuda.synchronize(dev)
+                l0, t0 = ops.launches(), time.perf_counter()
+                for _ in range(20):
+                    call()
+                torch.cuda.synchronize(dev)
+                small[f"{tag}_{loss_name}"] = {"ms_per_call_fwd_bwd": (time.perf_counter() - t0) / 20 * 1e3,
+                                              "b200ot_launches_per_call": (ops.launches() - l0) / 20}
+        small["workload"] = ("SamplesLoss(loss)(x, y) + autograd.grad w.r.t. x, uniform cube, D=3; batched inputs run as ONE "
+                             "launch group per Sinkhorn iteration (csrc/b200ot_small.cu)")
+        out["small_and_batched"] = small
+
     # ---- configs[3]: multiscale Sinkhorn (eps-scaling .5, truncate 5): N=M=1e6 at every --gpus, 1e7 at --gpus 8 ----
     sizes = [1_000_000] + ([10_000_000] if world >= 8 else [])
     ms = {}

@@ -30,6 +30,27 @@ def count_launches(n: int):
     _launches += n
 
 
+# NVTX ranges around every reduction (the reference's only tracing hook is the torch profiler in
+# examples/performances/plot_profile.py).  Off by default; B200OT_NVTX=1 brackets each softmin / kernel matvec so that a
+# timeline (nsys, or ncu --nvtx --nvtx-include) shows the Sinkhorn loop iteration by iteration.
+import os as _os
+
+NVTX = _os.environ.get("B200OT_NVTX", "0") == "1"
+
+
+class nvtx_range:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
+
+
 def launches() -> int:
     return _launches
 
@@ -110,7 +131,7 @@ def softmin_raw(eps, x, y, h_a, h_b=None, h_scale_b=0.0, *, p=2, center=None, ou
         raise ValueError("h must have one entry per column")
     dev = x.device
     L = _lib.lib()
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), nvtx_range(f"b200ot.softmin N={N} M={M} D={D} eps={float(eps):.3g}"):
         if out is None:
             out = torch.empty(N, dtype=torch.float32, device=dev)
         lse2 = torch.empty(N, dtype=torch.float32, device=dev) if want_lse2 else None
@@ -197,7 +218,7 @@ def kernel_conv_raw(kind, x, y, w, blur, *, center=None):
         raise ValueError("w must have one entry per column")
     dev = x.device
     L = _lib.lib()
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), nvtx_range(f"b200ot.kernel_conv kind={kind} N={N} M={M} D={D}"):
         out = torch.empty(N, dtype=torch.float32, device=dev)
         nbytes = L.b200ot_kernel_conv_scratch_bytes(N, M, D)
         scratch = _scratch(nbytes, dev, "conv")
