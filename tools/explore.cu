@@ -385,6 +385,16 @@ int main(int argc, char** argv) {
   const float ctr[16] = {0.5f, 0.5f, 0.5f};
   CK(cudaMemcpy(P.center, ctr, 64, cudaMemcpyHostToDevice));
 
+  // round 2: ring depth / tile width / off-load share around the shipped configuration (per-thread stage release)
+  run_variant<SoftminCfg<3, 2, 2, false, 0x1u, 256, 1024, 4, 8, 3, true>>("r2 stages4", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x1u, 256, 1024, 2, 8, 3, true>>("r2 stages2", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x1u, 256, 512, 4, 8, 3, true>>("r2 tj512 stages4", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x1u, 256, 2048, 2, 8, 3, true>>("r2 tj2048 stages2", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x0u, 256, 1024, 3, 8, 3, true>>("r2 nopoly", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x11u, 256, 1024, 3, 8, 3, true>>("r2 poly2of8", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x1u, 256, 1024, 3, 16, 3, true>>("r2 ch16 poly1of16", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x101u, 256, 1024, 3, 16, 3, true>>("r2 ch16 poly2of16", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x1u, 256, 1024, 3, 8, 3, true>>("r2 shipped", P, reps);
   run_variant<SoftminCfg<3, 4, 2, false, 0u, 256, 1024, 3, 4, 2>>("expand R4 CH4", P, reps);
   run_variant<SoftminCfg<3, 4, 2, false, 0u, 256, 1024, 3, 8, 2>>("expand R4 CH8", P, reps);
   run_variant<SoftminCfg<3, 2, 2, false, 0u, 256, 1024, 3, 8, 2>>("expand R2 CH8", P, reps);
