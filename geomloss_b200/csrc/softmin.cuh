@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
           if constexpr (!C::GUARD) cm[r] = fmax3(cm[r], t.x, t.y);
           const float2 a = __fadd2_rn(t, nm2[r]);
           float2 e;
-          if ((C::PMASK >> c) & 1u) {
+          if (c < 32 && ((C::PMASK >> (c & 31)) & 1u)) {
             e = ex2_poly2(a);
           } else {
             e.x = ex2_approx(a.x);

@@ -395,6 +395,18 @@ int main(int argc, char** argv) {
   run_variant<SoftminCfg<3, 2, 2, false, 0x1u, 256, 1024, 3, 16, 3, true>>("r2 ch16 poly1of16", P, reps);
   run_variant<SoftminCfg<3, 2, 2, false, 0x101u, 256, 1024, 3, 16, 3, true>>("r2 ch16 poly2of16", P, reps);
   run_variant<SoftminCfg<3, 2, 2, false, 0x1u, 256, 1024, 3, 8, 3, true>>("r2 shipped", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x0u, 256, 1024, 3, 16, 3, true>>("r3 ch16 nopoly", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x1u, 256, 1024, 3, 16, 3, true>>("r3 ch16 poly1of16", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x0u, 256, 1024, 3, 32, 3, true>>("r3 ch32 nopoly", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x1u, 256, 1024, 3, 32, 3, true>>("r3 ch32 poly1of32", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x10001u, 256, 1024, 3, 32, 3, true>>("r3 ch32 poly2of32", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x01010101u, 256, 1024, 3, 32, 3, true>>("r3 ch32 poly4of32", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x0u, 256, 1024, 3, 64, 3, true>>("r3 ch64 nopoly", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x1u, 256, 1024, 3, 64, 3, true>>("r3 ch64 poly1of64", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x1u, 256, 1024, 4, 16, 3, true>>("r3 ch16 poly1of16 stages4", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x1u, 256, 2048, 2, 16, 3, true>>("r3 ch16 poly1of16 tj2048", P, reps);
+  run_variant<SoftminCfg<3, 4, 2, false, 0x1u, 256, 1024, 3, 16, 2, true>>("r3 R4 ch16 poly1of16 occ2", P, reps);
+  run_variant<SoftminCfg<3, 2, 2, false, 0x1u, 128, 1024, 3, 16, 6, true>>("r3 NT128 ch16 poly1of16 occ6", P, reps);
   run_variant<SoftminCfg<3, 4, 2, false, 0u, 256, 1024, 3, 4, 2>>("expand R4 CH4", P, reps);
   run_variant<SoftminCfg<3, 4, 2, false, 0u, 256, 1024, 3, 8, 2>>("expand R4 CH8", P, reps);
   run_variant<SoftminCfg<3, 2, 2, false, 0u, 256, 1024, 3, 8, 2>>("expand R2 CH8", P, reps);
