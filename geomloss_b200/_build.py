@@ -37,37 +37,42 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def _compile_one(src: str, obj: str, verbose: bool):
-    cmd = [_nvcc(), "-c", *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, src, "-o", obj]
+def _compile_one(src: str, obj: str, verbose: bool, extra=()):
+    cmd = [_nvcc(), "-c", *NVCC_FLAGS, *extra, "-I", os.path.join(ROOT, "include"), "-I", CSRC, src, "-o", obj]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     return src, res.returncode, res.stdout + res.stderr
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA translation unit (in parallel) and link geomloss_b200/libb200ot.so; returns its path."""
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str | None = None) -> str:
+    """Compile every CUDA translation unit (in parallel) and link geomloss_b200/libb200ot.so; returns its path.
+
+    ``extra_flags`` / ``out`` build a variant library next to the shipped one (``-DB200OT_BIG_CH=8`` ...): the A/B
+    timing harness tools/ab_ops.py loads it through $B200OT_LIB."""
+    variant = out is not None
+    out = out or LIB_PATH
+    if not variant and not force and not _stale():
         return LIB_PATH
     from concurrent.futures import ThreadPoolExecutor
 
-    objdir = os.path.join(ROOT, "build", "obj")
+    objdir = os.path.join(ROOT, "build", "obj_" + os.path.basename(out) if variant else "obj")
     os.makedirs(objdir, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     objs = [os.path.join(objdir, os.path.basename(s)[:-3] + ".o") for s in srcs]
     with ThreadPoolExecutor(max_workers=len(srcs)) as pool:
-        results = list(pool.map(lambda so: _compile_one(so[0], so[1], verbose), zip(srcs, objs)))
+        results = list(pool.map(lambda so: _compile_one(so[0], so[1], verbose, tuple(extra_flags)), zip(srcs, objs)))
     for src, rc, log in results:
         if verbose:
             print(log)
         if rc != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{log}")
-    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *objs, "-o", LIB_PATH + ".tmp"]
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *objs, "-o", out + ".tmp"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
-    return LIB_PATH
+    os.replace(out + ".tmp", out)
+    return out
 
 
 if __name__ == "__main__":

@@ -9,7 +9,8 @@ import os
 from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libb200ot.so")
+# $B200OT_LIB: load a variant build instead (A/B kernel timing, tools/ab_ops.py) — never set in tests or the bench
+LIB_PATH = os.environ.get("B200OT_LIB") or os.path.join(_PKG, "libb200ot.so")
 
 _lib = None
 

@@ -65,23 +65,45 @@ __global__ void softmin_finalize_kernel(const float2* __restrict__ part, int n_p
 // -------------------------------------------------------------------------------------------------
 // dispatch
 // -------------------------------------------------------------------------------------------------
-// Measured on B200 at N = M = 1e6, D = 3 (profiles/r01_explore_*.jsonl): 2 rows/thread, 8-pair chunks,
-// 3 CTAs/SM, sum-guarded lazy max, one column pair in eight on the FMA-pipe exp2 -> 4.22e12 pairs/s
-// (91 % of the MUFU roofline); without the off-load 4.18e12, with the per-pair max tracking 4.0e12.
+// Measured on B200 (profiles/r02_explore_variants.jsonl: N = M = 1e6, D = 3; profiles/r02_ab_ops.jsonl: every D, p at
+// N = M = 4e5): 2 rows/thread, 3 CTAs/SM (2 for D > 4), sum-guarded lazy max.  What matters is the length of the
+// straight-line chunk between two max checks.  D = 3: 8 column pairs 243.4 ms, 16 pairs 232.5 ms (4.30e12 pairs/s,
+// 0.93 of the MUFU roofline), 32 pairs 230.5 ms, 64 pairs 229.7 ms — but on a 125k-column shard (multi-GPU) 16 pairs
+// is the fastest (30.6 / 31.0 / 32.4 ms), so 16 it is.  With 16-pair chunks the FMA-pipe exp2 off-load no longer pays
+// at D = 3, 4 (1 pair in 16: 232.0 ms, 2 in 16: 242.1 ms): the scheduler has enough independent work to keep the MUFU
+// queue full on its own.  Per (D, p), 16- vs 8-pair chunks: p = 1 wins 1-5 % for every D; p = 2 wins 5-8 % at D = 3, 4
+// but LOSES 4-9 % at D = 1, 2 (so little FMA work per pair that the off-load of one pair in eight still pays there)
+// and 3-7 % at D >= 5 (2 CTAs/SM: the longer chunk costs registers the occupancy cannot spare).
+// Ranges mode keeps 8-pair chunks: its pieces must be multiples of 2*CH columns, and 16-slot cluster padding
+// (kRangesAlign) costs less than the longer chunk gains on cluster-sized pieces.
 template <int D, int P, bool DIRECT>
 struct Variants {
-  static constexpr unsigned kPoly = (D <= 4 && P == 2 && !DIRECT) ? 0x01u : 0u;  // FMA pipe has room only there
-  using Big = SoftminCfg<D, kBigR, P, DIRECT, kPoly, kBigNT, kBigTJ, 3, 8, (D <= 4 ? 3 : 2), true>;
+#ifdef B200OT_BIG_CH  // A/B builds (tools/ab_ops.py)
+#ifndef B200OT_BIG_POLY
+#define B200OT_BIG_POLY 0u
+#endif
+  static constexpr int kCH = B200OT_BIG_CH;
+  static constexpr unsigned kPoly = (D <= 4 && P == 2 && !DIRECT) ? B200OT_BIG_POLY : 0u;
+#else
+  static constexpr int kCH = (DIRECT || D == 3 || D == 4) ? 16 : 8;
+  static constexpr unsigned kPoly = (D <= 2 && P == 2 && !DIRECT) ? 0x01u : 0u;
+#endif
+  using Big = SoftminCfg<D, kBigR, P, DIRECT, kPoly, kBigNT, kBigTJ, 3, kCH, (D <= 4 ? 3 : 2), true>;
+  using BigRanges = SoftminCfg<D, kBigR, P, DIRECT, 0u, kBigNT, kBigTJ, 3, 8, (D <= 4 ? 3 : 2), true>;
   using Small = SoftminCfg<D, kSmallR, P, DIRECT, 0u, kSmallNT, kSmallTJ, 3, 4, 4, true>;
+  static_assert(2 * BigRanges::CH <= kRangesAlign && 2 * Small::CH <= kRangesAlign,
+                "ranges pieces are kRangesAlign-aligned");
 };
 
-template <class C>
+template <class C, class CR = C>
 static int launch_partial(const float* x, const float* center, float scale, float clampq, const float* cols,
                           float* part, const ReducePlan& pl, int64_t N, cudaStream_t st, const int4* seg,
                           const int2* pieces) {
+  static_assert(C::SMEM_BYTES == CR::SMEM_BYTES && C::NT == CR::NT && C::ROWS_PER_CTA == CR::ROWS_PER_CTA,
+                "dense and ranges instantiations share one ReducePlan");
   if (seg != nullptr)
-    return launch_reduce<C>(softmin_partial_kernel<C, true>, pl, st, x, center, scale, clampq, cols,
-                            reinterpret_cast<float2*>(part), N, pl.ntiles, pl.tiles_per_split, seg, pieces);
+    return launch_reduce<CR>(softmin_partial_kernel<CR, true>, pl, st, x, center, scale, clampq, cols,
+                             reinterpret_cast<float2*>(part), N, pl.ntiles, pl.tiles_per_split, seg, pieces);
   return launch_reduce<C>(softmin_partial_kernel<C, false>, pl, st, x, center, scale, clampq, cols,
                           reinterpret_cast<float2*>(part), N, pl.ntiles, pl.tiles_per_split, seg, pieces);
 }
@@ -93,11 +115,11 @@ static int partial_for_d(int p, const float* x, const float* center, float scale
   if (p == 2) {
     using V = Variants<D, 2, false>;
     return pl.small ? launch_partial<typename V::Small>(x, center, scale, clampq, cols, part, pl, N, st, seg, pieces)
-                    : launch_partial<typename V::Big>(x, center, scale, clampq, cols, part, pl, N, st, seg, pieces);
+                    : launch_partial<typename V::Big, typename V::BigRanges>(x, center, scale, clampq, cols, part, pl, N, st, seg, pieces);
   } else {
     using V = Variants<D, 1, true>;
     return pl.small ? launch_partial<typename V::Small>(x, center, scale, clampq, cols, part, pl, N, st, seg, pieces)
-                    : launch_partial<typename V::Big>(x, center, scale, clampq, cols, part, pl, N, st, seg, pieces);
+                    : launch_partial<typename V::Big, typename V::BigRanges>(x, center, scale, clampq, cols, part, pl, N, st, seg, pieces);
   }
 }
 

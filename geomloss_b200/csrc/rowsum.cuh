@@ -30,6 +30,12 @@ __host__ __device__ constexpr int mode_nacc(int m, int D) {
              : ((m == kLaplaceBwd || m == kEnergyBwd) ? D : 1);
 }
 
+// column pairs unrolled in the inner loop of rowsum_partial_kernel (A/B builds: tools/ab_ops.py)
+#ifndef B200OT_ROWSUM_UNROLL
+#define B200OT_ROWSUM_UNROLL 2
+#endif
+constexpr int kRowsumUnroll = B200OT_ROWSUM_UNROLL;
+
 template <int MODE_, int D_, int R_, int NT_ = 256, int TJ_ = 1024, int STAGES_ = 3, int MINB_ = 2>
 struct RowSumCfg {
   static constexpr int MODE = MODE_;
@@ -159,7 +165,7 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
 #pragma unroll
       for (int a = 0; a < NACC; ++a) T[r][a] = dup2(0.f);
 
-#pragma unroll 2
+#pragma unroll(kRowsumUnroll)
     for (int jp = 0; jp < npairs; ++jp) {
       float2 S[NF2];
 #pragma unroll
