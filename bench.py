@@ -409,8 +409,8 @@ def run_b200(args):
             "clocks": clocks,
             "roofline": {
                 "bound": "sfu",
-                "kernel": "softmin_partial_kernel (1 exponential per pair: 7 of 8 column pairs on MUFU.EX2, 1 of 8 on "
-                          "the FMA-pipe polynomial; SURVEY.md 8(d): the path is exp-bound, not HBM-bound)",
+                "kernel": "softmin_partial_kernel (1 MUFU.EX2 per pair, 16-pair chunks between running-max checks, no "
+                          "FMA-pipe off-load at D=3; SURVEY.md 8(d): the path is exp-bound, not HBM-bound)",
                 "achieved": k_rate / 1e9, "peak": mufu_peak / 1e9, "unit": "Gexp/s", "frac": k_rate / mufu_peak,
                 "peak_source": "MUFU.EX2 micro-benchmark (b200ot_ubench) run in this process after the timed region",
                 "kernel_ms": kern["ms_per_launch"], "kernel_share_of_step": kern["ms_per_launch"] * 4 / (total_ms / args.steps),
