@@ -103,9 +103,10 @@ static int launch_partial(const float* x, const float* center, float scale, floa
                 "dense and ranges instantiations share one ReducePlan");
   if (seg != nullptr)
     return launch_reduce<CR>(softmin_partial_kernel<CR, true>, pl, st, x, center, scale, clampq, cols,
-                             reinterpret_cast<float2*>(part), N, pl.ntiles, pl.tiles_per_split, seg, pieces);
+                             reinterpret_cast<float2*>(part), N, pl.ntiles, pl.tiles_per_split, 0, seg, pieces);
   return launch_reduce<C>(softmin_partial_kernel<C, false>, pl, st, x, center, scale, clampq, cols,
-                          reinterpret_cast<float2*>(part), N, pl.ntiles, pl.tiles_per_split, seg, pieces);
+                          reinterpret_cast<float2*>(part), N, pl.ntiles, pl.tiles_per_split, pl.last_pairs, seg,
+                          pieces);
 }
 
 template <int D>

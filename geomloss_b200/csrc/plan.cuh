@@ -20,6 +20,7 @@ struct ReducePlan {
   int tj;        // columns per tile
   int rows_cta;  // rows per CTA
   int ntiles;
+  int last_pairs;  // column pairs the consumers visit in the LAST tile (dense mode): M rounded up to kTailAlign, not to tj
   int tiles_per_split;
   int n_split;
   int64_t row_tiles;
@@ -35,6 +36,9 @@ struct ReducePlan {
 // drift out of lock-step within a few waves) and GROWS with it on a 125 000-column shard (4 / 8 / 12 / 16 splits:
 // 32.6 / 34.1 / 35.4 / 36.9 ms): every extra CTA costs its prologue and a cold TMA ring, which is what the 8-GPU
 // shard kernel of round 1 was paying.  A 40-wave plan sized for the wave-quantisation model was tried and reverted.
+// consumers visit whole chunks: 32 columns = 16 column pairs, the longest chunk of any dense instantiation
+constexpr int kTailAlign = 32;
+
 inline ReducePlan make_plan(int64_t N, int64_t M, int D = 3) {
   (void)D;
   ReducePlan p;
@@ -43,6 +47,10 @@ inline ReducePlan make_plan(int64_t N, int64_t M, int D = 3) {
   p.tj = p.small ? kSmallTJ : kBigTJ;
   p.rows_cta = p.small ? kSmallNT * kSmallR : big_rows;
   p.ntiles = (int)(round_up64(M, p.tj) / p.tj);
+  // the packed buffer is padded with neutral columns up to a whole tile and the TMA producer always moves whole tiles,
+  // but the consumers stop at the chunk that holds column M-1: on a 125 000-column shard that is 96 instead of 1024
+  // columns in the 123rd tile (0.7 % of the kernel)
+  p.last_pairs = M > 0 ? (int)(round_up64(M - (int64_t)(p.ntiles - 1) * p.tj, kTailAlign) / 2) : 0;
   p.row_tiles = ceil_div64(N, p.rows_cta);
   const int64_t target_ctas = (int64_t)num_sms() * 2 * kPlanWaves;
   int64_t want = ceil_div64(target_ctas, p.row_tiles);
@@ -71,6 +79,7 @@ inline ReducePlan ranges_plan(int variant, int64_t n_seg) {
   p.tj = p.small ? kSmallTJ : kBigTJ;
   p.rows_cta = p.small ? kSmallNT * kSmallR : kBigNT * kBigR;
   p.ntiles = 0;
+  p.last_pairs = 0;
   p.tiles_per_split = 0;
   p.n_split = 1;
   p.row_tiles = n_seg;

@@ -61,7 +61,7 @@ template <class C, bool RANGES>
 __global__ void __launch_bounds__(C::NT + 32, C::MINB)
     rowsum_partial_kernel(const float* __restrict__ x, const float* __restrict__ center, float scale, float clampq,
                           const float* __restrict__ cols, const float* __restrict__ lse2, float* __restrict__ part,
-                          int64_t N, int ntiles, int tiles_per_split, const int4* __restrict__ seg,
+                          int64_t N, int ntiles, int tiles_per_split, int last_pairs, const int4* __restrict__ seg,
                           const int2* __restrict__ pieces) {
   constexpr int D = C::D, R = C::R, NT = C::NT, NF2 = C::NF2, STAGES = C::STAGES, NACC = C::NACC, MODE = C::MODE;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -150,11 +150,15 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
 #pragma unroll
     for (int a = 0; a < NACC; ++a) A[r][a] = dup2(0.f);
 
-  int np_next = (sparse && nt > 0) ? (pieces[t0].y >> 1) : C::TJ / 2;  // see softmin.cuh
+  int np_next = sparse ? (nt > 0 ? (pieces[t0].y >> 1) : 0) : (t0 + 1 == ntiles ? last_pairs : C::TJ / 2);  // softmin.cuh
   for (int k = 0; k < nt; ++k) {
     const int st = k % STAGES;
     const int npairs = np_next;
-    if (sparse && k + 1 < nt) np_next = pieces[t0 + k + 1].y >> 1;
+    if constexpr (sparse) {
+      if (k + 1 < nt) np_next = pieces[t0 + k + 1].y >> 1;
+    } else {
+      if (t0 + k + 2 == ntiles) np_next = last_pairs;
+    }
     mbar_wait(&full[st], (k / STAGES) & 1);
     const float4* tp = reinterpret_cast<const float4*>(tiles + st * C::TILE_FLOATS);
 

@@ -11,9 +11,9 @@ inline int launch_rowsum_kernel(const ReducePlan& pl, cudaStream_t st, const flo
                                 int64_t N, int ntiles, int tiles_per_split, const int4* seg, const int2* pieces) {
   if (seg != nullptr)
     return launch_reduce<C>(rowsum_partial_kernel<C, true>, pl, st, x, center, scale, clampq, cols, lse2, part, N,
-                            ntiles, tiles_per_split, seg, pieces);
+                            ntiles, tiles_per_split, 0, seg, pieces);
   return launch_reduce<C>(rowsum_partial_kernel<C, false>, pl, st, x, center, scale, clampq, cols, lse2, part, N,
-                          ntiles, tiles_per_split, seg, pieces);
+                          ntiles, tiles_per_split, pl.last_pairs, seg, pieces);
 }
 
 }  // namespace b200ot

@@ -127,7 +127,7 @@ template <class C, bool RANGES>
 __global__ void __launch_bounds__(C::NT + 32, C::MINB)
     softmin_partial_kernel(const float* __restrict__ x, const float* __restrict__ center, float scale,
                            float clampq, const float* __restrict__ cols, float2* __restrict__ part, int64_t N,
-                           int ntiles, int tiles_per_split, const int4* __restrict__ seg,
+                           int ntiles, int tiles_per_split, int last_pairs, const int4* __restrict__ seg,
                            const int2* __restrict__ pieces) {
   constexpr int D = C::D, R = C::R, NT = C::NT, NF2 = C::NF2, CH = C::CH, STAGES = C::STAGES;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
   }
 
   // ranges mode: column pairs of the next piece, fetched one piece ahead (every thread reads the same descriptor word)
-  int np_next = (sparse && nt > 0) ? (pieces[t0].y >> 1) : C::TJ / 2;
+  // (dense mode: whole tiles, except that the last tile of the cloud ends at the chunk holding its last column)
+  int np_next = sparse ? (nt > 0 ? (pieces[t0].y >> 1) : 0) : (t0 + 1 == ntiles ? last_pairs : C::TJ / 2);
 
   // Max pre-pass.  Starting from m = -inf, every chunk in which some row of the warp meets a term 2^64 above its stale
   // max is computed twice, and while the nearest columns of a row are still being discovered that is most chunks: it
@@ -252,7 +253,11 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
   for (int k = 0; k < nt; ++k) {
     const int st = k % STAGES;
     const int npairs = np_next;
-    if (sparse && k + 1 < nt) np_next = pieces[t0 + k + 1].y >> 1;
+    if constexpr (sparse) {
+      if (k + 1 < nt) np_next = pieces[t0 + k + 1].y >> 1;
+    } else {
+      if (t0 + k + 2 == ntiles) np_next = last_pairs;
+    }
     mbar_wait(&full[st], (k / STAGES) & 1);
     const float4* tp = reinterpret_cast<const float4*>(tiles + st * C::TILE_FLOATS);
 

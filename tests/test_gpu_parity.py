@@ -66,7 +66,9 @@ def test_softmin_operator_vs_reference_golden():
 
 @pytest.mark.parametrize("p", [1, 2])
 @pytest.mark.parametrize("shape", [(1, 1, 3), (3, 1, 2), (1, 5, 1), (257, 131, 3), (130, 1025, 2), (2100, 4099, 3),
-                                   (4611, 5003, 3), (700, 300, 5), (300, 4200, 8)])
+                                   (4611, 5003, 3), (700, 300, 5), (300, 4200, 8),
+                                   # last tile of the big shape cut to 1 / 1 / 2 / 32 chunks of 32 columns, and whole
+                                   (4100, 4097, 3), (4100, 4128, 3), (4100, 4129, 3), (4100, 5120, 3), (4100, 6144, 2)])
 def test_softmin_vs_oracle_shapes(p, shape):
     """Ragged sizes around the tile boundaries (2-column packets, 256/1024-column tiles, 128/512-row CTAs),
     both kernel variants (small / big), against the fp64 oracle."""
@@ -253,6 +255,32 @@ def test_kernel_conv_gradients_vs_autograd(kind):
     for got, ref in ((gx, rx), (gy, ry), (gw, rw)):
         ref = ref.numpy()
         np.testing.assert_allclose(got.cpu().numpy(), ref, atol=3e-5 * max(1.0, np.abs(ref).max()))
+
+
+@pytest.mark.parametrize("m", [257, 288, 289, 4097, 4128, 4129, 5120])
+def test_row_reductions_last_tile_lengths(m):
+    """The consumers stop at the 32-column chunk holding the last column (plan.cuh: last_pairs) instead of visiting the
+    neutral padding of the last tile: softmin row gradients and the three kernel products, small and big tile shape,
+    at column counts just before / on / after a chunk and a tile boundary."""
+    from geomloss_b200 import ops
+    from oracle import geomloss_oracle as O
+
+    n = 4100 if m > 4000 else 300
+    g = torch.Generator().manual_seed(m)
+    x, y = torch.rand(n, 3, generator=g), torch.rand(m, 3, generator=g)
+    h = torch.randn(m, generator=g) - np.log(m)
+    w, go = torch.randn(m, generator=g), torch.randn(n, generator=g)
+    c = ops.default_center(x.to(DEV), y.to(DEV))
+    for p in (1, 2):
+        ref = O.softmin_grad_rows(0.02, x.double(), y.double(), h.double(), go.double(), p=p).numpy()
+        xg = x.to(DEV).requires_grad_(True)
+        (gx,) = torch.autograd.grad(ops.softmin(0.02, xg, y.to(DEV), h.to(DEV), p=p, center=c), xg, go.to(DEV))
+        np.testing.assert_allclose(gx.cpu().numpy(), ref, atol=2e-5 * max(1.0, np.abs(ref).max()))
+    for kind in ("gaussian", "laplacian", "energy"):
+        ref = O.kernel_conv_points(kind, x.double(), y.double(), w.double(), 0.1).numpy()
+        out = ops.kernel_conv_raw(kind, x.to(DEV), y.to(DEV), w.to(DEV), 0.1, center=c)
+        np.testing.assert_allclose(out.cpu().numpy(), ref,
+                                   atol=5e-6 * max(1e-3, np.abs(ref).max()) + 2e-7 * w.abs().sum().item())
 
 
 # ------------------------------------------------------------------------------------------------

@@ -232,6 +232,7 @@ static void run_variant(const char* name, Problem& P, int reps) {
   if (want < 1) want = 1;
   if (g_nsplit > 0) want = g_nsplit < ntiles ? g_nsplit : ntiles;
   const int tps = (int)ceil_div64(ntiles, want);
+  const int last_pairs = (int)(round_up64(P.M - (int64_t)(ntiles - 1) * C::TJ, 32) / 2);
   const int nsplit = (int)ceil_div64(ntiles, tps);
   const float scale = p == 2 ? sqrtf(kLog2e / P.eps) : kLog2e / P.eps;
   const float clampq = scale * scale * 1e-8f;
@@ -249,7 +250,7 @@ static void run_variant(const char* name, Problem& P, int reps) {
   dim3 grid((unsigned)row_tiles, (unsigned)nsplit);
   auto launch = [&]() {
     kern<<<grid, C::NT + 32, C::SMEM_BYTES>>>(P.x, P.center, scale, clampq, P.cols, (float2*)P.part, P.N, ntiles,
-                                              tps, (const int4*)nullptr, (const int2*)nullptr);
+                                              tps, last_pairs, (const int4*)nullptr, (const int2*)nullptr);
   };
   const double ms = time_kernel(launch, reps);
   CK(b200ot_softmin_finalize(P.part, nsplit, nullptr, 0.f, 1.f, P.out, P.lse2, P.N, P.eps, nullptr) == 0
