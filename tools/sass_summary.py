@@ -17,8 +17,8 @@ LIB = os.path.join(ROOT, "geomloss_b200", "libb200ot.so")
 KEYS = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "SYNCS", "FFMA2", "FADD2", "FMUL2", "FFMA", "FADD", "MUFU.EX2",
         "MUFU.RSQ", "MUFU.SQRT", "MUFU.LG2", "LDS", "STS", "LDG", "STG", "BAR", "FMNMX", "FMNMX3", "SHFL", "ATOM", "RED"]
 WANT = {
-    "softmin_partial_D3_big": r"softmin_partial_kernel<b200ot::SoftminCfg<3, 2, 2, false, 1u, 256, 1024, 3, 8, 3, true>",
-    "rowsum_softmin_bwd_D3_big": r"rowsum_partial_kernel<b200ot::RowSumCfg<0, 3, 2, 256, 1024, 3, 2>",
+    "softmin_partial_D3_big": r"softmin_partial_kernel<b200ot::SoftminCfg<3, 2, 2, false, 0u, 256, 1024, 3, 16, 3, true>, false>",
+    "rowsum_softmin_bwd_D3_big": r"rowsum_partial_kernel<b200ot::RowSumCfg<0, 3, 2, 256, 1024, 3, 2>, false>",
     "tc_reduce_conv": r"tc_reduce_kernel<b200ot::TcCfg<128, 16>, 0>",
     "tc_reduce_softmin": r"tc_reduce_kernel<b200ot::TcCfg<128, 16>, 1>",
     "tc_bwd_conv": r"tc_bwd_kernel<b200ot::TcCfg<128, 8>, 2>",
