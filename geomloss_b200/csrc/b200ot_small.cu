@@ -37,6 +37,7 @@ struct SmallProblemSet {
   float* lse2[4];         // nullable
   const float* lse2_in[4];   // backward: saved lse2 of the forward final step
   const float* gout[4];      // backward: upstream gradient per row (nullable = zero)
+  const float* go_scale;     // backward: per-batch-element factor on every gout (nullable = 1)
   int nrows[4], ncols[4];
 };
 
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
     const float* __restrict__ logw = S.logw[q] + (int64_t)b * ncols;
     const float* __restrict__ pot = S.pot[q] ? S.pot[q] + (int64_t)b * ncols : nullptr;
     const float lse2 = S.lse2_in[q][(int64_t)b * nrows + i];
-    const float go = go_p[(int64_t)b * nrows + i];
+    const float go = go_p[(int64_t)b * nrows + i] * (S.go_scale ? S.go_scale[b] : 1.0f);
     float A[D];
     float sw = 0.f;
 #pragma unroll
@@ -329,6 +330,151 @@ static void fill_problems(SmallProblemSet& S, const float* x, const float* y, co
     S.lse2_in[q] = nullptr;
     S.gout[q] = nullptr;
   }
+  S.go_scale = nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// sinkhorn_cost on small clouds (sinkhorn_divergence.py:165-255, scal(batch=True) of utils.py:13-18): one block per
+// batch element, fixed-order reduction (bitwise reproducible).
+//   balanced    value = <a, f_ba - f_aa> + <b, g_ab - g_bb>                          (no debias: <a, f_ba> + <b, g_ab>)
+//   unbalanced  value = <a, w (e^{-f_aa/rho} - e^{-f_ba/rho})> + <b, ...>,  w = rho + eps/2   (no debias: w (1 - e^{-f_ba/rho}))
+// Optionally writes d value / d potential (the `go_*` inputs of b200ot_sinkhorn_final_bwd_small) and the per-point
+// terms phi = d value / d a_i, psi = d value / d b_j.
+// ---------------------------------------------------------------------------------------------------------------
+struct SmallCostSet {
+  const float* w[2];     // a (B, N), b (B, M)
+  const float* cross[2]; // f_ba, g_ab
+  const float* self[2];  // f_aa, g_bb (nullable: no debias)
+  float* go_cross[2];    // nullable
+  float* go_self[2];     // nullable
+  float* term[2];        // phi, psi (nullable)
+  float c_cross, c_self; // balanced mode: t = c_cross * cross - c_self * self
+  int n[2];
+};
+
+__global__ void __launch_bounds__(256) sinkhorn_cost_small_kernel(SmallCostSet S, float rho, float wgt,
+                                                                  float* __restrict__ value) {
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  const bool unb = rho > 0.f;
+  const float inv_rho = unb ? 1.0f / rho : 0.f;
+  float acc = 0.f;
+  for (int side = 0; side < 2; ++side) {
+    const int n = S.n[side];
+    const int64_t base = (int64_t)b * n;
+    for (int i = threadIdx.x; i < n; i += 256) {
+      const float w = S.w[side][base + i];
+      const float fc = S.cross[side][base + i];
+      const bool deb = S.self[side] != nullptr;
+      const float fs = deb ? S.self[side][base + i] : 0.f;
+      float t, gc, gs;
+      if (unb) {
+        const float ec = expf(-fc * inv_rho), es = deb ? expf(-fs * inv_rho) : 1.0f;
+        t = wgt * (es - ec);
+        gc = wgt * inv_rho * ec;
+        gs = -wgt * inv_rho * es;
+      } else {
+        t = S.c_cross * fc - S.c_self * fs;
+        gc = S.c_cross;
+        gs = -S.c_self;
+      }
+      acc = fmaf(w, t, acc);
+      if (S.go_cross[side]) S.go_cross[side][base + i] = w * gc;
+      if (deb && S.go_self[side]) S.go_self[side][base + i] = w * gs;
+      if (S.term[side]) S.term[side][base + i] = t;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += red[k];
+    value[b] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bounding box of two clouds (sinkhorn_divergence.py:96-112, max_diameter): lo[D], hi[D] over the rows of x and y in
+// ONE launch (torch: four reductions, two elementwise kernels, a norm).  Blocks publish their partial boxes; the last
+// block to finish folds them.  The ticket counter lives in the caller's scratch (zero before the first use; the last
+// block puts it back to zero), so launches on different scratch buffers never share state.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kExtentBlocks = 64;
+
+__global__ void __launch_bounds__(256) cloud_extent_kernel(const float* __restrict__ x, int64_t n,
+                                                           const float* __restrict__ y, int64_t m, int D,
+                                                           float* __restrict__ partial, unsigned int* ticket,
+                                                           float* __restrict__ out) {
+  __shared__ float slo[8][B200OT_MAX_D], shi[8][B200OT_MAX_D];
+  __shared__ bool last;
+  float lo[B200OT_MAX_D], hi[B200OT_MAX_D];
+  for (int d = 0; d < B200OT_MAX_D; ++d) {
+    lo[d] = INFINITY;
+    hi[d] = -INFINITY;
+  }
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n + m; i += stride) {
+    const float* pnt = i < n ? x + i * D : y + (i - n) * D;
+    for (int d = 0; d < D; ++d) {
+      const float v = pnt[d];
+      lo[d] = fminf(lo[d], v);
+      hi[d] = fmaxf(hi[d], v);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto block_fold = [&]() {
+    for (int d = 0; d < D; ++d) {
+      for (int o = 16; o > 0; o >>= 1) {
+        lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+        hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+      }
+      if (lane == 0) {
+        slo[warp][d] = lo[d];
+        shi[warp][d] = hi[d];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < D) {
+      float a = slo[0][threadIdx.x], c = shi[0][threadIdx.x];
+      for (int w = 1; w < 8; ++w) {
+        a = fminf(a, slo[w][threadIdx.x]);
+        c = fmaxf(c, shi[w][threadIdx.x]);
+      }
+      slo[0][threadIdx.x] = a;
+      shi[0][threadIdx.x] = c;
+    }
+    __syncthreads();
+  };
+  block_fold();
+  if (threadIdx.x < D) {
+    partial[(blockIdx.x * 2 + 0) * B200OT_MAX_D + threadIdx.x] = slo[0][threadIdx.x];
+    partial[(blockIdx.x * 2 + 1) * B200OT_MAX_D + threadIdx.x] = shi[0][threadIdx.x];
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int d = 0; d < B200OT_MAX_D; ++d) {
+    lo[d] = INFINITY;
+    hi[d] = -INFINITY;
+  }
+  for (int k = threadIdx.x; k < (int)gridDim.x; k += 256)
+    for (int d = 0; d < D; ++d) {
+      lo[d] = fminf(lo[d], __ldcg(&partial[(k * 2 + 0) * B200OT_MAX_D + d]));
+      hi[d] = fmaxf(hi[d], __ldcg(&partial[(k * 2 + 1) * B200OT_MAX_D + d]));
+    }
+  __syncthreads();
+  block_fold();
+  if (threadIdx.x < D) {
+    out[threadIdx.x] = slo[0][threadIdx.x];
+    out[D + threadIdx.x] = shi[0][threadIdx.x];
+  }
+  if (threadIdx.x == 0) *ticket = 0;
 }
 
 
@@ -596,7 +742,7 @@ B200OT_API int b200ot_sinkhorn_final_bwd_small(const float* x, const float* y, c
                                                const float* go_g_ab, const float* go_f_aa, const float* go_g_bb,
                                                float* grad_x, float* grad_y, int64_t B, int64_t N, int64_t M,
                                                int32_t D, int32_t p, float eps, float scale_out,
-                                               int32_t weights_linear, void* stream) {
+                                               const float* go_scale, int32_t weights_linear, void* stream) {
   if (!x || !y || !a_log || !b_log || !lse2 || !grad_x || !grad_y || B <= 0 || N <= 0 || M <= 0 || B > 65535 ||
       N > B200OT_SMALL_MAX_POINTS || M > B200OT_SMALL_MAX_POINTS || !supported_simt_dim(D) || !valid_p(p) ||
       !(eps > 0.f))
@@ -609,6 +755,7 @@ B200OT_API int b200ot_sinkhorn_final_bwd_small(const float* x, const float* y, c
     S.gout[q] = go[q];
     S.lse2_in[q] = lse2 + off[q];
   }
+  S.go_scale = go_scale;
   const int n_terms = (go_f_aa || go_g_bb) ? 2 : 1;
   const int pe = p_exponent(p);
   const float scale = softmin_coord_scale(pe, eps);
@@ -620,6 +767,67 @@ B200OT_API int b200ot_sinkhorn_final_bwd_small(const float* x, const float* y, c
   launch_bwd<DD>(pe, S, grid, scale, kLog2e / eps, clampq, scale_out, grad_x, grad_y, n_terms, weights_linear, st)
   B200OT_DISPATCH_D(D, CALL)
 #undef CALL
+}
+
+B200OT_API int b200ot_sinkhorn_cost_small(const float* a, const float* b, const float* f_ba, const float* g_ab,
+                                          const float* f_aa, const float* g_bb, int64_t B, int64_t N, int64_t M,
+                                          float rho, float eps, float* value, float* go_f_ba, float* go_g_ab,
+                                          float* go_f_aa, float* go_g_bb, float* phi, float* psi, void* stream) {
+  if (!a || !b || !f_ba || !g_ab || !value || B <= 0 || N <= 0 || M <= 0 || B > 65535 ||
+      N > B200OT_SMALL_MAX_POINTS || M > B200OT_SMALL_MAX_POINTS || (f_aa == nullptr) != (g_bb == nullptr))
+    return B200OT_EINVAL;
+  SmallCostSet S;
+  S.w[0] = a, S.w[1] = b;
+  S.cross[0] = f_ba, S.cross[1] = g_ab;
+  S.self[0] = f_aa, S.self[1] = g_bb;
+  S.go_cross[0] = go_f_ba, S.go_cross[1] = go_g_ab;
+  S.go_self[0] = go_f_aa, S.go_self[1] = go_g_bb;
+  S.term[0] = phi, S.term[1] = psi;
+  S.c_cross = S.c_self = 1.0f;
+  S.n[0] = (int)N, S.n[1] = (int)M;
+  sinkhorn_cost_small_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(S, rho, rho > 0.f ? rho + 0.5f * eps : 0.f,
+                                                                            value);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  return B200OT_OK;
+}
+
+B200OT_API int b200ot_kernel_mmd_value_small(const float* a, const float* b, const float* a_x, const float* b_y,
+                                             const float* b_x, int64_t B, int64_t N, int64_t M, float* value,
+                                             void* stream) {
+  if (!a || !b || !a_x || !b_y || !b_x || !value || B <= 0 || N <= 0 || M <= 0 || B > 65535 ||
+      N > B200OT_SMALL_MAX_POINTS || M > B200OT_SMALL_MAX_POINTS)
+    return B200OT_EINVAL;
+  // 1/2 <a, a_x> + 1/2 <b, b_y> - <a, b_x>  =  <a, 1/2 a_x - b_x> + <b, 1/2 b_y>: coefficients (1/2, 1), the `self` slot
+  // carries b_x on the a side only
+  SmallCostSet S;
+  S.w[0] = a, S.w[1] = b;
+  S.cross[0] = a_x, S.cross[1] = b_y;
+  S.self[0] = b_x, S.self[1] = nullptr;
+  S.go_cross[0] = S.go_cross[1] = S.go_self[0] = S.go_self[1] = nullptr;
+  S.term[0] = S.term[1] = nullptr;
+  S.c_cross = 0.5f, S.c_self = 1.0f;
+  S.n[0] = (int)N, S.n[1] = (int)M;
+  sinkhorn_cost_small_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(S, -1.0f, 0.f, value);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  return B200OT_OK;
+}
+
+B200OT_API int64_t b200ot_cloud_extent_scratch_bytes(void) {
+  return (int64_t)kExtentBlocks * 2 * B200OT_MAX_D * 4 + 16;
+}
+
+B200OT_API int b200ot_cloud_extent(const float* x, int64_t n, const float* y, int64_t m, int32_t D, float* lo_hi,
+                                   void* scratch, int64_t scratch_bytes, void* stream) {
+  if (!x || !lo_hi || !scratch || n <= 0 || m < 0 || (m > 0 && !y) || D < 1 || D > B200OT_MAX_D ||
+      scratch_bytes < b200ot_cloud_extent_scratch_bytes())
+    return B200OT_EINVAL;
+  int64_t blocks = ceil_div64(n + m, 256 * 8);
+  if (blocks > kExtentBlocks) blocks = kExtentBlocks;
+  float* partial = (float*)scratch;
+  unsigned int* ticket = (unsigned int*)(partial + kExtentBlocks * 2 * B200OT_MAX_D);
+  cloud_extent_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, y, m, D, partial, ticket, lo_hi);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  return B200OT_OK;
 }
 
 B200OT_API int b200ot_sinkhorn_loop_small(const float* x, const float* y, const float* a, const float* b,

@@ -31,8 +31,14 @@ class _MMDValue(torch.autograd.Function):
     def forward(ctx, a, x, b, y, kid, blur):
         need_b = ctx.needs_input_grad[2]
         a_x, b_y, b_x, a_y = _forward(kid, a, x, b, y, blur, want_ay=need_b)
-        B = x.shape[0]
-        val = (0.5 * (a * a_x).view(B, -1).sum(1) + 0.5 * (b * b_y).view(B, -1).sum(1) - (a * b_x).view(B, -1).sum(1))
+        B, N, _ = x.shape
+        val = torch.empty(B, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().b200ot_kernel_mmd_value_small(ops._ptr(a), ops._ptr(b), ops._ptr(a_x), ops._ptr(b_y),
+                                                          ops._ptr(b_x), B, N, y.shape[1], ops._ptr(val),
+                                                          ops._stream(x.device))
+        _lib.check(rc, "b200ot_kernel_mmd_value_small")
+        ops.count_launches(1)
         ctx.save_for_backward(a, x, b, y, a_x, b_y, b_x, a_y if need_b else a_x)
         ctx.meta = (int(kid), float(blur), need_b)
         return val

@@ -104,8 +104,40 @@ def _scratch(nbytes: int, dev, tag: str):
     return buf
 
 
+_extent_scratch: dict = {}
+
+
+def cloud_extent(x, y=None):
+    """(2, D) device tensor [minima; maxima] over the rows of x (and y) in ONE launch (b200ot_cloud_extent), or None
+    when the clouds are not float32 CUDA tensors with D <= MAX_D (callers then use torch reductions)."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and 1 <= x.shape[1] <= MAX_D and x.shape[0] > 0):
+        return None
+    if y is not None and not (y.is_cuda and y.dtype == torch.float32 and y.dim() == 2 and y.shape[1] == x.shape[1]
+                              and y.device == x.device):
+        return None
+    x = x.detach().contiguous()
+    y = None if y is None or y.shape[0] == 0 else y.detach().contiguous()
+    dev = x.device
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+        scratch = _extent_scratch.get(key)
+        if scratch is None:  # zero once: the kernel's ticket counter returns to zero after every launch
+            scratch = _extent_scratch[key] = torch.zeros(L.b200ot_cloud_extent_scratch_bytes(), dtype=torch.uint8,
+                                                         device=dev)
+        out = torch.empty(2, x.shape[1], dtype=torch.float32, device=dev)
+        rc = L.b200ot_cloud_extent(_ptr(x), x.shape[0], _ptr(y), 0 if y is None else y.shape[0], x.shape[1], _ptr(out),
+                                   _ptr(scratch), scratch.numel(), _stream(dev))
+    _lib.check(rc, "b200ot_cloud_extent")
+    count_launches(1)
+    return out
+
+
 def default_center(x, y):
     """Mid-point of the joint bounding box: the origin of the |x|^2 - 2x.y + |y|^2 expansion."""
+    lh = cloud_extent(x, y)
+    if lh is not None:
+        return (0.5 * (lh[0] + lh[1])).contiguous()
     lo = torch.minimum(x.min(0).values, y.min(0).values)
     hi = torch.maximum(x.max(0).values, y.max(0).values)
     return (0.5 * (lo + hi)).float().contiguous()

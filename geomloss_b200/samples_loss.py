@@ -46,6 +46,9 @@ def _route(loss):
     raise KeyError(loss)
 
 
+_uniform_weights: dict = {}
+
+
 class SamplesLoss(Module):
     """Geometric loss between two weighted point clouds (see the module docstring).
 
@@ -193,11 +196,17 @@ class SamplesLoss(Module):
             "A SamplesLoss accepts two (x, y), four (α, x, β, y) or six (l_x, α, x, l_y, β, y)  arguments.")
 
     def generate_weights(self, x):
-        if x.dim() == 2:
-            return torch.ones(x.shape[0]).type_as(x) / x.shape[0]
-        if x.dim() == 3:
-            return torch.ones(x.shape[0], x.shape[1]).type_as(x) / x.shape[1]
-        raise ValueError("Input samples 'x' and 'y' should be encoded as (N,D) or (B,N,D) (batch) tensors.")
+        """Uniform weights 1/N (samples_loss.py:328-335); read-only, so one tensor per (shape, device, dtype) is kept
+        instead of three tiny launches per cloud and call."""
+        if x.dim() not in (2, 3):
+            raise ValueError("Input samples 'x' and 'y' should be encoded as (N,D) or (B,N,D) (batch) tensors.")
+        key = (tuple(x.shape[:-1]), x.device, x.dtype)
+        w = _uniform_weights.get(key)
+        if w is None:
+            if len(_uniform_weights) >= 64:
+                _uniform_weights.clear()
+            w = _uniform_weights[key] = torch.ones(x.shape[:-1]).type_as(x) / x.shape[-2]
+        return w
 
     @staticmethod
     def _check_labels(l, n, which):

@@ -95,10 +95,84 @@ class _FinalStep(torch.autograd.Function):
             rc = L.b200ot_sinkhorn_final_bwd_small(P(x), P(y), P(a), P(b), P(f_ba), P(g_ab),
                                                    P(f_aa) if debias else None, P(g_bb) if debias else None, P(lse2),
                                                    P(gos[0]), P(gos[1]), P(gos[2]), P(gos[3]), P(gx), P(gy), B, N, M,
-                                                   D, p, eps, lam, 1, ops._stream(x.device))
+                                                   D, p, eps, lam, None, 1, ops._stream(x.device))
         _lib.check(rc, "b200ot_sinkhorn_final_bwd_small")
         ops.count_launches(1)
         return (gx, gy) + (None,) * 10
+
+
+class _FinalValue(torch.autograd.Function):
+    """Final update + sinkhorn_cost (sinkhorn_divergence.py:612-623, :165-255) as TWO launches forward and ONE backward:
+    the (B,) loss values come from b200ot_sinkhorn_cost_small, which also leaves d value / d potential for the backward
+    kernel — no elementwise torch kernels, no autograd graph between the potentials and the value."""
+
+    @staticmethod
+    def forward(ctx, x, y, a, b, f_ba, g_ab, f_aa, g_bb, eps, lam, p, debias, rho, eps_final):
+        B, N, D = x.shape
+        M = y.shape[1]
+        dev = x.device
+        tot = B * (2 * N + 2 * M)
+        need_xy = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        need_w = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        # one allocation: new potentials | lse2 | d value / d potential | phi, psi
+        work = torch.empty(3 * tot + B * (N + M), dtype=torch.float32, device=dev)
+        new, lse2, gos, terms = work[:tot], work[tot: 2 * tot], work[2 * tot: 3 * tot], work[3 * tot:]
+        value = torch.empty(B, dtype=torch.float32, device=dev)
+        n_f_ba, n_g_ab, n_f_aa, n_g_bb = _views(new, B, N, M, debias)
+        go_f_ba, go_g_ab, go_f_aa, go_g_bb = _views(gos, B, N, M, debias)
+        ad, bd = a.detach(), b.detach()
+        L = _lib.lib()
+        P = ops._ptr
+        with torch.cuda.device(dev):
+            st = ops._stream(dev)
+            rc = L.b200ot_sinkhorn_iteration_small(P(x), P(y), P(ad), P(bd), P(f_ba), P(g_ab), P(f_aa), P(g_bb),
+                                                   P(n_f_ba), P(n_g_ab), P(n_f_aa), P(n_g_bb),
+                                                   P(lse2) if need_xy else None, B, N, M, D, int(p), float(eps), 0.0,
+                                                   float(lam), 1, st)
+            _lib.check(rc, "b200ot_sinkhorn_iteration_small")
+            rc = L.b200ot_sinkhorn_cost_small(P(ad), P(bd), P(n_f_ba), P(n_g_ab), P(n_f_aa), P(n_g_bb), B, N, M,
+                                              -1.0 if rho is None else float(rho), float(eps_final), P(value),
+                                              P(go_f_ba) if need_xy else None, P(go_g_ab) if need_xy else None,
+                                              P(go_f_aa) if need_xy and debias else None,
+                                              P(go_g_bb) if need_xy and debias else None,
+                                              P(terms[: B * N]) if need_w else None,
+                                              P(terms[B * N:]) if need_w else None, st)
+            _lib.check(rc, "b200ot_sinkhorn_cost_small")
+        ops.count_launches(2)
+        if need_xy or need_w:
+            ctx.save_for_backward(x, y, ad, bd, f_ba, g_ab, f_aa if debias else f_ba, g_bb if debias else g_ab, work)
+            ctx.meta = (float(eps), float(lam), int(p), bool(debias), need_xy, need_w)
+        return value
+
+    @staticmethod
+    def backward(ctx, gv):
+        x, y, a, b, f_ba, g_ab, f_aa, g_bb, work = ctx.saved_tensors
+        eps, lam, p, debias, need_xy, need_w = ctx.meta
+        B, N, D = x.shape
+        M = y.shape[1]
+        tot = B * (2 * N + 2 * M)
+        gv = gv.contiguous().float()
+        gx = gy = ga = gb = None
+        if need_xy:
+            lse2, gos = work[tot: 2 * tot], work[2 * tot: 3 * tot]
+            go_f_ba, go_g_ab, go_f_aa, go_g_bb = _views(gos, B, N, M, debias)
+            gx, gy = torch.empty_like(x), torch.empty_like(y)
+            L = _lib.lib()
+            P = ops._ptr
+            with torch.cuda.device(x.device):
+                rc = L.b200ot_sinkhorn_final_bwd_small(P(x), P(y), P(a), P(b), P(f_ba), P(g_ab),
+                                                       P(f_aa) if debias else None, P(g_bb) if debias else None,
+                                                       P(lse2), P(go_f_ba), P(go_g_ab), P(go_f_aa), P(go_g_bb), P(gx),
+                                                       P(gy), B, N, M, D, p, eps, lam, P(gv), 1, ops._stream(x.device))
+            _lib.check(rc, "b200ot_sinkhorn_final_bwd_small")
+            ops.count_launches(1)
+        if need_w:
+            terms = work[3 * tot:]
+            if ctx.needs_input_grad[2]:
+                ga = terms[: B * N].view(B, N) * gv[:, None]
+            if ctx.needs_input_grad[3]:
+                gb = terms[B * N:].view(B, M) * gv[:, None]
+        return (gx, gy, ga, gb) + (None,) * 10
 
 
 def sinkhorn_small(a, x, b, y, p=2, blur=0.05, reach=None, diameter=None, scaling=0.5, debias=True, potentials=False,
@@ -117,6 +191,8 @@ def sinkhorn_small(a, x, b, y, p=2, blur=0.05, reach=None, diameter=None, scalin
         f_ba, g_ab, f_aa, g_bb = _descent(x.detach(), y.detach(), ad, bd, eps_list, rho, pk, debias)
     eps = eps_list[-1]
     lam = damping(eps, rho)
+    if not potentials:
+        return _FinalValue.apply(x, y, a, b, f_ba, g_ab, f_aa, g_bb, eps, lam, pk, debias, rho, eps_final)
     outs = _FinalStep.apply(x, y, ad, bd, f_ba, g_ab, f_aa, g_bb, eps, lam, pk, debias)
     if debias:
         n_f_ba, n_g_ab, n_f_aa, n_g_bb = outs

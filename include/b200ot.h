@@ -36,7 +36,7 @@ extern "C" {
 #define B200OT_API
 #endif
 
-#define B200OT_VERSION 200 /* 0.2.0 */
+#define B200OT_VERSION 201 /* 0.2.1 */
 #define B200OT_MAX_D 8     /* dimensions served by the CUDA-core (register tile) kernels of this build */
 
 /* error codes */
@@ -258,7 +258,33 @@ B200OT_API int b200ot_sinkhorn_final_bwd_small(const float* x, const float* y, c
                                                const float* go_g_ab, const float* go_f_aa, const float* go_g_bb,
                                                float* grad_x, float* grad_y, int64_t B, int64_t N, int64_t M,
                                                int32_t D, int32_t p, float eps, float scale_out,
-                                               int32_t weights_linear, void* stream);
+                                               const float* go_scale, int32_t weights_linear, void* stream);
+/* go_scale (nullable): (B,) per-problem factor applied to every go_* — the upstream gradient of the B loss values when
+ * go_* hold d value / d potential as written by b200ot_sinkhorn_cost_small.
+ *
+ * sinkhorn_cost (sinkhorn_divergence.py:165-255) of B stacked small problems in one launch, one value per problem:
+ *     rho <= 0 (balanced):  value = <a, f_ba - f_aa> + <b, g_ab - g_bb>
+ *     rho  > 0:             value = <a, w (e^{-f_aa/rho} - e^{-f_ba/rho})> + <b, w (e^{-g_bb/rho} - e^{-g_ab/rho})>,
+ *                           w = rho + eps/2
+ * (f_aa = g_bb = NULL: no debiasing — <a, f_ba> + <b, g_ab>, resp. w (1 - e^{-f/rho}).)  Nullable outputs: go_* =
+ * d value / d potential per point, phi (B,N) / psi (B,M) = d value / d a_i, d value / d b_j. */
+B200OT_API int b200ot_sinkhorn_cost_small(const float* a, const float* b, const float* f_ba, const float* g_ab,
+                                          const float* f_aa, const float* g_bb, int64_t B, int64_t N, int64_t M,
+                                          float rho, float eps, float* value, float* go_f_ba, float* go_g_ab,
+                                          float* go_f_aa, float* go_g_bb, float* phi, float* psi, void* stream);
+
+/* value[b] = 1/2 <a, a_x> + 1/2 <b, b_y> - <a, b_x> (kernel_samples.py:139-146) from the outputs of
+ * b200ot_kernel_mmd_small, one launch, fixed summation order. */
+B200OT_API int b200ot_kernel_mmd_value_small(const float* a, const float* b, const float* a_x, const float* b_y,
+                                             const float* b_x, int64_t B, int64_t N, int64_t M, float* value,
+                                             void* stream);
+
+/* Bounding box of the rows of x:(n,D) and y:(m,D) (m = 0: x alone), D <= B200OT_MAX_D: lo_hi[0..D) = minima,
+ * lo_hi[D..2D) = maxima — the inputs of max_diameter (sinkhorn_divergence.py:96-112) in one launch.  scratch:
+ * b200ot_cloud_extent_scratch_bytes() bytes, ZERO before its first use (the kernel leaves it reusable). */
+B200OT_API int64_t b200ot_cloud_extent_scratch_bytes(void);
+B200OT_API int b200ot_cloud_extent(const float* x, int64_t n, const float* y, int64_t m, int32_t D, float* lo_hi,
+                                   void* scratch, int64_t scratch_bytes, void* stream);
 
 /* Kernel norms on small clouds (same size limits): the matvecs of kernel_loss (kernel_samples.py:116-137) in one launch,
  *     a_x = K(x,x) a   b_y = K(y,y) b   b_x = K(x,y) b   a_y = K(y,x) a  (a_y nullable: only needed for potentials / d/db)

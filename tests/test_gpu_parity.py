@@ -283,6 +283,66 @@ def test_row_reductions_last_tile_lengths(m):
                                    atol=5e-6 * max(1e-3, np.abs(ref).max()) + 2e-7 * w.abs().sum().item())
 
 
+@pytest.mark.parametrize("shape", [(1, 0, 3), (5, 7, 1), (1000, 1300, 3), (70000, 5, 2), (300000, 200000, 8)])
+def test_cloud_extent_vs_torch(shape):
+    """b200ot_cloud_extent (one launch, last-block fold) == torch min / max; repeated calls re-use the ticket scratch."""
+    from geomloss_b200 import ops
+    from geomloss_b200.sinkhorn import max_diameter
+
+    n, m, d = shape
+    g = torch.Generator().manual_seed(n + m)
+    x = (torch.randn(n, d, generator=g) * 3).to(DEV)
+    y = (torch.randn(m, d, generator=g) - 1).to(DEV)
+    for _ in range(3):
+        lh = ops.cloud_extent(x, y if m else None)
+        both = torch.cat([x, y]) if m else x
+        assert torch.equal(lh[0], both.min(0).values) and torch.equal(lh[1], both.max(0).values)
+    if m:
+        ref = (both.max(0).values - both.min(0).values).norm().item()
+        assert abs(max_diameter(x, y) - ref) <= 2e-7 * ref
+        assert torch.equal(ops.default_center(x, y), 0.5 * (both.min(0).values + both.max(0).values))
+
+
+@pytest.mark.parametrize("rho", [None, 0.7])
+@pytest.mark.parametrize("debias", [True, False])
+def test_sinkhorn_cost_small_kernel_vs_torch(rho, debias):
+    """b200ot_sinkhorn_cost_small: values, d value / d potential and d value / d weight against autograd of the host
+    formula (sinkhorn.sinkhorn_cost_batched = sinkhorn_divergence.py:165-255)."""
+    import ctypes
+
+    from geomloss_b200 import _lib, ops
+    from geomloss_b200.sinkhorn import sinkhorn_cost_batched
+
+    B, N, M, eps = 3, 257, 301, 0.01
+    g = torch.Generator().manual_seed(3)
+    a = torch.rand(B, N, generator=g).to(DEV).requires_grad_(True)
+    b = torch.rand(B, M, generator=g).to(DEV).requires_grad_(True)
+    pots = [(torch.randn(B, n, generator=g) * 0.3).to(DEV).requires_grad_(True) for n in (N, M, N, M)]
+    f_ba, g_ab, f_aa, g_bb = pots
+    ref = sinkhorn_cost_batched(eps, rho, a.reshape(-1), b.reshape(-1), f_aa.reshape(-1) if debias else None,
+                                g_bb.reshape(-1) if debias else None, g_ab.reshape(-1), f_ba.reshape(-1), B,
+                                debias=debias)
+    go = torch.tensor([1.0, -2.0, 0.5], device=DEV)
+    used = [a, b, f_ba, g_ab] + ([f_aa, g_bb] if debias else [])
+    grads = torch.autograd.grad(ref, used, go)
+    val = torch.empty(B, device=DEV)
+    outs = [torch.zeros(B, n, device=DEV) for n in (N, M, N, M, N, M)]
+    P = ops._ptr
+    rc = _lib.lib().b200ot_sinkhorn_cost_small(P(a.detach()), P(b.detach()), P(f_ba.detach()), P(g_ab.detach()),
+                                               P(f_aa.detach()) if debias else None,
+                                               P(g_bb.detach()) if debias else None, B, N, M,
+                                               -1.0 if rho is None else rho, eps, P(val), P(outs[0]), P(outs[1]),
+                                               P(outs[2]) if debias else None, P(outs[3]) if debias else None,
+                                               P(outs[4]), P(outs[5]), ctypes.c_void_p(0))
+    assert rc == 0
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(val.cpu().numpy(), ref.detach().cpu().numpy(), rtol=2e-6, atol=1e-6)
+    got = [outs[4], outs[5], outs[0], outs[1]] + ([outs[2], outs[3]] if debias else [])
+    for k, (gt, rf) in enumerate(zip(got, grads)):
+        np.testing.assert_allclose((gt * go[:, None]).cpu().numpy(), rf.cpu().numpy(), rtol=3e-6, atol=1e-6,
+                                   err_msg=f"output {k}")
+
+
 # ------------------------------------------------------------------------------------------------
 # SamplesLoss vs the reference's golden outputs
 # ------------------------------------------------------------------------------------------------
