@@ -23,8 +23,16 @@
 namespace b200ot {
 
 constexpr int kSmallRows = 32;   // rows per CTA (one per lane)
-constexpr int kSmallWarps = 4;   // warps per CTA: each reduces a quarter of every column tile
-constexpr int kSmallTile = 256;  // columns staged per step
+#ifndef B200OT_SMALL_WARPS  // A/B builds: tools/ab_small.py
+#define B200OT_SMALL_WARPS 4
+#endif
+#ifndef B200OT_SMALL_TILE
+#define B200OT_SMALL_TILE 256
+#endif
+constexpr int kSmallWarps = B200OT_SMALL_WARPS;  // warps per CTA: each reduces its share of every column tile
+constexpr int kSmallTile = B200OT_SMALL_TILE;    // columns staged per step
+static_assert(kSmallTile % (8 * kSmallWarps) == 0 && kSmallTile % (8 * 8) == 0,
+              "a warp takes whole 8-column chunks of a tile");
 
 struct SmallProblemSet {
   // per problem q in {0: xy -> f_ba, 1: yx -> g_ab, 2: xx -> f_aa, 3: yy -> g_bb}
@@ -70,13 +78,14 @@ __device__ __forceinline__ float pair_exponent_small(const float (&X)[D], const 
 }
 
 // smem column tile layout: [kSmallTile][D + 1] floats, slot D = H (log2-domain additive term)
-template <int D, int P>
-__global__ void __launch_bounds__(kSmallWarps * 32)
+// WARPS: 4, or 8 when the grid underfills the machine (launch_iter)
+template <int D, int P, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
     sinkhorn_iteration_small_kernel(SmallProblemSet S, float scale, float inv_eps_log2e, float clampq,
                                     float alpha_old, float beta_neg_eps_ln2, int w_linear) {
   constexpr int W = D + 1;
   __shared__ float tile[kSmallTile * W];
-  __shared__ float2 red[kSmallWarps][kSmallRows];
+  __shared__ float2 red[WARPS][kSmallRows];
   const int q = blockIdx.y;
   const int b = blockIdx.z;
   const int nrows = S.nrows[q], ncols = S.ncols[q];
@@ -97,7 +106,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
   for (int j0 = 0; j0 < ncols; j0 += kSmallTile) {
     const int nt = min(kSmallTile, ncols - j0);
     __syncthreads();
-    for (int e = threadIdx.x; e < kSmallTile; e += kSmallWarps * 32) {
+    for (int e = threadIdx.x; e < kSmallTile; e += WARPS * 32) {
       float* dst = tile + e * W;
       if (e < nt) {
         const int j = j0 + e;
@@ -114,8 +123,8 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
     }
     __syncthreads();
     // warp w takes columns [w*64, w*64 + 64) of the tile, 8 at a time
-    const int c_begin = warp * (kSmallTile / kSmallWarps);
-    const int c_end = min(c_begin + kSmallTile / kSmallWarps, (nt + 7) & ~7);
+    const int c_begin = warp * (kSmallTile / WARPS);
+    const int c_end = min(c_begin + kSmallTile / WARPS, (nt + 7) & ~7);
     for (int c0 = c_begin; c0 < c_end; c0 += 8) {
       float t[8];
       float cm = kNegBig;
@@ -140,10 +149,10 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
   if (warp == 0 && row0 + lane < nrows) {
     float mm = red[0][lane].x;
 #pragma unroll
-    for (int w = 1; w < kSmallWarps; ++w) mm = fmaxf(mm, red[w][lane].x);
+    for (int w = 1; w < WARPS; ++w) mm = fmaxf(mm, red[w][lane].x);
     float ss = 0.f;
 #pragma unroll
-    for (int w = 0; w < kSmallWarps; ++w) ss += red[w][lane].y * ex2_approx(red[w][lane].x - mm);
+    for (int w = 0; w < WARPS; ++w) ss += red[w][lane].y * ex2_approx(red[w][lane].x - mm);
     int e = 0;
     const float fr = frexpf(ss, &e);
     const float lse2 = ss > 0.f ? (mm + (float)e) + log2f(fr) : -INFINITY;
@@ -271,15 +280,30 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
   }
 }
 
+// Warps per CTA (each reduces its share of every column tile).  Measured on B200 (tools/ab_small.py,
+// profiles/r02_ab_small.jsonl), us per iteration with 4 / 8 warps: one problem of 200 / 1000 / 3000 / 6000 points
+// 8.1/6.3, 14.1/10.2, 36.6/30.9, 101.9/96.2 — the grid (N/32 x 4 CTAs) underfills 148 SMs and the extra warps hide
+// the latency of the tile loads; 64 x 500: 38.8/40.9 and 256 x 100: 14.2/18.2 — thousands of CTAs, the machine is
+// full and the wider CTA only adds barrier and merge cost.
+template <int D, int P>
+static void launch_iter_p(const SmallProblemSet& S, dim3 grid, float scale, float inv_eps_log2e, float clampq,
+                          float alpha_old, float beta_neg_eps_ln2, int w_linear, cudaStream_t st) {
+  const int64_t ctas = (int64_t)grid.x * grid.y * grid.z;
+  if (ctas <= 1024)
+    sinkhorn_iteration_small_kernel<D, P, 8><<<grid, 8 * 32, 0, st>>>(S, scale, inv_eps_log2e, clampq, alpha_old,
+                                                                      beta_neg_eps_ln2, w_linear);
+  else
+    sinkhorn_iteration_small_kernel<D, P, 4><<<grid, 4 * 32, 0, st>>>(S, scale, inv_eps_log2e, clampq, alpha_old,
+                                                                      beta_neg_eps_ln2, w_linear);
+}
+
 template <int D>
 static int launch_iter(int pe, const SmallProblemSet& S, dim3 grid, float scale, float inv_eps_log2e, float clampq,
                        float alpha_old, float beta_neg_eps_ln2, int w_linear, cudaStream_t st) {
   if (pe == 2)
-    sinkhorn_iteration_small_kernel<D, 2><<<grid, kSmallWarps * 32, 0, st>>>(S, scale, inv_eps_log2e, clampq,
-                                                                             alpha_old, beta_neg_eps_ln2, w_linear);
+    launch_iter_p<D, 2>(S, grid, scale, inv_eps_log2e, clampq, alpha_old, beta_neg_eps_ln2, w_linear, st);
   else
-    sinkhorn_iteration_small_kernel<D, 1><<<grid, kSmallWarps * 32, 0, st>>>(S, scale, inv_eps_log2e, clampq,
-                                                                             alpha_old, beta_neg_eps_ln2, w_linear);
+    launch_iter_p<D, 1>(S, grid, scale, inv_eps_log2e, clampq, alpha_old, beta_neg_eps_ln2, w_linear, st);
   B200OT_CUDA_TRY(cudaGetLastError());
   return B200OT_OK;
 }

@@ -24,7 +24,7 @@ WANT = {
     "tc_bwd_conv": r"tc_bwd_kernel<b200ot::TcCfg<128, 8>, 2>",
     "tc_bwd_softmin": r"tc_bwd_kernel<b200ot::TcCfg<128, 8>, 3>",
     "grid_pass_p2": r"grid_pass_kernel<2, 32>",
-    "sinkhorn_iteration_small_D3": r"sinkhorn_iteration_small_kernel<3, 2>",
+    "sinkhorn_iteration_small_D3": r"sinkhorn_iteration_small_kernel<3, 2, 8>",
 }
 
 
