@@ -112,6 +112,17 @@ if "loss" in which:
     v = SamplesLoss("sinkhorn", blur=0.1)(x.requires_grad_(True), y)
     v.sum().backward()
     print("batched sinkhorn", v.tolist())
+    v = SamplesLoss("sinkhorn", blur=0.1, reach=0.5, debias=False)(x.detach().requires_grad_(True), y)
+    v.sum().backward()
+    print("batched unbalanced sinkhorn (small-problem kernels: iteration, cost, backward)", v.tolist())
+    v = SamplesLoss("gaussian", blur=0.1)(x.detach().requires_grad_(True), y)
+    v.sum().backward()
+    print("batched gaussian (fused MMD + value kernel)", v.tolist())
+    big = torch.rand(100000, 3, generator=g).to(DEV)
+    for _ in range(2):  # many CTAs: partial boxes + last-block fold, ticket counter re-used
+        lh = ops.cloud_extent(big, big[:777])
+    assert torch.equal(lh[0], big.min(0).values) and torch.equal(lh[1], big.max(0).values)
+    print("cloud_extent ok")
     v = SamplesLoss("sinkhorn", blur=0.05, backend="multiscale", cluster_scale=0.2, truncate=2)(x[0], y[0])
     print("multiscale sinkhorn", v.item())
     v = SamplesLoss("gaussian", blur=0.1, backend="multiscale", truncate=2)(x[0], y[0])
