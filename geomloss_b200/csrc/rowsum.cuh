@@ -119,15 +119,26 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
   }
 
   const int tid = threadIdx.x - 32;
-  const int64_t row_base = row0 + tid;
+  // local row of slot r: see softmin.cuh (ranges mode: a warp owns R*32 consecutive rows, warps without rows idle)
+  const auto local_row = [&](int r) { return sparse ? (lane + 32 * (R * (tid >> 5) + r)) : (tid + r * NT); };
+  if constexpr (sparse) {
+    if (local_row(0) - lane >= nrows) {
+      for (int k = 0; k < nt; ++k) {
+        const int st = k % STAGES;
+        mbar_wait(&full[st], (k / STAGES) & 1);
+        mbar_arrive(&empty[st]);
+      }
+      return;
+    }
+  }
 
   float2 X[R][D];
   float2 rt2[R];  // per-row additive exponent term, duplicated
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    int64_t i = row_base + (int64_t)r * NT;
+    int64_t i = row0 + local_row(r);
     if constexpr (sparse) {
-      if (tid + r * NT >= nrows) i = row0 + nrows - 1;
+      if (local_row(r) >= nrows) i = row0 + nrows - 1;
     } else {
       if (i >= N) i = N - 1;
     }
@@ -247,8 +258,8 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
 
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const int64_t i = row_base + (int64_t)r * NT;
-    const bool live = sparse ? (tid + r * NT < nrows) : (i < N);
+    const int64_t i = row0 + local_row(r);
+    const bool live = sparse ? (local_row(r) < nrows) : (i < N);
     if (live) {
 #pragma unroll
       for (int a = 0; a < NACC; ++a) part[((int64_t)split * N + i) * NACC + a] = A[r][a].x + A[r][a].y;

@@ -190,15 +190,29 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
 
   // ===== consumers =====
   const int tid = threadIdx.x - 32;
-  const int64_t row_base = row0 + tid;
+  // local row of slot r.  Dense mode: tid + r*NT (all rows live but in the last CTA).  Ranges mode: a warp owns R*32
+  // CONSECUTIVE rows, so a segment of n rows keeps ceil(n / (32 R)) warps busy and the others idle — segments are
+  // whole clusters cut at ROWS_PER_CTA rows, i.e. often a full CTA followed by a sliver, or a small boundary cluster
+  const auto local_row = [&](int r) { return sparse ? (lane + 32 * (R * (tid >> 5) + r)) : (tid + r * NT); };
+  if constexpr (sparse) {
+    if (local_row(0) - lane >= nrows) {
+      // idle warp: no row of the segment — keep the ring's arrival counts in step, compute nothing
+      for (int k = 0; k < nt; ++k) {
+        const int st = k % STAGES;
+        mbar_wait(&full[st], (k / STAGES) & 1);
+        mbar_arrive(&empty[st]);
+      }
+      return;
+    }
+  }
 
   float2 X[R][D];
   float rowc[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    int64_t i = row_base + (int64_t)r * NT;
+    int64_t i = row0 + local_row(r);
     if constexpr (sparse) {
-      if (tid + r * NT >= nrows) i = row0 + nrows - 1;
+      if (local_row(r) >= nrows) i = row0 + nrows - 1;
     } else {
       if (i >= N) i = N - 1;
     }
@@ -345,8 +359,8 @@ __global__ void __launch_bounds__(C::NT + 32, C::MINB)
 
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const int64_t i = row_base + (int64_t)r * NT;
-    const bool live = sparse ? (tid + r * NT < nrows) : (i < N);
+    const int64_t i = row0 + local_row(r);
+    const bool live = sparse ? (local_row(r) < nrows) : (i < N);
     if (live) part[(int64_t)split * N + i] = make_float2(m[r] + rowc[r], s2[r].x + s2[r].y);
   }
 }
