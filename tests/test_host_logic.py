@@ -411,3 +411,20 @@ def test_batch_problem_is_block_diagonal():
     want = torch.block_diag(*[torch.ones(N, M, dtype=torch.int32)] * B)
     assert torch.equal(_pair_mask(prob, B * N, B * M), want)
     assert prob.density == pytest.approx(1.0 / B)
+
+
+def test_uniform_weights_are_cached_per_shape():
+    """generate_weights (samples_loss.py:328-335 in the reference): 1/N per point; the engine keeps one read-only tensor
+    per (shape, device, dtype) instead of rebuilding it on every call."""
+    from geomloss_b200 import SamplesLoss
+
+    L = SamplesLoss("sinkhorn")
+    x = torch.zeros(7, 3)
+    w = L.generate_weights(x)
+    assert w.shape == (7,) and torch.allclose(w, torch.full((7,), 1 / 7)) and not w.requires_grad
+    assert L.generate_weights(torch.ones(7, 2)) is w  # same leading shape, device, dtype
+    wb = L.generate_weights(torch.zeros(4, 5, 3))
+    assert wb.shape == (4, 5) and torch.allclose(wb, torch.full((4, 5), 0.2))
+    assert L.generate_weights(torch.zeros(7, 3, dtype=torch.float64)).dtype == torch.float64
+    with pytest.raises(ValueError):
+        L.generate_weights(torch.zeros(3))
