@@ -9,9 +9,9 @@
 // One pass = one launch of grid_pass_kernel over the tensor viewed as [outer][N][inner]: a CTA loads a
 // tile of 32 lines (all N entries along the axis) into shared memory with coalesced accesses — along the
 // contiguous direction for the strided passes, transposed for the last axis — then every thread owns 8
-// outputs of one line at a time and sweeps the N inputs (conflict-free LDS, lanes = lines): direct
-// differences on the integer grid (exact), lazy-max log-sum-exp in the log2 domain with the same 2^64 sum
-// guard as softmin.cuh, 1 MUFU.EX2 per (output, input) pair.  Results are staged in a second shared tile
+// outputs of one line at a time and sweeps the N inputs (conflict-free LDS, lanes = lines): cost terms from
+// exact integer offsets on the grid (a 14-entry packed table per 8 x 8 chunk), packed fp32 adds, lazy-max
+// log-sum-exp in the log2 domain with the same 2^64 sum guard as softmin.cuh, 1 MUFU.EX2 per (output, input) pair.  Results are staged in a second shared tile
 // and written back with the access pattern of the load, so passes run in place.
 // Work per pass: N^(dim+1) pairs -> SFU-bound like the point-cloud softmin (256^3: 4.3e9 pairs, ~1 ms);
 // HBM traffic 2 x 4 N^dim bytes per pass.
@@ -87,13 +87,19 @@ __global__ void __launch_bounds__(kGridWarps * 32) grid_pass_kernel(GridPassArgs
   __syncthreads();
 
   // ---- sweep: warp g owns outputs [g*per_warp, (g+1)*per_warp) of every line of the tile ----
+  // A thread owns kGridR = 8 consecutive outputs of its line and sweeps the inputs 8 at a time.  The cost term of the
+  // pair (output ib + r, input j0 + c) depends on n = (ib - j0) + (r - c) only: 14 packed table entries
+  //     W[k] = ( -k(n), -k(n - 1) ),  n = (ib - j0) + k,  k = r - 2q in [-6, 7]        k(n) = xs^2 n^2  or  xs |n|
+  // per chunk (n and n^2 are exact small integers in fp32: ONE rounding per entry) serve its 64 pairs, which are then
+  // three packed instructions per two pairs — t = a + W, t - m, sum += 2^(t - m) — instead of four scalar ones per
+  // pair: the loop is bound by the 64 MUFU.EX2, not by issue slots (ncu before: XU 77 %, issue 68 %).
+  const float kq = (P == 2) ? -A.xscale * A.xscale : -A.xscale;
   const int per_warp = (N + kGridWarps * NSUB - 1) / (kGridWarps * NSUB);
   const int i_end = min(N, (warp + 1) * per_warp);
   for (int ib = warp * per_warp; ib < i_end; ib += kGridR) {
-    float xi[kGridR], m[kGridR], s[kGridR];
+    float m[kGridR], s[kGridR];
 #pragma unroll
     for (int r = 0; r < kGridR; ++r) {
-      xi[r] = A.xscale * (float)(ib + r);
       // reference exponent = the j = i term (a lower bound of the row max, usually within a few units of it): a
       // sweep that starts from -big climbs the whole Gaussian flank and re-bases at EVERY chunk left of i
       // (measured: 1.58 XU ops per pair instead of 1)
@@ -101,27 +107,44 @@ __global__ void __launch_bounds__(kGridWarps * 32) grid_pass_kernel(GridPassArgs
       s[r] = 0.f;
     }
     for (int j0 = 0; j0 < N; j0 += 8) {
-      float a[8], xj[8];
+      float2 a2[4];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        a[c] = (j0 + c < N) ? tile[(j0 + c) * kGridRS + lane] : -INFINITY;
-        xj[c] = A.xscale * (float)(j0 + c);
+      for (int q = 0; q < 4; ++q) {
+        a2[q].x = (j0 + 2 * q < N) ? tile[(j0 + 2 * q) * kGridRS + lane] : -INFINITY;
+        a2[q].y = (j0 + 2 * q + 1 < N) ? tile[(j0 + 2 * q + 1) * kGridRS + lane] : -INFINITY;
+      }
+      const float2 base = dup2((float)(ib - j0));
+      float2 W[14];
+#pragma unroll
+      for (int k = -6; k <= 7; ++k) {
+        const float2 n = __fadd2_rn(base, make_float2((float)k, (float)(k - 1)));
+        if (P == 2) {
+          W[k + 6] = __fmul2_rn(__fmul2_rn(n, n), dup2(kq));
+        } else {
+          W[k + 6] = __fmul2_rn(make_float2(fabsf(n.x), fabsf(n.y)), dup2(kq));
+        }
       }
 #pragma unroll
       for (int r = 0; r < kGridR; ++r) {
-        float t[8];
-        float cs = 0.f;
+        const float2 nm = dup2(-m[r]);
+        float2 cs2 = dup2(0.f);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float d = xi[r] - xj[c];
-          t[c] = (P == 2) ? fmaf(-d, d, a[c]) : a[c] - fabsf(d);
-          cs += ex2_approx(t[c] - m[r]);
+        for (int q = 0; q < 4; ++q) {
+          const float2 e = __fadd2_rn(__fadd2_rn(a2[q], W[r - 2 * q + 6]), nm);
+          cs2 = __fadd2_rn(cs2, make_float2(ex2_approx(e.x), ex2_approx(e.y)));
         }
+        float cs = cs2.x + cs2.y;
         if (!(cs <= 1.8446744e19f)) {
           // outdated max (or first chunk): rebase on this chunk's max and redo it
-          float cm = t[0];
+          float t[8];
+          float cm = -INFINITY;
 #pragma unroll
-          for (int c = 1; c < 8; ++c) cm = fmaxf(cm, t[c]);
+          for (int c = 0; c < 8; ++c) {
+            const float n = (float)(ib + r - j0 - c);
+            const float av = (c & 1) ? a2[c >> 1].y : a2[c >> 1].x;
+            t[c] = av + kq * ((P == 2) ? n * n : fabsf(n));
+            cm = fmaxf(cm, t[c]);
+          }
           cs = 0.f;
           if (cm > kNegBig) {  // otherwise every input of the chunk is -inf: nothing to add
             s[r] *= ex2_approx(m[r] - cm);
