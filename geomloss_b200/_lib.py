@@ -54,6 +54,8 @@ _SIGNATURES = {
                                          c_int64, _P]),
     "b200ot_kernel_conv_bwd_x": (c_int32, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int32, c_int32, c_float, _P,
                                            c_int64, _P]),
+    "b200ot_kernel_conv_fwd_bwd_x": (c_int32, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int32, c_int32, c_float,
+                                               _P, c_int64, _P]),
     "b200ot_kernel_conv_pack_gather": (c_int32, [_P, _P, _P, _P, c_int64, c_int32, c_int32, c_float, _P, _P]),
     "b200ot_kernel_conv_partial_ranges": (c_int32, [_P, _P, _P, _P, c_int64, _P, _P, c_int64, c_int32, c_int32,
                                                     c_float, c_int32, c_int32, _P]),

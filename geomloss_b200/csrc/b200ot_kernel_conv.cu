@@ -13,6 +13,9 @@
 #include "tcbwd.cuh"
 #include "tcconv.cuh"
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <type_traits>
 
 namespace b200ot {
@@ -67,15 +70,19 @@ __global__ void conv_fwd_finalize_kernel(const float* __restrict__ part, int n_s
 __global__ void conv_bwd_finalize_kernel(const float* __restrict__ part, int n_split, const float* __restrict__ x,
                                          const float* __restrict__ center, const float* __restrict__ grad_out,
                                          float* __restrict__ grad_x, int64_t N, int D, int kind, float scale,
-                                         float coef, const float* __restrict__ w_absmax) {
+                                         float coef, const float* __restrict__ w_absmax,
+                                         float* __restrict__ value_out = nullptr) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  float go = grad_out[i];
-  if (w_absmax != nullptr && *w_absmax > 0.f) go *= *w_absmax;  // tensor-core path: weights were normalised
+  float go = grad_out ? grad_out[i] : 1.f;  // no upstream gradient: the unit row gradient (value + gradient pass)
+  float wmax = 1.f;
+  if (w_absmax != nullptr && *w_absmax > 0.f) wmax = *w_absmax;  // tensor-core path: weights were normalised
+  go *= wmax;
   if (kind == B200OT_KERNEL_GAUSSIAN) {
     const int na = D + 1;
     float a0 = 0.f;
     for (int s = 0; s < n_split; ++s) a0 += part[((int64_t)s * N + i) * na];
+    if (value_out) value_out[i] = wmax * a0;  // sum_j w_j k_ij: the forward value comes with the gradient sums
     for (int k = 0; k < D; ++k) {
       float a = 0.f;
       for (int s = 0; s < n_split; ++s) a += part[((int64_t)s * N + i) * na + 1 + k];
@@ -174,7 +181,8 @@ static float conv_bwd_coef(int kind_flags, const ConvScales& cs, float blur) {
 constexpr int kTcBN = 128;    // columns per MMA tile
 constexpr int kTcEpi = 16;    // epilogue warps of the forward kernels: 4 per TMEM lane quarter hide the tcgen05.ld latency
 using TcConvCfg = TcCfg<kTcBN, kTcEpi>;
-using TcBwdCfg = TcCfg<kTcBN, 8>;  // (16 epilogue warps measured no faster here: 0.453 s vs 0.441 s on the D=64 MMD)
+using TcBwdCfg = TcCfg<kTcBN, 8>;  // (16 epilogue warps measured no faster with PT = 2: 0.453 s vs 0.441 s on the D=64 MMD)
+using TcBwdCfg16 = TcCfg<kTcBN, 16>;
 
 struct TcPlan {
   int kp, nstage, n_split, tiles_per_split;
@@ -182,7 +190,65 @@ struct TcPlan {
   int64_t off_b, off_part, off_misc, total;
 };
 
-bool tc_supported_dim(int D) { return D > B200OT_MAX_D && D <= 64; }
+// Which path serves an operator.  Above B200OT_MAX_D the tensor-core kernels are the only ones.  At or below it both
+// exist: the CUDA-core kernels are FMA-pipe bound from D = 5 up (softmin forward at N = M = 4e5: 3.0e12 pairs/s at
+// D = 6, 2.0e12 at D = 8; profiles/r02_ab_ops.jsonl) while the tensor-core kernels run the padded dk = 16 problem at
+// the same ~3.7e12 whatever D, so a dimension threshold per operator decides, for problems large enough to fill the
+// 256-row CTAs of the tensor-core grid.  Defaults = the measured cross-over (tools/ab_tc_route.py);
+// $B200OT_TC_MIN_D ("d" or "softmin_fwd,softmin_bwd,conv_fwd,conv_bwd") and $B200OT_TC_MIN_PAIRS override them for
+// A/B timing — read on every call, never set by the tests' default run or the bench.
+static const int kTcMinDimDefault[4] = {9, 9, 9, 9};
+static const double kTcMinPairsDefault = 1.0e9;
+
+bool tc_routed(int op, int D, int64_t N, int64_t M) {
+  if (!tc_capable_dim(D)) return false;
+  if (D > B200OT_MAX_D) return true;
+  int min_dim[4] = {kTcMinDimDefault[0], kTcMinDimDefault[1], kTcMinDimDefault[2], kTcMinDimDefault[3]};
+  double min_pairs = kTcMinPairsDefault;
+  if (const char* e = getenv("B200OT_TC_MIN_D")) {
+    int v[4];
+    const int n = sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]);
+    if (n == 1) {
+      for (int k = 0; k < 4; ++k) min_dim[k] = v[0];
+    } else if (n == 4) {
+      for (int k = 0; k < 4; ++k) min_dim[k] = v[k];
+    }
+  }
+  if (const char* e = getenv("B200OT_TC_MIN_PAIRS")) {
+    const double v = atof(e);
+    if (v >= 0.0) min_pairs = v;
+  }
+  return D >= min_dim[op] && (double)N * (double)M >= min_pairs;
+}
+
+bool tc_any_routed(int D, int64_t N, int64_t M) {
+  for (int op = 0; op < 4; ++op)
+    if (tc_routed(op, D, N, M)) return true;
+  return false;
+}
+
+// Tuning of the row-gradient kernels (tcbwd.cuh): fp16 terms of P in GEMM 2 (PT), epilogue warps, one tcgen05.ld.x64
+// per tile (LDALL), hi.[Y_h | Y_l] as one N = 2 dk instruction (MERGE).  Defaults = the measured best
+// (tools/ab_tc_route.py); $B200OT_TC_BWD ("p_terms,epi,ldall,merge", e.g. "2,8,0,1") overrides them
+// for A/B timing.
+struct TcBwdTuning {
+  int p_terms, epi, ldall, merge;
+};
+static const TcBwdTuning kTcBwdDefault = {2, 8, 0, 0};
+static TcBwdTuning tc_bwd_tuning() {
+  TcBwdTuning t = kTcBwdDefault;
+  if (const char* e = getenv("B200OT_TC_BWD")) {
+    int a, b, c, d;
+    if (sscanf(e, "%d,%d,%d,%d", &a, &b, &c, &d) == 4 && (a == 1 || a == 2) && (b == 8 || b == 16) &&
+        (c == 0 || c == 1) && (d == 0 || d == 1)) {
+      t.p_terms = a;
+      t.epi = b;
+      t.ldall = c;
+      t.merge = d;
+    }
+  }
+  return t;
+}
 
 static TcPlan make_tc_plan(int64_t N, int64_t M, int D, bool bwd = false) {
   TcPlan p;
@@ -244,18 +310,32 @@ int bwd_partial_tc(int kind, const float* x, const float* y, const float* w, con
       y, w, h_a, h_b, h_scale_b, kLog2e, center, scale, M, D, p.kp, kTcBN, 1, b_imgs, nullptr, w_absmax);
   B200OT_CUDA_TRY(cudaGetLastError());
   dim3 grid((unsigned)p.a_tiles, (unsigned)p.n_split);
-  if (kind == 0) {
-    auto kern = tc_bwd_kernel<TcBwdCfg, 2>;
+  const int self_mode = (kind == 0 && x == y && N == M) ? 1 : 0;  // K_xx: exact zero exponent on the diagonal
+  const TcBwdTuning tn = tc_bwd_tuning();
+  auto launch = [&](auto kern, int threads) -> int {
     B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    kern<<<grid, TcBwdCfg::THREADS, (size_t)p.smem, st>>>(a_imgs, b_imgs, part, N, p.kp, (int)p.b_tiles,
-                                                         p.tiles_per_split, p.nstage, D);
-  } else {
-    auto kern = tc_bwd_kernel<TcBwdCfg, 3>;
-    B200OT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    kern<<<grid, TcBwdCfg::THREADS, (size_t)p.smem, st>>>(a_imgs, b_imgs, part, N, p.kp, (int)p.b_tiles,
-                                                         p.tiles_per_split, p.nstage, D);
-  }
-  B200OT_CUDA_TRY(cudaGetLastError());
+    kern<<<grid, threads, (size_t)p.smem, st>>>(a_imgs, b_imgs, part, N, p.kp, (int)p.b_tiles, p.tiles_per_split,
+                                                p.nstage, D, self_mode);
+    B200OT_CUDA_TRY(cudaGetLastError());
+    return B200OT_OK;
+  };
+  // (MODE, PT, epilogue warps, LDALL, MERGE) -> instantiation
+  auto pick3 = [&](auto mode_tag, auto pt_tag, auto merge_tag) -> int {
+    constexpr int MODE = decltype(mode_tag)::value, PT = decltype(pt_tag)::value;
+    constexpr bool MG = decltype(merge_tag)::value;
+    if (tn.epi == 16) return launch(tc_bwd_kernel<TcBwdCfg16, MODE, PT, false, MG>, TcBwdCfg16::THREADS);
+    if (tn.ldall) return launch(tc_bwd_kernel<TcBwdCfg, MODE, PT, true, MG>, TcBwdCfg::THREADS);
+    return launch(tc_bwd_kernel<TcBwdCfg, MODE, PT, false, MG>, TcBwdCfg::THREADS);
+  };
+  auto pick = [&](auto mode_tag) -> int {
+    using T1 = std::integral_constant<int, 1>;
+    using T2 = std::integral_constant<int, 2>;
+    if (tn.merge)
+      return tn.p_terms == 1 ? pick3(mode_tag, T1{}, std::true_type{}) : pick3(mode_tag, T2{}, std::true_type{});
+    return tn.p_terms == 1 ? pick3(mode_tag, T1{}, std::false_type{}) : pick3(mode_tag, T2{}, std::false_type{});
+  };
+  const int rc = (kind == 0) ? pick(std::integral_constant<int, 2>{}) : pick(std::integral_constant<int, 3>{});
+  if (rc) return rc;
   *part_out = part;
   *n_part_out = p.n_split;  // G of a CTA is complete over its column split (both column halves feed one GEMM)
   return B200OT_OK;
@@ -328,11 +408,13 @@ extern "C" {
 
 B200OT_API int64_t b200ot_kernel_conv_scratch_bytes(int64_t N, int64_t M, int32_t D) {
   if (N <= 0 || M <= 0 || D <= 0) return 0;
-  if (tc_supported_dim(D)) return tc_scratch_bytes(N, M, D);
+  if (D > B200OT_MAX_D) return tc_capable_dim(D) ? tc_scratch_bytes(N, M, D) : 0;
   const ReducePlan pl = make_plan(N, M, D);
   const int64_t cols = b200ot_packed_cols_floats(M, D, 2) * 4;
   const int64_t part = (int64_t)pl.n_split * N * 4 * (D + 1);
-  return round_up64(cols, 256) + round_up64(part, 256);
+  const int64_t simt = round_up64(cols, 256) + round_up64(part, 256);
+  // (one size for every operator of the shape: the caller does not say which one it is about to run)
+  return tc_any_routed(D, N, M) ? std::max(simt, tc_scratch_bytes(N, M, D)) : simt;
 }
 
 B200OT_API int b200ot_kernel_conv_finalize(const float* part, int32_t n_part, float* out, int64_t N, int32_t kind,
@@ -391,7 +473,7 @@ B200OT_API int b200ot_kernel_conv_partial_ranges(const float* x, const float* ce
 B200OT_API int b200ot_kernel_conv_fwd(const float* x, const float* y, const float* w, const float* center,
                                       float* out, int64_t N, int64_t M, int32_t D, int32_t kind, float blur,
                                       void* scratch, int64_t scratch_bytes, void* stream) {
-  const bool tc = (kind_base(kind) == B200OT_KERNEL_GAUSSIAN) && tc_supported_dim(D);
+  const bool tc = (kind_base(kind) == B200OT_KERNEL_GAUSSIAN) && tc_routed(kTcConvFwd, D, N, M);
   if (!x || !y || !w || !out || !scratch || N <= 0 || M <= 0 || (!supported_simt_dim(D) && !tc) || !valid_kind(kind))
     return B200OT_EINVAL;
   if (kind_base(kind) != B200OT_KERNEL_ENERGY && !(blur > 0.f)) return B200OT_EINVAL;
@@ -411,13 +493,14 @@ B200OT_API int b200ot_kernel_conv_fwd(const float* x, const float* y, const floa
   return b200ot_kernel_conv_finalize(part, pl.n_split, out, N, kind, stream);
 }
 
-B200OT_API int b200ot_kernel_conv_bwd_x(const float* x, const float* y, const float* w, const float* center,
-                                        const float* grad_out, float* grad_x, int64_t N, int64_t M, int32_t D,
-                                        int32_t kind, float blur, void* scratch, int64_t scratch_bytes,
-                                        void* stream) {
-  const bool tc = (kind_base(kind) == B200OT_KERNEL_GAUSSIAN) && tc_supported_dim(D);
-  if (!x || !y || !w || !grad_out || !grad_x || !scratch || N <= 0 || M <= 0 || (!supported_simt_dim(D) && !tc) ||
-      !valid_kind(kind))
+// Row gradients (and, with value_out, the forward values from the same pass: gaussian only).
+static int conv_bwd_x_impl(const float* x, const float* y, const float* w, const float* center, const float* grad_out,
+                           float* grad_x, float* value_out, int64_t N, int64_t M, int32_t D, int32_t kind, float blur,
+                           void* scratch, int64_t scratch_bytes, void* stream) {
+  const bool gauss = kind_base(kind) == B200OT_KERNEL_GAUSSIAN;
+  const bool tc = gauss && tc_routed(kTcConvBwd, D, N, M);
+  if (!x || !y || !w || !grad_x || !scratch || N <= 0 || M <= 0 || (!supported_simt_dim(D) && !tc) ||
+      !valid_kind(kind) || (value_out && !gauss))
     return B200OT_EINVAL;
   if (kind_base(kind) != B200OT_KERNEL_ENERGY && !(blur > 0.f)) return B200OT_EINVAL;
   if (((uintptr_t)scratch) & 15) return B200OT_EALIGN;
@@ -431,7 +514,8 @@ B200OT_API int b200ot_kernel_conv_bwd_x(const float* x, const float* y, const fl
                                   &tc_part, &n_part, (cudaStream_t)stream, &w_absmax);
     if (rc) return rc;
     conv_bwd_finalize_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, (cudaStream_t)stream>>>(
-        tc_part, n_part, x, center, grad_out, grad_x, N, D, 0, scale, 1.0f / (scale * blur * blur), w_absmax);
+        tc_part, n_part, x, center, grad_out, grad_x, N, D, 0, scale, 1.0f / (scale * blur * blur), w_absmax,
+        value_out);
     B200OT_CUDA_TRY(cudaGetLastError());
     return B200OT_OK;
   }
@@ -445,7 +529,29 @@ B200OT_API int b200ot_kernel_conv_bwd_x(const float* x, const float* y, const fl
   if (rc) return rc;
   rc = conv_partial(kind, true, pl, st, x, center, cs, cols, part, N, D);
   if (rc) return rc;
-  return b200ot_kernel_conv_bwd_finalize(part, pl.n_split, x, center, grad_out, grad_x, N, D, kind, blur, stream);
+  conv_bwd_finalize_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, st>>>(
+      part, pl.n_split, x, center, grad_out, grad_x, N, D, kind_base(kind), cs.scale, conv_bwd_coef(kind, cs, blur),
+      (const float*)nullptr, value_out);
+  B200OT_CUDA_TRY(cudaGetLastError());
+  return B200OT_OK;
+}
+
+B200OT_API int b200ot_kernel_conv_bwd_x(const float* x, const float* y, const float* w, const float* center,
+                                        const float* grad_out, float* grad_x, int64_t N, int64_t M, int32_t D,
+                                        int32_t kind, float blur, void* scratch, int64_t scratch_bytes,
+                                        void* stream) {
+  if (!grad_out) return B200OT_EINVAL;
+  return conv_bwd_x_impl(x, y, w, center, grad_out, grad_x, nullptr, N, M, D, kind, blur, scratch, scratch_bytes,
+                         stream);
+}
+
+B200OT_API int b200ot_kernel_conv_fwd_bwd_x(const float* x, const float* y, const float* w, const float* center,
+                                            float* out, float* grad_unit, int64_t N, int64_t M, int32_t D,
+                                            int32_t kind, float blur, void* scratch, int64_t scratch_bytes,
+                                            void* stream) {
+  if (!out) return B200OT_EINVAL;
+  return conv_bwd_x_impl(x, y, w, center, nullptr, grad_unit, out, N, M, D, kind, blur, scratch, scratch_bytes,
+                         stream);
 }
 
 }  // extern "C"

@@ -177,12 +177,13 @@ B200OT_API int32_t b200ot_softmin_num_splits(int64_t N, int64_t M, int32_t D) {
 
 B200OT_API int64_t b200ot_softmin_scratch_bytes(int64_t N, int64_t M, int32_t D) {
   if (N <= 0 || M <= 0 || D <= 0) return 0;
-  if (tc_supported_dim(D)) return tc_scratch_bytes(N, M, D);
+  if (D > B200OT_MAX_D) return tc_capable_dim(D) ? tc_scratch_bytes(N, M, D) : 0;
   const ReducePlan pl = make_plan(N, M, D);
   const int64_t cols = b200ot_packed_cols_floats(M, D, 1) * 4;
   // forward partials are (m, s) pairs; the backward pass keeps D+1 sums per (split, row)
   const int64_t part = (int64_t)pl.n_split * N * 4 * (D + 1 > 2 ? D + 1 : 2);
-  return round_up64(cols, 256) + round_up64(part, 256);
+  const int64_t simt = round_up64(cols, 256) + round_up64(part, 256);
+  return tc_any_routed(D, N, M) ? (simt > tc_scratch_bytes(N, M, D) ? simt : tc_scratch_bytes(N, M, D)) : simt;
 }
 
 B200OT_API int b200ot_softmin_pack(const float* y, const float* h_a, const float* h_b, float h_scale_b,
@@ -264,7 +265,7 @@ B200OT_API int b200ot_softmin_fwd(const float* x, const float* y, const float* h
                                   float h_scale_b, const float* center, const float* out_old, float alpha_old,
                                   float beta, float* out, float* lse2_out, int64_t N, int64_t M, int32_t D,
                                   int32_t p, float eps, void* scratch, int64_t scratch_bytes, void* stream) {
-  const bool tc = tc_supported_dim(D) && p_exponent(p) == 2;  // 8 < D <= 64: exponent from the tensor cores (tcconv.cuh)
+  const bool tc = p_exponent(p) == 2 && tc_routed(kTcSoftminFwd, D, N, M);  // exponent from the tensor cores (tcconv.cuh)
   if (!x || !y || !h_a || !scratch || N <= 0 || M <= 0 || (!supported_simt_dim(D) && !tc) || !valid_p(p) ||
       !(eps > 0.f) || (!out && !lse2_out))
     return B200OT_EINVAL;

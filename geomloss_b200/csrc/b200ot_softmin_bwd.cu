@@ -141,7 +141,7 @@ B200OT_API int b200ot_softmin_bwd_finalize(const float* part, int32_t n_part, co
                                            const float* grad_out, float* grad_x, int64_t N, int32_t D, int32_t p,
                                            float eps, void* stream) {
   if (!part || n_part <= 0 || !x || !grad_out || !grad_x || N <= 0 ||
-      (!supported_simt_dim(D) && !(tc_supported_dim(D) && p_exponent(p) == 2)) || !valid_p(p) || !(eps > 0.f))
+      (!supported_simt_dim(D) && !(tc_capable_dim(D) && p_exponent(p) == 2)) || !valid_p(p) || !(eps > 0.f))
     return B200OT_EINVAL;
   const int threads = 256;
   softmin_bwd_finalize_kernel<<<(unsigned)ceil_div64(N, threads), threads, 0, (cudaStream_t)stream>>>(
@@ -155,7 +155,7 @@ static int softmin_bwd_partials(const float* x, const float* y, const float* h_a
                                 const float* center, const float* lse2, int64_t N, int64_t M, int32_t D, int32_t p,
                                 float eps, void* scratch, int64_t scratch_bytes, void* stream, float** part_out,
                                 int* n_part_out) {
-  const bool tc = tc_supported_dim(D) && p_exponent(p) == 2;
+  const bool tc = p_exponent(p) == 2 && tc_routed(kTcSoftminBwd, D, N, M);
   if (!x || !y || !h_a || !lse2 || !scratch || N <= 0 || M <= 0 || (!supported_simt_dim(D) && !tc) || !valid_p(p) ||
       !(eps > 0.f))
     return B200OT_EINVAL;

@@ -40,8 +40,13 @@ inline float softmin_coord_scale(int p, float eps) {
 int softmin_pack_impl(const float* y, const float* h_a, const float* h_b, float h_scale_b, const float* center,
                       int64_t M, int D, int p, float eps, float* cols_out, cudaStream_t st, const int* src);
 
-// Tensor-core (tcgen05) path for 8 < D <= 64, defined in b200ot_kernel_conv.cu.
-bool tc_supported_dim(int D);
+// Tensor-core (tcgen05) path, defined in b200ot_kernel_conv.cu.  The kernels serve any 1 <= D <= 64 (coordinates are
+// zero-padded to a multiple of 16); above B200OT_MAX_D they are the only path, at or below it `tc_routed` decides per
+// operator from the measured cross-over (see there).
+enum TcOp { kTcSoftminFwd = 0, kTcSoftminBwd = 1, kTcConvFwd = 2, kTcConvBwd = 3 };
+inline bool tc_capable_dim(int D) { return D >= 1 && D <= 64; }
+bool tc_routed(int op, int D, int64_t N, int64_t M);
+bool tc_any_routed(int D, int64_t N, int64_t M);  // some operator of this shape takes the tensor-core path (scratch sizing)
 int64_t tc_scratch_bytes(int64_t N, int64_t M, int D);
 int softmin_partial_tc(const float* x, const float* y, const float* h_a, const float* h_b, float h_scale_b,
                        const float* center, int64_t N, int64_t M, int D, float eps, void* scratch,

@@ -54,16 +54,33 @@ __host__ __device__ constexpr uint32_t make_idesc_f16_bmn(int M, int N) { return
 
 // MODE 2: gaussian row gradient (P = w_j 2^S), MODE 3: softmin row gradient (P = 2^(S - lse2_i): lse2 rides in the
 // row operand's rank-one chunk).  part[(split*N + row)*(D+1) + {0, 1+k}] = sum_j P_ij {1, Y_jk}
-template <class C, int MODE>
+//
+// PT = fp16 terms of P fed to GEMM 2.  PT = 2: P = hi + lo, products hi.h, hi.l, lo.h (error ~2^-22 |P||Y|).
+// PT = 1: P = hi only, products hi.h, hi.l — a third less GEMM-2 work and no lo split / second tcgen05.st in the
+// epilogue.  Every weight is then perturbed by <= 2^-12 relative (round to nearest, unbiased); the row sum of P is
+// taken over the SAME rounded values, so the gradient (sum_j P_ij Y_j) - X_i (sum_j P_ij) = sum_j hi_ij (Y_j - X_i)
+// stays a combination of exact differences — the perturbation never meets the cancellation between the two sums.
+//
+// MERGE: GEMM 2's hi.h and hi.l products are one N = 2 dk instruction per K step (G occupies 2 dk <= 128 columns,
+// 384..511), the halves are added at read-back: 16 instead of 24 instructions and TMEM reads of P per tile.
+//
+// LDALL (8 epilogue warps: a warp owns 64 columns of a tile): the two 32-column chunks come from one
+// tcgen05.ld.x64 instead of two x32 round trips.
+//
+// self_mode: rows and columns are the same cloud (the K_xx term): the exponent of pair (i, i) is exactly 0, as in
+// tc_reduce_kernel — matters when sum_j P_ij is used as the forward VALUE (b200ot_kernel_conv_fwd_bwd_x).
+template <class C, int MODE, int PT, bool LDALL, bool MERGE>
 __global__ void __launch_bounds__(C::THREADS, 1)
     tc_bwd_kernel(const unsigned char* __restrict__ a_imgs, const unsigned char* __restrict__ b_imgs,
-                  float* __restrict__ part, int64_t N, int kp, int ntiles_b, int tiles_per_split, int NSTAGE, int D) {
+                  float* __restrict__ part, int64_t N, int kp, int ntiles_b, int tiles_per_split, int NSTAGE, int D,
+                  int self_mode) {
+  static_assert(PT == 1 || PT == 2, "P is fed to GEMM 2 as one or two fp16 terms");
   constexpr int BN = C::BN, NEPI = C::NEPI, NACC = 2;
   static_assert(BN == 128 && (NEPI == 8 || NEPI == 16), "layout below assumes 128-column tiles, 8 or 16 epilogue warps");
   constexpr int NH = NEPI / 4;   // warps per TMEM lane quarter = column shares of a tile
   constexpr int CW = BN / NH;    // columns per warp per tile (64 or 32)
   constexpr int A_COL0 = NACC * BN;   // row operand X behind the two S/P buffers
-  constexpr int G_COL0 = 384;         // gradient accumulator (dk <= 64 columns)
+  constexpr int G_COL0 = 384;         // gradient accumulator (dk <= 64 columns; MERGE: 2 dk <= 128)
   extern __shared__ __align__(1024) unsigned char smem[];
   const int a_bytes = kTcM * kp * 2;
   const int dk = tc_dk_of_kp(kp);
@@ -120,6 +137,7 @@ __global__ void __launch_bounds__(C::THREADS, 1)
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_f16(kTcM, BN), idesc_r1 = make_idesc_bf16(kTcM, BN);
       const uint32_t idesc_g = make_idesc_f16_bmn(kTcM, dk);
+      const uint32_t idesc_g2 = make_idesc_f16_bmn(kTcM, 2 * dk);  // MERGE: hi x [Y_h | Y_l]
       const int seg = dk / 8;  // 8-element chunks per split term
       const uint32_t a_tmem = tmem_base + A_COL0, g_tmem = tmem_base + G_COL0;
       mbar_wait(bar_a, 0);
@@ -153,16 +171,36 @@ __global__ void __launch_bounds__(C::THREADS, 1)
           tc_fence_after();
           const uint32_t b_addr = smem_u32(sb + st * b_bytes);
           const uint32_t p_tmem = tmem_base + acc * BN;
-#pragma unroll
-          for (int prod = 0; prod < 3; ++prod) {
-            // (P term, Y term): hi.h, hi.l, lo.h
-            const int tp = (prod == 2) ? 1 : 0, ty = (prod == 1) ? 1 : 0;
+          if constexpr (MERGE) {
+            // the l term of Y follows its h term in the image (8-dim groups 0..seg-1 = h, seg..2 seg-1 = l, one
+            // stride): ONE instruction with N = 2 dk multiplies hi by [Y_h | Y_l] into [G_a | G_b] — the same tensor
+            // work as two N = dk instructions, but P is read from TMEM once instead of twice
 #pragma unroll
             for (int kk = 0; kk < BN / 16; ++kk) {
-              // columns 16kk..16kk+15 of the tile: 32-column chunk kk/2, half kk%2; hi at +0, lo at +16
-              const uint32_t pa = p_tmem + 32 * (kk >> 1) + 8 * (kk & 1) + 16 * tp;
-              const uint64_t db = make_smem_desc(b_addr + ty * seg * (BN * 16) + (2 * kk) * 128, 128, BN * 16);
-              umma_bf16_ts(g_tmem, pa, db, idesc_g, !(j == 0 && prod == 0 && kk == 0));
+              const uint32_t pa = p_tmem + 32 * (kk >> 1) + 8 * (kk & 1);
+              const uint64_t db = make_smem_desc(b_addr + (2 * kk) * 128, 128, BN * 16);
+              umma_bf16_ts(g_tmem, pa, db, idesc_g2, !(j == 0 && kk == 0));
+            }
+            if constexpr (PT == 2) {
+#pragma unroll
+              for (int kk = 0; kk < BN / 16; ++kk) {  // lo . Y_h -> G_a
+                const uint32_t pa = p_tmem + 32 * (kk >> 1) + 8 * (kk & 1) + 16;
+                const uint64_t db = make_smem_desc(b_addr + (2 * kk) * 128, 128, BN * 16);
+                umma_bf16_ts(g_tmem, pa, db, idesc_g, true);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int prod = 0; prod < PT + 1; ++prod) {
+              // (P term, Y term): hi.h, hi.l, lo.h (the last one only when P carries its lo term)
+              const int tp = (prod == 2) ? 1 : 0, ty = (prod == 1) ? 1 : 0;
+#pragma unroll
+              for (int kk = 0; kk < BN / 16; ++kk) {
+                // columns 16kk..16kk+15 of the tile: 32-column chunk kk/2, half kk%2; hi at +0, lo at +16
+                const uint32_t pa = p_tmem + 32 * (kk >> 1) + 8 * (kk & 1) + 16 * tp;
+                const uint64_t db = make_smem_desc(b_addr + ty * seg * (BN * 16) + (2 * kk) * 128, 128, BN * 16);
+                umma_bf16_ts(g_tmem, pa, db, idesc_g, !(j == 0 && prod == 0 && kk == 0));
+              }
             }
           }
           umma_commit(&empty_b[st]);  // the column tile may be overwritten once GEMM 2 has read it
@@ -196,12 +234,23 @@ __global__ void __launch_bounds__(C::THREADS, 1)
       mbar_wait(&s_full[acc], (k / NACC) & 1);
       tc_fence_after();
       const float* wts = reinterpret_cast<const float*>(sb + st * b_bytes + BN * kp * 2);
+      // one 32-column chunk of S -> P, in place; v = the chunk's exponents (registers)
+      auto chunk = [&](float* v, const int col0) {
+        if constexpr (MODE == 2) {
+          if (self_mode) {
+            // warp-uniform: does this 32-column chunk meet the diagonal of this warp's 32 rows?
+            const int64_t gcol0 = (int64_t)(t0 + k) * BN + col0;
+            const int64_t row_lo = (int64_t)row_tile * kTcM + quarter * 32;
+            if (gcol0 < row_lo + 32 && row_lo < gcol0 + 32) {
+              const int diag = (int)(row_lo + lane - gcol0);
 #pragma unroll
-      for (int c0 = 0; c0 < CW; c0 += 32) {
-        const int col0 = half * CW + c0;
-        float v[32];
-        tmem_ld32(lane_base + acc * BN + col0, v);
+              for (int c = 0; c < 32; ++c)
+                if (c == diag) v[c] = 0.f;
+            }
+          }
+        }
         uint32_t ph[16], pl[16];
+        float cs0 = 0.f, cs1 = 0.f;  // per-chunk sums (two-level accumulation, like the forward kernel's per-tile sums)
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
           float p0 = ex2_approx(v[c]), p1 = ex2_approx(v[c + 1]);
@@ -210,15 +259,37 @@ __global__ void __launch_bounds__(C::THREADS, 1)
             p0 *= w.x;
             p1 *= w.y;
           }
-          sum0 += p0;
-          sum1 += p1;
           const uint32_t h = pack_f16x2(p0, p1);
-          const float2 hf = unpack_f16x2(h);
           ph[c / 2] = h;
-          pl[c / 2] = pack_f16x2(p0 - hf.x, p1 - hf.y);
+          if constexpr (PT == 2) {
+            cs0 += p0;
+            cs1 += p1;
+            const float2 hf = unpack_f16x2(h);
+            pl[c / 2] = pack_f16x2(p0 - hf.x, p1 - hf.y);
+          } else {
+            const float2 hf = unpack_f16x2(h);  // the sums see exactly what GEMM 2 sees
+            cs0 += hf.x;
+            cs1 += hf.y;
+          }
         }
+        sum0 += cs0;
+        sum1 += cs1;
         tmem_st16(lane_base + acc * BN + col0, ph);
-        tmem_st16(lane_base + acc * BN + col0 + 16, pl);
+        if constexpr (PT == 2) tmem_st16(lane_base + acc * BN + col0 + 16, pl);
+      };
+      if constexpr (LDALL && CW == 64) {
+        // both chunks of this warp's 64 columns in ONE tcgen05.ld: one TMEM round trip per tile instead of two
+        float vv[64];
+        tmem_ld64(lane_base + acc * BN + half * CW, vv);
+        chunk(&vv[0], half * CW);
+        chunk(&vv[32], half * CW + 32);
+      } else {
+#pragma unroll
+        for (int c0 = 0; c0 < CW; c0 += 32) {
+          float v[32];
+          tmem_ld32(lane_base + acc * BN + half * CW + c0, v);
+          chunk(v, half * CW + c0);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
@@ -233,6 +304,12 @@ __global__ void __launch_bounds__(C::THREADS, 1)
     if (half * 32 < dk) {
       float g[32];
       tmem_ld32(lane_base + G_COL0 + half * 32, g);
+      if constexpr (MERGE) {
+        float gb[32];  // G_b = hi . Y_l lives dk columns further
+        tmem_ld32(lane_base + G_COL0 + dk + half * 32, gb);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) g[c] += gb[c];
+      }
       if (row < N) {
         float* dst = part + ((int64_t)split * N + row) * (D + 1);
         if (half == 0) {

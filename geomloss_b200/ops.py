@@ -281,33 +281,73 @@ def kernel_conv_grad_rows(kind, x, y, w, blur, grad_out, *, center=None):
     return gx
 
 
+def kernel_conv_value_and_grad_rows(kind, x, y, w, blur, *, center=None):
+    """(out, grad_unit) with out_i = sum_j k(x_i, y_j) w_j and grad_unit[i] = sum_j w_j dk(x_i, y_j)/dx_i from ONE
+    pass over the pairs (gaussian kernel; b200ot_kernel_conv_fwd_bwd_x).  No autograd."""
+    x, y, w, center = _f32c(x, "x"), _f32c(y, "y"), _f32c(w, "w"), _f32c(center, "center")
+    if (kind_id(kind) & 0xFF) != 0:
+        raise ValueError("the one-pass value + row gradient exists for the gaussian kernel only")
+    _check_clouds(x, y, MAX_D_TC)
+    N, D = x.shape
+    M = y.shape[0]
+    if w.numel() != M:
+        raise ValueError("w must have one entry per column")
+    dev = x.device
+    L = _lib.lib()
+    with torch.cuda.device(dev), nvtx_range(f"b200ot.kernel_conv value+grad kind={kind} N={N} M={M} D={D}"):
+        out = torch.empty(N, dtype=torch.float32, device=dev)
+        gunit = torch.empty_like(x)
+        nbytes = L.b200ot_kernel_conv_scratch_bytes(N, M, D)
+        scratch = _scratch(nbytes, dev, "conv")
+        rc = L.b200ot_kernel_conv_fwd_bwd_x(_ptr(x), _ptr(y), _ptr(w), _ptr(center), _ptr(out), _ptr(gunit), N, M, D,
+                                            kind_id(kind), float(blur), _ptr(scratch), scratch.numel(), _stream(dev))
+    _lib.check(rc, "b200ot_kernel_conv_fwd_bwd_x")
+    count_launches(3)
+    return out, gunit
+
+
+# A gaussian matvec whose ROW cloud requires a gradient is evaluated by the row-gradient reduction, which accumulates
+# sum_j w_j k_ij next to sum_j w_j k_ij y_j anyway: value and unit gradient come from one pass over the N x M pairs and
+# backward() is an N x D elementwise product — 3 reductions instead of 5 for SamplesLoss("gaussian")(x, y) + grad w.r.t.
+# x.  The price: a forward that is never differentiated pays the (slower) gradient reduction, and (N, D) floats are kept
+# until backward.  B200OT_FUSED_CONV_GRAD=0 restores the two-pass evaluation.
+FUSED_CONV_GRAD = _os.environ.get("B200OT_FUSED_CONV_GRAD", "0") == "1"
+
+
 class _KernelConv(torch.autograd.Function):
     """out = K(x, y) @ w, differentiable w.r.t. x, y and w (kernels are symmetric, so the y- and
     w-gradients are the same reduction with the roles of the clouds swapped)."""
 
     @staticmethod
-    def forward(ctx, x, y, w, kind, blur, center):
-        out = kernel_conv_raw(kind, x, y, w, blur, center=center)
-        ctx.save_for_backward(x, y, w, center if center is not None else w)
-        ctx.meta = (kind, float(blur), center is not None)
+    def forward(ctx, x, y, w, kind, blur, center, fused):
+        if fused:
+            out, gunit = kernel_conv_value_and_grad_rows(kind, x, y, w, blur, center=center)
+        else:
+            out, gunit = kernel_conv_raw(kind, x, y, w, blur, center=center), None
+        ctx.save_for_backward(x, y, w, center if center is not None else w, gunit if fused else w)
+        ctx.meta = (kind, float(blur), center is not None, fused)
         return out
 
     @staticmethod
     def backward(ctx, go):
-        x, y, w, center = ctx.saved_tensors
-        kind, blur, has_center = ctx.meta
+        x, y, w, center, gunit = ctx.saved_tensors
+        kind, blur, has_center, fused = ctx.meta
         center = center if has_center else None
         go = go.contiguous()
         gx = gy = gw = None
         if ctx.needs_input_grad[0]:
-            gx = kernel_conv_grad_rows(kind, x, y, w, blur, go, center=center)
+            if fused:
+                gx = go.unsqueeze(1) * gunit
+            else:
+                gx = kernel_conv_grad_rows(kind, x, y, w, blur, go, center=center)
         if ctx.needs_input_grad[1]:
             # d/dy_j sum_i go_i k(x_i, y_j) w_j = w_j * sum_i go_i dk(y_j, x_i)/dy_j
             gy = kernel_conv_grad_rows(kind, y, x, go, blur, w, center=center)
         if ctx.needs_input_grad[2]:
             gw = kernel_conv_raw(kind, y, x, go, blur, center=center)
-        return gx, gy, gw, None, None, None
+        return gx, gy, gw, None, None, None, None
 
 
 def kernel_conv(kind, x, y, w, blur, *, center=None):
-    return _KernelConv.apply(x, y, w, kind, blur, center)
+    fused = (FUSED_CONV_GRAD and torch.is_grad_enabled() and x.requires_grad and (kind_id(kind) & 0xFF) == 0)
+    return _KernelConv.apply(x, y, w, kind, blur, center, bool(fused))

@@ -36,7 +36,7 @@ extern "C" {
 #define B200OT_API
 #endif
 
-#define B200OT_VERSION 201 /* 0.2.1 */
+#define B200OT_VERSION 202 /* 0.2.2 */
 #define B200OT_MAX_D 8     /* dimensions served by the CUDA-core (register tile) kernels of this build */
 
 /* error codes */
@@ -184,8 +184,10 @@ B200OT_API int b200ot_softmin_bwd_finalize(const float* part, int32_t n_part, co
 /* ---------------------------------------------------------------------------------------------
  * Kernel convolution  —  out_i = sum_j k(x_i, y_j) * w_j      (kernel_samples.py:128-137)
  * ------------------------------------------------------------------------------------------- */
-/* Gaussian forward additionally accepts 8 < D <= 64: that range runs on the tensor cores (tcgen05, bf16x3
- * split operands, exponent accumulated in TMEM); other kinds / the gradients are limited to D <= B200OT_MAX_D. */
+/* The gaussian kernel (forward and row gradients) additionally accepts 8 < D <= 64: that range runs on the tensor
+ * cores (tcgen05, fp16x2 split operands, exponent accumulated in TMEM); laplacian / energy are limited to
+ * D <= B200OT_MAX_D.  For D <= B200OT_MAX_D the library picks the faster of the two paths per operator and problem
+ * size (csrc/b200ot_kernel_conv.cu: tc_routed); results agree to the tolerances of DESIGN.md section 4 either way. */
 B200OT_API int64_t b200ot_kernel_conv_scratch_bytes(int64_t N, int64_t M, int32_t D);
 
 B200OT_API int b200ot_kernel_conv_fwd(const float* x, const float* y, const float* w, const float* center, float* out,
@@ -196,6 +198,16 @@ B200OT_API int b200ot_kernel_conv_fwd(const float* x, const float* y, const floa
 B200OT_API int b200ot_kernel_conv_bwd_x(const float* x, const float* y, const float* w, const float* center,
                              const float* grad_out, float* grad_x, int64_t N, int64_t M, int32_t D, int32_t kind,
                              float blur, void* scratch, int64_t scratch_bytes, void* stream);
+
+/* Value AND unit row gradient from ONE pass over the N x M pairs (gaussian only; EINVAL otherwise):
+ *   out[i] = sum_j k(x_i, y_j) w_j,    grad_unit[i,:] = sum_j w_j * d k(x_i, y_j) / d x_i
+ * i.e. b200ot_kernel_conv_fwd and b200ot_kernel_conv_bwd_x(grad_out = 1) together: the row-gradient reduction
+ * accumulates sum_j w_j k_ij anyway, so a caller that will differentiate (autograd of kernel_loss's matvecs,
+ * kernel_samples.py:116-137) saves the separate forward reduction and multiplies grad_unit by its upstream gradient
+ * row by row.  Same scratch size as the other two. */
+B200OT_API int b200ot_kernel_conv_fwd_bwd_x(const float* x, const float* y, const float* w, const float* center,
+                                 float* out, float* grad_unit, int64_t N, int64_t M, int32_t D, int32_t kind,
+                                 float blur, void* scratch, int64_t scratch_bytes, void* stream);
 
 /* --- stages of the CUDA-core kernel convolutions (D <= B200OT_MAX_D), ranges mode: truncated block-sparse
  *     MMDs (kernel_multiscale, kernel_samples.py:177-271) and batched problems.  cols: gather-packed,

@@ -31,7 +31,7 @@ def test_every_declared_symbol_is_exported(L):
 
 
 def test_version_and_strerror(L):
-    assert L.b200ot_version() == 201
+    assert L.b200ot_version() == 202
     assert L.b200ot_strerror(0) == b"ok"
     assert b"invalid" in L.b200ot_strerror(-1)
     assert b"scratch" in L.b200ot_strerror(-2)
