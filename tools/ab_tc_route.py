@@ -226,11 +226,29 @@ def part_d(dev, N, reps):
     ops.FUSED_CONV_GRAD = False
 
 
+def part_e(dev, N, dims, reps):
+    """Forward kernels side by side: the softmin epilogue (no column weights: MUFU + FADD) against the gaussian one
+    (weights from shared memory: LDS.128 + MUFU + FFMA) — bounds what folding log2 w_j into the exponent could buy."""
+    g = torch.Generator().manual_seed(3)
+    M = N
+    for D in dims:
+        x = torch.rand(N, D, generator=g).to(dev)
+        y = torch.rand(M, D, generator=g).to(dev)
+        h = (torch.rand(M, generator=g) * 0.1).to(dev)
+        w = (torch.rand(M, generator=g) / M).to(dev)
+        blur = 0.25 * (D / 3.0) ** 0.5
+        center = ops.default_center(x, y)
+        t_s = best_ms(lambda: ops.softmin_raw(blur * blur, x, y, h, p=2, center=center), reps)
+        t_c = best_ms(lambda: ops.kernel_conv_raw("gaussian", x, y, w, blur, center=center), reps)
+        emit(part="E", D=D, N=N, softmin_fwd_ms=round(t_s, 3), conv_fwd_ms=round(t_c, 3),
+             softmin_Tpairs_s=round(N * M / t_s * 1e-9, 3), conv_Tpairs_s=round(N * M / t_c * 1e-9, 3))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true", help="small sizes (functional check of the script)")
     ap.add_argument("--reps", type=int, default=2)
-    ap.add_argument("--parts", default="BCDA")
+    ap.add_argument("--parts", default="BCDEA")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     big = 20000 if args.quick else 400000
@@ -240,8 +258,10 @@ def main():
         part_c(dev, big, (3, 64), args.reps)
     if "D" in args.parts:
         part_d(dev, 50000 if args.quick else 1000000, 1)
+    if "E" in args.parts:
+        part_e(dev, big, (16, 32, 64), args.reps)
     if "A" in args.parts:
-        part_a(dev, [3000] if args.quick else [10000, 30000, 100000, 400000], (4, 5, 6, 7, 8), args.reps)
+        part_a(dev, [3000] if args.quick else [30000, 100000, 400000], (4, 5, 6, 7, 8), args.reps)
 
 
 if __name__ == "__main__":
