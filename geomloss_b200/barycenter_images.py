@@ -11,8 +11,10 @@ input here with a closed-form backward that is ITSELF two grid softmins (no N^2 
     out_i = -eps log sum_j exp(h_j - C_ij/eps)    =>    d<go, out>/dh_j = -eps e^{h_j} sum_i (go_i e^{out_i/eps}) e^{-C_ij/eps}
 
 and the symmetric kernel sum on the right is ``exp(-softmin_grid(log(go^+-) + out/eps)/eps)`` for the positive and
-negative parts of ``go``.  Parity: unpinned against the reference (its softmin_grid needs pykeops); tests compare with
-a dense CPU restatement (oracle.images_barycenter) incl. autograd gradients.
+negative parts of ``go``.  Parity: pinned — tests/golden/img_bary_*.npz hold the outputs (and autograd gradients
+w.r.t. weights and measures) of the unmodified reference run on tests/golden/pykeops_shim
+(tests/golden/make_golden_images.py); tests/test_gpu_reference_goldens.py::test_images_barycenter_vs_reference checks
+the CUDA path against them, the oracle's dense restatement (oracle.images_barycenter) is pinned to the same files.
 """
 from __future__ import annotations
 
