@@ -481,7 +481,13 @@ def secondary_configs(torch, dev, world, rank, engine, peaks_file, mufu_peak):
 
         t_fb, _ = _ev_time(torch, dev, fwd_bwd, reps=2)
         fwd_rate = 3.0 * N * N / t_fwd          # K_xx a, K_yy b, K_xy b
-        bwd_rate = 2.0 * N * N / (t_fb - t_fwd)  # row gradients of the xx and xy terms
+        one_pass = bool(ops.FUSED_CONV_GRAD)
+        if one_pass:
+            # the two matvecs whose rows need a gradient come out of the row-gradient reduction itself (value + unit
+            # gradient in one pass, ops._KernelConv): forward + backward = 1 plain reduction (K_yy b) + 2 such passes
+            bwd_rate = 2.0 * N * N / (t_fb - t_fwd / 3.0)
+        else:
+            bwd_rate = 2.0 * N * N / (t_fb - t_fwd)  # row gradients of the xx and xy terms, after a 3-reduction forward
         # spot parity at blur = 2 (at the config's blur = .05 every off-diagonal kernel value underflows in [0,1]^64:
         # SURVEY.md 8(d)); 128 sampled rows of K_xy @ b against fp64 brute force on the device
         w = torch.full((N,), 1.0 / N, device=dev)
@@ -493,6 +499,7 @@ def secondary_configs(torch, dev, world, rank, engine, peaks_file, mufu_peak):
         out["cfg3_gaussian_mmd_D64"] = {
             "workload": "SamplesLoss('gaussian', blur=.05) N=M=1e6 D=64, uniform in [0,1]^64",
             "s_fwd": t_fwd, "s_fwd_bwd": t_fb, "fwd_pairs_per_s": fwd_rate, "bwd_pairs_per_s": bwd_rate,
+            "reductions_fwd_bwd": 3 if one_pass else 5, "one_pass_value_and_gradient": one_pass,
             "sfu_frac_fwd": fwd_rate / mufu_peak, "sfu_frac_bwd": bwd_rate / mufu_peak,
             "tensor_frac_fwd_algorithmic_128_flop_per_pair": fwd_rate * 128 / tensor_peak,
             "tensor_frac_fwd_issued_416_flop_per_pair": fwd_rate * 416 / tensor_peak,

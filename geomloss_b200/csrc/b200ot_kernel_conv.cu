@@ -191,14 +191,21 @@ struct TcPlan {
 };
 
 // Which path serves an operator.  Above B200OT_MAX_D the tensor-core kernels are the only ones.  At or below it both
-// exist: the CUDA-core kernels are FMA-pipe bound from D = 5 up (softmin forward at N = M = 4e5: 3.0e12 pairs/s at
-// D = 6, 2.0e12 at D = 8; profiles/r02_ab_ops.jsonl) while the tensor-core kernels run the padded dk = 16 problem at
-// the same ~3.7e12 whatever D, so a dimension threshold per operator decides, for problems large enough to fill the
-// 256-row CTAs of the tensor-core grid.  Defaults = the measured cross-over (tools/ab_tc_route.py);
-// $B200OT_TC_MIN_D ("d" or "softmin_fwd,softmin_bwd,conv_fwd,conv_bwd") and $B200OT_TC_MIN_PAIRS override them for
-// A/B timing — read on every call, never set by the tests' default run or the bench.
-static const int kTcMinDimDefault[4] = {9, 9, 9, 9};
-static const double kTcMinPairsDefault = 1.0e9;
+// exist: the CUDA-core kernels are FMA-pipe bound from D = 5 up while the tensor-core kernels run the zero-padded
+// dk = 16 problem at the same rate whatever D.  Measured on B200 at N = M = 4e5 (tools/ab_tc_route.py,
+// profiles/r02_ab_tc_route.jsonl; CUDA-core -> tensor-core, 1e12 pairs/s):
+//   softmin forward   D = 5: 3.36 -> 3.38   D = 6: 2.99 -> 3.32   D = 7: 2.69 -> 3.29   D = 8: 2.13 -> 3.26
+//   gaussian forward  D = 4: 3.93 -> 3.58   D = 5: 2.58 -> 3.58   D = 6: 2.27 -> 3.58   D = 8: 1.82 -> 3.58
+//   row gradients     D = 7: 1.60 / 1.48 -> 1.54 / 1.46 (softmin / gaussian); D = 8: 1.33 / 1.36 -> 1.54 / 1.46
+// (the same ratios at N = M = 1e5 and 3e4).  The forward operators switch at D = 6 (softmin) and D = 5 (gaussian).  The
+// row gradients stay on the CUDA cores for every D <= 8: the gain is 8-16 % at D = 8 only, and the fp16 image of P that
+// GEMM 2 consumes costs accuracy at small blur in low dimension (relative difference between the two paths' gradients at
+// blur = .05: 3e-3 at D = 4, 5e-4 at D = 6, 6e-5 at D = 8).  Problems below 8e8 pairs keep the CUDA-core kernels (the
+// cross-over was measured down to N = M = 3e4).  $B200OT_TC_MIN_D ("d" or "softmin_fwd,softmin_bwd,conv_fwd,conv_bwd")
+// and $B200OT_TC_MIN_PAIRS override the defaults for A/B timing and for the parity tests of both routes — read on every
+// call, never set by the bench.
+static const int kTcMinDimDefault[4] = {6, 9, 5, 9};
+static const double kTcMinPairsDefault = 8.0e8;
 
 bool tc_routed(int op, int D, int64_t N, int64_t M) {
   if (!tc_capable_dim(D)) return false;
@@ -228,13 +235,17 @@ bool tc_any_routed(int D, int64_t N, int64_t M) {
 }
 
 // Tuning of the row-gradient kernels (tcbwd.cuh): fp16 terms of P in GEMM 2 (PT), epilogue warps, one tcgen05.ld.x64
-// per tile (LDALL), hi.[Y_h | Y_l] as one N = 2 dk instruction (MERGE).  Defaults = the measured best
-// (tools/ab_tc_route.py); $B200OT_TC_BWD ("p_terms,epi,ldall,merge", e.g. "2,8,0,1") overrides them
-// for A/B timing.
+// per tile (LDALL), hi.[Y_h | Y_l] as one N = 2 dk instruction (MERGE).  Measured on B200, gaussian row gradients at
+// N = M = 4e5, D = 64 / D = 16, ms per reduction (tools/ab_tc_route.py, profiles/r02_ab_tc_route.jsonl):
+//   "2,8,0,0" 130.2 / 109.5   "2,8,0,1" 118.0 / 91.0 (shipped)   "2,8,1,0" 130.7 / 110.0   "2,16,0,0" 137.1 / 116.3
+//   "2,16,0,1" 120.8 / 97.9   "1,8,0,0" 110.8 / 89.6             "1,8,0,1" 101.9 / 75.2    "1,16,0,1" 105.7 / 82.7
+// MERGE is accuracy-neutral (same products, same fp32 accumulation) and ships.  PT = 1 is another 14-17 % but feeds GEMM 2
+// an 11-bit image of P whose subnormal flush also reaches the row sums — kept as a knob, not the default.
+// $B200OT_TC_BWD ("p_terms,epi,ldall,merge") overrides the default for A/B timing and the variants' parity tests.
 struct TcBwdTuning {
   int p_terms, epi, ldall, merge;
 };
-static const TcBwdTuning kTcBwdDefault = {2, 8, 0, 0};
+static const TcBwdTuning kTcBwdDefault = {2, 8, 0, 1};
 static TcBwdTuning tc_bwd_tuning() {
   TcBwdTuning t = kTcBwdDefault;
   if (const char* e = getenv("B200OT_TC_BWD")) {

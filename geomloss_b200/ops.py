@@ -309,9 +309,12 @@ def kernel_conv_value_and_grad_rows(kind, x, y, w, blur, *, center=None):
 # A gaussian matvec whose ROW cloud requires a gradient is evaluated by the row-gradient reduction, which accumulates
 # sum_j w_j k_ij next to sum_j w_j k_ij y_j anyway: value and unit gradient come from one pass over the N x M pairs and
 # backward() is an N x D elementwise product — 3 reductions instead of 5 for SamplesLoss("gaussian")(x, y) + grad w.r.t.
-# x.  The price: a forward that is never differentiated pays the (slower) gradient reduction, and (N, D) floats are kept
-# until backward.  B200OT_FUSED_CONV_GRAD=0 restores the two-pass evaluation.
-FUSED_CONV_GRAD = _os.environ.get("B200OT_FUSED_CONV_GRAD", "0") == "1"
+# x.  Measured on B200 (tools/ab_tc_route.py part D: BASELINE configs[2], N = M = 1e6, D = 64, forward + gradient):
+# 2.64 s two-pass -> 1.92 s one-pass (1.72 s with the merged GEMM-2 instruction); N = M = 4e5, D = 3: 90 -> 53 ms per
+# (value, gradient) pair of reductions.  The price: a forward whose result is never differentiated although x requires a
+# gradient pays the (slower) gradient reduction, and (N, D) floats are kept until backward.
+# B200OT_FUSED_CONV_GRAD=0 restores the two-pass evaluation.
+FUSED_CONV_GRAD = _os.environ.get("B200OT_FUSED_CONV_GRAD", "1") == "1"
 
 
 class _KernelConv(torch.autograd.Function):
