@@ -21,8 +21,11 @@ WANT = {
     "rowsum_softmin_bwd_D3_big": r"rowsum_partial_kernel<b200ot::RowSumCfg<0, 3, 2, 256, 1024, 3, 2>, false>",
     "tc_reduce_conv": r"tc_reduce_kernel<b200ot::TcCfg<128, 16>, 0>",
     "tc_reduce_softmin": r"tc_reduce_kernel<b200ot::TcCfg<128, 16>, 1>",
-    "tc_bwd_conv": r"tc_bwd_kernel<b200ot::TcCfg<128, 8>, 2>",
-    "tc_bwd_softmin": r"tc_bwd_kernel<b200ot::TcCfg<128, 8>, 3>",
+    # <Cfg, MODE, PT, LDALL, MERGE>: the shipped instantiations (PT = 2, merged hi.[Y_h | Y_l] instruction) and, for
+    # comparison, the three-instruction GEMM 2 they replace
+    "tc_bwd_conv": r"tc_bwd_kernel<b200ot::TcCfg<128, 8>, 2, 2, false, true>",
+    "tc_bwd_softmin": r"tc_bwd_kernel<b200ot::TcCfg<128, 8>, 3, 2, false, true>",
+    "tc_bwd_conv_unmerged": r"tc_bwd_kernel<b200ot::TcCfg<128, 8>, 2, 2, false, false>",
     "grid_pass_p2": r"grid_pass_kernel<2, 32>",
     "sinkhorn_iteration_small_D3": r"sinkhorn_iteration_small_kernel<3, 2, 8>",
 }
