@@ -74,6 +74,57 @@ def test_argument_validation_needs_no_gpu(L):
     assert L.b200ot_softmin_merge(fake, 0, fake, 10, null) == -1
 
 
+def test_routing_below_nine_dimensions_shows_in_the_scratch_size(L, monkeypatch):
+    """D <= 8: large forward problems take the tensor-core path from D = 6 (softmin) / D = 5 (gaussian)
+    (csrc/b200ot_kernel_conv.cu: tc_routed); the size queries then cover both paths.  $B200OT_TC_MIN_D /
+    $B200OT_TC_MIN_PAIRS are read on every call.  (Observed on a small shape with the size threshold lifted: there the
+    tensor-core images are the larger of the two needs.)"""
+    def sizes():
+        return {d: (L.b200ot_softmin_scratch_bytes(1000, 1000, d), L.b200ot_kernel_conv_scratch_bytes(1000, 1000, d))
+                for d in range(1, 9)}
+
+    monkeypatch.delenv("B200OT_TC_MIN_D", raising=False)
+    monkeypatch.delenv("B200OT_TC_MIN_PAIRS", raising=False)
+    default = sizes()  # 1e6 pairs: below the 8e8-pair threshold, never routed
+    monkeypatch.setenv("B200OT_TC_MIN_D", "9")
+    assert sizes() == default
+    monkeypatch.setenv("B200OT_TC_MIN_PAIRS", "0")
+    cuda_core = sizes()
+    assert cuda_core == default
+    monkeypatch.delenv("B200OT_TC_MIN_D")
+    routed = sizes()  # default dimension thresholds, any size
+    for d in range(1, 5):
+        assert routed[d] == cuda_core[d], d  # no operator of these dimensions leaves the CUDA cores
+    for d in range(5, 9):
+        assert routed[d][0] > cuda_core[d][0] and routed[d][1] > cuda_core[d][1], d  # one size for all operators of a shape
+    monkeypatch.setenv("B200OT_TC_MIN_D", "6,9,5,9")  # the defaults, spelled out
+    assert sizes() == routed
+    monkeypatch.setenv("B200OT_TC_MIN_D", "1")
+    assert all(sizes()[d][0] > cuda_core[d][0] for d in range(1, 9))
+    monkeypatch.setenv("B200OT_TC_MIN_D", "7,9,9,9")  # only the forward softmin, only D >= 7
+    assert sizes()[6] == cuda_core[6] and sizes()[7][0] > cuda_core[7][0]
+    # a big problem is never sized below what either path needs; above B200OT_MAX_D nothing is configurable
+    monkeypatch.delenv("B200OT_TC_MIN_D")
+    monkeypatch.delenv("B200OT_TC_MIN_PAIRS")
+    n = 100_000
+    big = L.b200ot_softmin_scratch_bytes(n, n, 8)
+    monkeypatch.setenv("B200OT_TC_MIN_D", "9")
+    assert big >= L.b200ot_softmin_scratch_bytes(n, n, 8)
+    assert L.b200ot_softmin_scratch_bytes(n, n, 16) > 0 and L.b200ot_softmin_scratch_bytes(n, n, 65) == 0
+
+
+def test_one_pass_value_and_gradient_entry_validates_its_arguments(L):
+    null, fake = ctypes.c_void_p(None), ctypes.c_void_p(0x1000)
+    args = (10, 10, 3)
+    # gaussian only; out and grad_unit are both required
+    assert L.b200ot_kernel_conv_fwd_bwd_x(fake, fake, fake, null, fake, fake, *args, 1, 0.1, fake, 1 << 30, null) == -1
+    assert L.b200ot_kernel_conv_fwd_bwd_x(fake, fake, fake, null, null, fake, *args, 0, 0.1, fake, 1 << 30, null) == -1
+    assert L.b200ot_kernel_conv_fwd_bwd_x(fake, fake, fake, null, fake, null, *args, 0, 0.1, fake, 1 << 30, null) == -1
+    assert L.b200ot_kernel_conv_fwd_bwd_x(fake, fake, fake, null, fake, fake, *args, 0, 0.0, fake, 1 << 30, null) == -1
+    assert L.b200ot_kernel_conv_fwd_bwd_x(fake, fake, fake, null, fake, fake, *args, 0, 0.1, fake, 16, null) == -2
+    assert L.b200ot_kernel_conv_fwd_bwd_x(fake, fake, fake, null, fake, fake, 10, 10, 65, 0, 0.1, fake, 1 << 30, null) == -1
+
+
 def test_product_requires_cuda_tensors():
     """The host wrappers refuse CPU tensors instead of falling back to a CPU implementation."""
     import torch
