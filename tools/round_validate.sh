@@ -18,6 +18,7 @@ for tool in memcheck racecheck; do
   done
 done
 timeout 700 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"
+timeout 300 python tools/ab_tc_route.py > gpurun_out/ab_tc_route.jsonl 2>/dev/null
 timeout 300 python tools/bench_samplesloss.py 1000 5000 10000 100000 2>/dev/null | grep '^{' > gpurun_out/samplesloss.jsonl
 timeout 600 bash tools/profile.sh > gpurun_out/profile_sh.log 2>&1
 timeout 1200 bash tools/profile_aux.sh > gpurun_out/profile_aux.log 2>&1
