@@ -20,6 +20,13 @@
  *   - a reduction is split into two launches so that the column cloud can be packed once and
  *     reused (and so that partial results of column shards living on other GPUs can be merged):
  *         pack  ->  partial reduction  ->  finalize.
+ *
+ * Environment variables (read by the one-call entry points on every call; meant for A/B timing and for the parity tests
+ * that hold both settings of every switch to the oracle — a deployment leaves them unset):
+ *   B200OT_TC_MIN_D      "d" or "softmin_fwd,softmin_bwd,conv_fwd,conv_bwd": smallest D <= B200OT_MAX_D an operator
+ *                        hands to the tensor-core kernels (default "6,9,5,9": forward softmin from 6, gaussian from 5)
+ *   B200OT_TC_MIN_PAIRS  smallest N*M for that hand-over (default 8e8)
+ *   B200OT_TC_BWD        "p_terms,epilogue_warps,ldall,merge" of the tensor-core row-gradient kernel (default "2,8,0,1")
  */
 #ifndef B200OT_H_
 #define B200OT_H_
