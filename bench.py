@@ -582,6 +582,44 @@ def secondary_configs(torch, dev, world, rank, engine, peaks_file, mufu_peak):
                              "launch group per Sinkhorn iteration (csrc/b200ot_small.cu)")
         out["small_and_batched"] = small
 
+    if world == 1:
+        # ---- D = 6, 8: the forward operators of large problems run on the tensor-core kernels (the
+        #      CUDA-core rates they replace are in profiles/r02_ab_tc_route.jsonl).  Default routing, nothing forced; a
+        #      failure here drops this entry, not the bench line ----
+        try:
+            dims = {}
+            N = 400_000
+            for D in (6, 8):
+                g = torch.Generator().manual_seed(D)
+                x = torch.rand(N, D, generator=g).to(dev)
+                y = torch.rand(N, D, generator=g).to(dev)
+                h = (torch.rand(N, generator=g) * 0.1).to(dev)
+                w = (torch.rand(N, generator=g) / N).to(dev)
+                c = ops.default_center(x, y)
+                eps, blur = 1e-3, 0.15
+                t_s, f = _ev_time(torch, dev, lambda: ops.softmin_raw(eps, x, y, h, p=2, center=c)[0], reps=2)
+                t_c, kv = _ev_time(torch, dev, lambda: ops.kernel_conv_raw("gaussian", x, y, w, blur, center=c), reps=2)
+                rows = torch.randint(0, N, (64,), generator=g).to(dev)
+                xr, yd = x[rows].double(), y.double()
+                d2 = ((xr * xr).sum(1)[:, None] - 2 * xr @ yd.t() + (yd * yd).sum(1)[None, :]).clamp_min(0)
+                f_ref = -eps * torch.logsumexp(h.double()[None, :] - d2 / (2 * eps), dim=1)
+                k_ref = torch.exp(-d2 / (2 * blur * blur)) @ w.double()
+                dims[f"D{D}"] = {
+                    "softmin_fwd_ms": t_s * 1e3, "softmin_fwd_pairs_per_s": N * N / t_s, "sfu_frac_softmin": N * N / t_s / mufu_peak,
+                    "gaussian_fwd_ms": t_c * 1e3, "gaussian_fwd_pairs_per_s": N * N / t_c, "sfu_frac_gaussian": N * N / t_c / mufu_peak,
+                    "spot_parity": {"what": "64 sampled rows vs fp64 brute force",
+                                    "softmin_max_abs_err": float((f[rows].double() - f_ref).abs().max()),
+                                    "softmin_scale": float(f_ref.abs().max()),
+                                    "gaussian_max_rel_err": float(((kv[rows].double() - k_ref).abs() / k_ref.abs()).max())},
+                }
+                del x, y, h, w, d2, xr, yd
+            dims["workload"] = ("ops.softmin_raw(eps=1e-3, p=2) and ops.kernel_conv_raw('gaussian', blur=.15), N=M=4e5, uniform cube; "
+                                "tensor-core kernels on the zero-padded dk=16 problem (forward softmin from D=6, gaussian from D=5)")
+            out["forward_D6_D8"] = dims
+        except Exception as exc:  # pragma: no cover
+            out["forward_D6_D8"] = {"error": repr(exc)[:300]}
+        torch.cuda.empty_cache()
+
     # ---- configs[3]: multiscale Sinkhorn (eps-scaling .5, truncate 5): N=M=1e6 at every --gpus, 1e7 at --gpus 8 ----
     sizes = [1_000_000] + ([10_000_000] if world >= 8 else [])
     ms = {}
